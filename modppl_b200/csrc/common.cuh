@@ -1,0 +1,249 @@
+// common.cuh -- shared device helpers: error handling, Philox4x32-10, uniform/normal transforms, reductions.
+// sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string>
+
+namespace mpl {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (thread-local message behind mpl_last_error())
+// ------------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define MPL_CUDA_OK(expr)                                                                                     \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return ::mpl::fail(-2, std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                                       std::to_string(__LINE__));                                             \
+    } while (0)
+
+constexpr int kNumSMs = 148;   // B200
+constexpr double kPi = 3.14159265358979323846;
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10.  ctr = {id_lo, id_hi, t, purpose<<24 | block}, key = seed.  Replaces ThreadRng
+// (reference modppl/src/modeling/dists/distribution.rs:5-7): counter-based, so a draw depends only on
+// (seed, global id, step, purpose, block) and never on which GPU or thread computes it.
+// ------------------------------------------------------------------------------------------------
+enum Purpose : uint32_t { P_MODEL = 0, P_RESAMPLE_U = 1, P_RESAMPLE_OFFSET = 2, P_IS = 3, P_MH = 4, P_IS_RESAMPLE = 5, P_MH_INIT = 6 };
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+#else
+        uint64_t p0 = (uint64_t)0xD2511F53u * c.x, p1 = (uint64_t)0xCD9E8D57u * c.z;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+struct Stream {
+    uint2 key;
+    uint32_t id_lo, id_hi, t, purpose;
+    __host__ __device__ __forceinline__ Stream(uint64_t seed, uint64_t id, uint32_t t_, uint32_t purpose_)
+        : key(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32))), id_lo((uint32_t)id), id_hi((uint32_t)(id >> 32)), t(t_), purpose(purpose_) {}
+    __host__ __device__ __forceinline__ uint4 block(uint32_t blk) const {
+        return philox4x32_10(make_uint4(id_lo, id_hi, t, (purpose << 24) | blk), key);
+    }
+};
+
+__host__ __device__ __forceinline__ double u01_co64(uint32_t hi, uint32_t lo) { return (double)((((uint64_t)hi << 32) | lo) >> 11) * 0x1.0p-53; }        // [0,1)
+__host__ __device__ __forceinline__ double u01_oc64(uint32_t hi, uint32_t lo) { return (double)(((((uint64_t)hi << 32) | lo) >> 11) + 1) * 0x1.0p-53; }  // (0,1]
+__host__ __device__ __forceinline__ float u01_co32(uint32_t x) { return (float)(x >> 8) * 0x1.0p-24f; }
+__host__ __device__ __forceinline__ float u01_oc32(uint32_t x) { return (float)((x >> 8) + 1) * 0x1.0p-24f; }
+
+__device__ __forceinline__ void box_muller(float u1, float u2, float& z0, float& z1) {
+    float r = sqrtf(-2.f * logf(u1));
+    float s, c;
+    sincospif(2.f * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+__device__ __forceinline__ void box_muller(double u1, double u2, double& z0, double& z1) {
+    double r = sqrt(-2. * log(u1));
+    double s, c;
+    sincospi(2. * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// COUNT standard normals starting at Philox block `first_blk`.
+//   float : one block -> two Box-Muller pairs (z[4b..4b+3]);   double: one block -> one pair (z[2b], z[2b+1]).
+template <int COUNT>
+__device__ __forceinline__ void draw_normals(const Stream& s, uint32_t first_blk, float (&z)[COUNT]) {
+#pragma unroll
+    for (int i = 0; i < COUNT; i += 4) {
+        uint4 x = s.block(first_blk + i / 4);
+        float a, b;
+        box_muller(u01_oc32(x.x), u01_co32(x.y), a, b);
+        z[i] = a;
+        if (i + 1 < COUNT) z[i + 1] = b;
+        if (i + 2 < COUNT) {
+            box_muller(u01_oc32(x.z), u01_co32(x.w), a, b);
+            z[i + 2] = a;
+            if (i + 3 < COUNT) z[i + 3] = b;
+        }
+    }
+}
+template <int COUNT>
+__device__ __forceinline__ void draw_normals(const Stream& s, uint32_t first_blk, double (&z)[COUNT]) {
+#pragma unroll
+    for (int i = 0; i < COUNT; i += 2) {
+        uint4 x = s.block(first_blk + i / 2);
+        double a, b;
+        box_muller(u01_oc64(x.x, x.y), u01_co64(x.z, x.w), a, b);
+        z[i] = a;
+        if (i + 1 < COUNT) z[i + 1] = b;
+    }
+}
+template <int COUNT>
+__device__ __forceinline__ void draw_uniforms(const Stream& s, uint32_t first_blk, float (&u)[COUNT]) {
+#pragma unroll
+    for (int i = 0; i < COUNT; i += 4) {
+        uint4 x = s.block(first_blk + i / 4);
+        u[i] = u01_co32(x.x);
+        if (i + 1 < COUNT) u[i + 1] = u01_co32(x.y);
+        if (i + 2 < COUNT) u[i + 2] = u01_co32(x.z);
+        if (i + 3 < COUNT) u[i + 3] = u01_co32(x.w);
+    }
+}
+template <int COUNT>
+__device__ __forceinline__ void draw_uniforms(const Stream& s, uint32_t first_blk, double (&u)[COUNT]) {
+#pragma unroll
+    for (int i = 0; i < COUNT; i += 2) {
+        uint4 x = s.block(first_blk + i / 2);
+        u[i] = u01_co64(x.x, x.y);
+        if (i + 1 < COUNT) u[i + 1] = u01_co64(x.z, x.w);
+    }
+}
+
+// fp64 draw helper for the IS / MH paths: every draw consumes one whole Philox block.
+struct Rng64 {
+    Stream s;
+    uint32_t blk;
+    __device__ __forceinline__ Rng64(uint64_t seed, uint64_t id, uint32_t t, uint32_t purpose) : s(seed, id, t, purpose), blk(0) {}
+    __device__ __forceinline__ double uniform() { uint4 x = s.block(blk++); return u01_co64(x.x, x.y); }
+    __device__ __forceinline__ void uniform2(double& a, double& b) { uint4 x = s.block(blk++); a = u01_co64(x.x, x.y); b = u01_co64(x.z, x.w); }
+    __device__ __forceinline__ void normal2(double& a, double& b) { uint4 x = s.block(blk++); box_muller(u01_oc64(x.x, x.y), u01_co64(x.z, x.w), a, b); }
+    __device__ __forceinline__ double normal() { double a, b; normal2(a, b); return a; }
+    __device__ __forceinline__ void skip(uint32_t n) { blk += n; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// built-in log-densities (reference modppl/src/modeling/dists/*.rs), generic over Real
+// ------------------------------------------------------------------------------------------------
+template <typename Real>
+__host__ __device__ __forceinline__ Real normal_logpdf(Real x, Real mu, Real sd) {
+    // normal.rs:13-17   -(|z|^2 + ln 2pi)/2 - ln std
+    Real z = (x - mu) / sd;
+    return -(z * z + (Real)1.8378770664093453) / 2 - log(sd);
+}
+__host__ __device__ __forceinline__ double bernoulli_logpdf(bool a, double p) { return log(a ? p : 1. - p); }   // bernoulli.rs:12-14
+__host__ __device__ __forceinline__ double uniform_logpdf(double x, double a, double b) {                        // uniform.rs:22-26
+    return (a <= x && x <= b) ? -log(b - a) : -INFINITY;
+}
+__host__ __device__ __forceinline__ double uniform2d_logpdf(double x, double y, const double* bd) {              // tests/pointed_model/types_2d.rs:15-21
+    return (bd[0] <= x && x <= bd[1] && bd[2] <= y && y <= bd[3]) ? -log((bd[1] - bd[0]) * (bd[3] - bd[2])) : -INFINITY;
+}
+// mvnormal.rs:14-22 for k = 2, with det and inverse hoisted to the host once per model (quirk Q8):
+// prec = {inv00, inv01, inv10, inv11}, log_norm = k ln 2pi + ln det
+__host__ __device__ __forceinline__ double mvnormal2_logpdf(double x0, double x1, double m0, double m1, const double* prec, double log_norm) {
+    double c0 = x0 - m0, c1 = x1 - m1;
+    double t0 = c0 * prec[0] + c1 * prec[2], t1 = c0 * prec[1] + c1 * prec[3];
+    return -(log_norm + (t0 * c0 + t1 * c1)) / 2.;
+}
+
+// ------------------------------------------------------------------------------------------------
+// online log-sum-exp triple: (m, s, s2) represents sum exp(x) = s*exp(m), sum exp(2x) = s2*exp(2m)
+// ------------------------------------------------------------------------------------------------
+template <typename Acc>
+struct Lse3 {
+    Acc m, s, s2;
+};
+template <typename Acc>
+__host__ __device__ __forceinline__ Lse3<Acc> lse3_identity() { return Lse3<Acc>{(Acc)-INFINITY, (Acc)0, (Acc)0}; }
+template <typename Acc>
+__device__ __forceinline__ Lse3<Acc> lse3_combine(const Lse3<Acc>& a, const Lse3<Acc>& b) {
+    Acc m = fmax(a.m, b.m);   // fmax ignores NaN like f64::max (lib.rs:35)
+    if (m == (Acc)-INFINITY) return Lse3<Acc>{m, (Acc)0, (Acc)0};
+    Acc ea = exp(a.m - m), eb = exp(b.m - m);
+    return Lse3<Acc>{m, a.s * ea + b.s * eb, a.s2 * ea * ea + b.s2 * eb * eb};
+}
+template <typename Acc>
+__device__ __forceinline__ Lse3<Acc> lse3_shfl_xor(const Lse3<Acc>& v, int lane_mask) {
+    return Lse3<Acc>{__shfl_xor_sync(0xffffffffu, v.m, lane_mask), __shfl_xor_sync(0xffffffffu, v.s, lane_mask), __shfl_xor_sync(0xffffffffu, v.s2, lane_mask)};
+}
+template <typename Acc>
+__device__ __forceinline__ Lse3<Acc> lse3_warp_reduce(Lse3<Acc> v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = lse3_combine(v, lse3_shfl_xor(v, o));
+    return v;
+}
+
+// order-preserving float <-> uint mapping for atomicMax on floats
+__host__ __device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(f);
+#else
+    memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ordered_to_float(uint32_t u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// fixed-point weights: q = rint(exp(d) * 2^kbits), built only from correctly-rounded IEEE operations so that a
+// CPU restatement reproduces it bit for bit (oracle/modppl_oracle.cpp: mo_fixed_weight).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float exp2_poly(float f) {
+    float p = 1.5252733804059841e-05f;
+    p = __fmaf_rn(p, f, 0.00015403530393381608f);
+    p = __fmaf_rn(p, f, 0.0013333558146428443f);
+    p = __fmaf_rn(p, f, 0.009618129107628477f);
+    p = __fmaf_rn(p, f, 0.05550410866482158f);
+    p = __fmaf_rn(p, f, 0.2402265069591007f);
+    p = __fmaf_rn(p, f, 0.6931471805599453f);
+    p = __fmaf_rn(p, f, 1.0f);
+    return p;
+}
+__device__ __forceinline__ uint64_t fixed_weight(float d, int kbits) {
+    if (!(d > -88.0f)) return 0;   // also NaN / -inf
+    d = fminf(d, 0.f);
+    float y = __fmul_rn(d, 1.44269504088896341f);
+    float n = rintf(y);
+    float f = __fsub_rn(y, n);
+    float p = exp2_poly(f);
+    int shift = kbits + (int)n;
+    if (shift < -2) return 0;
+    // p * 2^shift, exactly, then round-half-even to integer
+    double v = (double)p * __longlong_as_double((long long)(1023 + shift) << 52);
+    return (uint64_t)__double2ull_rn(v);
+}
+inline int fixed_kbits(uint64_t n_total) {
+    int lg = 0;
+    while (((uint64_t)1 << lg) < n_total) ++lg;
+    int k = 62 - lg;
+    return k > 40 ? 40 : k;
+}
+
+}  // namespace mpl

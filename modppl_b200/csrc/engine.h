@@ -1,0 +1,62 @@
+// engine.h -- host-side objects behind the opaque handles of include/modppl_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/modppl_b200.h"
+#include "pf_kernels.cuh"
+
+struct mpl_model {
+    int kind;
+    std::string name;
+    std::vector<double> params;
+    int state_dim, obs_dim, num_latents;
+};
+
+namespace mpl {
+
+struct KernelTimer {
+    double total_ms = 0.;
+    uint64_t launches = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+int model_from_name(const std::string& name);
+
+}  // namespace mpl
+
+struct mpl_ps {
+    const mpl_model* model_ref;
+    mpl_model model;   // copy
+    int dtype, device;
+    size_t n, ld;
+    uint64_t seed, gid_offset, n_global;
+    int D;
+    cudaStream_t stream;
+    void* state[2];   // D x ld Real
+    int cur;          // index of the live state buffer
+    void* lw;         // ld Real
+    int32_t* anc;     // ld
+    double* probs;    // ld (exact schemes), lazily allocated
+    double* cums;     // ld
+    unsigned long long* icum;   // ld (integer multinomial)
+    unsigned long long* desc;   // scan tile descriptors
+    mpl::OverflowEntry* overflow;
+    size_t overflow_cap;
+    mpl::DeviceStats* stats;    // device
+    mpl::DeviceStats* stats_host;   // pinned
+    mpl::Lse3<double>* partials;
+    unsigned long long* ipartials;
+    double* obs_dev;
+    size_t obs_steps;
+    double* staging;   // ld*max(D,1) doubles for read/write conversions
+    int grid_extend, grid_reduce;
+    long long t;       // next kernel time index (host mirror)
+    bool initialised, pending_gather, stats_valid;
+    bool profile;
+    std::map<std::string, mpl::KernelTimer> timers;
+    uint64_t launch_count;
+    // multi-GPU
+    int rank, world;
+};

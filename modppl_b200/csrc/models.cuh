@@ -1,0 +1,124 @@
+// models.cuh -- device functors: the "restricted vectorisable form" of modppl's Unfold kernels.
+//
+// A functor mirrors DynUnfold::generate / update(Extend) (reference modppl/src/modeling/dynunfold.rs:41-100) for one
+// particle: `kernel(t, stream, x, obs)` sees t = 0 at init_step and t = k at the k-th step (quirk Q5), mutates the
+// fixed-shape state x in place (state = last retv, dynunfold.rs:76) and returns the weight = sum of the constrained
+// choices' log-densities (Generate-mode semantics, dyngenfn.rs:121-136).
+#pragma once
+#include "common.cuh"
+
+namespace mpl {
+
+struct Obs {
+    double v[4];
+};
+
+enum ModelKind : int { M_LGSSM4 = 0, M_SPIRAL = 1, M_SV = 2, M_HMM = 3, M_LINE = 10, M_HIER = 11, M_POINTED = 12 };
+
+// ---- config 4: 4-D constant-velocity linear-Gaussian tracker, two independent `normal` observations -----------
+template <typename Real>
+struct Lgssm4 {
+    static constexpr int D = 4;
+    static constexpr int NOBS = 2;
+    Real q, r, x0, ln_r;
+    __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
+        Real z[4];
+        draw_normals<4>(s, 0, z);
+        if (t == 0) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) x[d] = z[d] * x0;
+        } else {
+            x[0] = x[0] + x[2] + z[0] * q;
+            x[1] = x[1] + x[3] + z[1] * q;
+            x[2] = x[2] + z[2] * q;
+            x[3] = x[3] + z[3] * q;
+        }
+        Real lw = 0;
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            Real zz = ((Real)obs.v[d] - x[d]) / r;
+            lw += -(zz * zz + (Real)1.8378770664093453) / 2 - ln_r;   // normal.rs:13-17
+        }
+        return lw;
+    }
+};
+
+// ---- config 1: spiral model, reference tests/dyngenfns/unfold.rs:14-33 ------------------------------------------
+template <typename Real>
+struct Spiral {
+    static constexpr int D = 2;
+    static constexpr int NOBS = 2;
+    Real dr_std, dth_mean, dth_std;
+    double prec[4], log_norm;   // mvnormal.rs:14-22 with det/inverse hoisted (quirk Q8)
+    Real inv_var, log_norm_r;
+    __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
+        if (t == 0) {
+            Real u[2];
+            draw_uniforms<2>(s, 0, u);
+            x[0] = u[0] * (Real)(1. - 0.) + (Real)0.;                     // uniform.rs:28-32
+            x[1] = u[1] * (Real)(2. * kPi - 0.) + (Real)0.;
+        } else {
+            Real z[2];
+            draw_normals<2>(s, 0, z);
+            x[0] = x[0] + (z[0] * dr_std + (Real)0.);                     // normal.rs:26
+            x[1] = x[1] + (z[1] * dth_std + dth_mean);
+        }
+        if (sizeof(Real) == 8) {
+            double sn, cs;
+            sincos((double)x[1], &sn, &cs);
+            return (Real)mvnormal2_logpdf(obs.v[0], obs.v[1], (double)x[0] * cs, (double)x[0] * sn, prec, log_norm);
+        } else {
+            float sn, cs;
+            sincosf((float)x[1], &sn, &cs);
+            Real c0 = (Real)obs.v[0] - x[0] * (Real)cs, c1 = (Real)obs.v[1] - x[0] * (Real)sn;
+            Real mahal = c0 * c0 * inv_var + c1 * c1 * inv_var;
+            return -(log_norm_r + mahal) / 2;
+        }
+    }
+};
+
+// ---- config 5: stochastic volatility -------------------------------------------------------------------------------
+template <typename Real>
+struct StochVol {
+    static constexpr int D = 1;
+    static constexpr int NOBS = 1;
+    Real mu, phi, sig, sd0;
+    __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
+        Real z[1];
+        draw_normals<1>(s, 0, z);
+        if (t == 0) x[0] = mu + sd0 * z[0];
+        else x[0] = mu + phi * (x[0] - mu) + sig * z[0];
+        Real sd = exp(x[0] / 2);
+        Real zz = (Real)obs.v[0] / sd;
+        return -(zz * zz + (Real)1.8378770664093453) / 2 - x[0] / 2;
+    }
+};
+
+// ---- K-state HMM, reference tests/hmm/model.rs:24-81 --------------------------------------------------------------
+constexpr int kHmmMaxK = 8;
+template <typename Real>
+struct Hmm {
+    static constexpr int D = 1;
+    static constexpr int NOBS = 1;
+    int K, M;
+    double prior[kHmmMaxK], log_emis[kHmmMaxK * kHmmMaxK], trans[kHmmMaxK * kHmmMaxK];   // log_emis[o*K+s], trans[to*K+from]
+    __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
+        double u[1];
+        draw_uniforms<1>(s, 0, u);
+        int prev = (t == 0) ? 0 : (int)x[0];
+        // categorical.rs:22-32: x = first index whose running sum reaches u, clamped (quirk Q2)
+        double acc = 0.;
+        int st = -1;
+        for (int k = 0; k < K; ++k) {
+            if (!(acc < u[0])) break;
+            acc += (t == 0) ? prior[k] : trans[k * K + prev];
+            st = k;
+        }
+        st = st < 0 ? 0 : st;
+        x[0] = (Real)st;
+        int o = (int)obs.v[0];
+        return (Real)log_emis[o * K + st];
+    }
+};
+
+}  // namespace mpl

@@ -1,0 +1,751 @@
+// pf.cu -- ParticleSystem host driver + C ABI (reference modppl/src/inference/particle_filter.rs:8-121).
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include "engine.h"
+
+namespace mpl {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+
+int model_from_name(const std::string& name) {
+    if (name == "lgssm4") return M_LGSSM4;
+    if (name == "spiral") return M_SPIRAL;
+    if (name == "sv") return M_SV;
+    if (name == "hmm") return M_HMM;
+    if (name == "line") return M_LINE;
+    if (name == "hierarchical") return M_HIER;
+    if (name == "pointed") return M_POINTED;
+    return -1;
+}
+
+// ---- device functor construction from the parameter vector ---------------------------------------------
+template <typename Real> Lgssm4<Real> make_lgssm4(const mpl_model& m) {
+    const auto& p = m.params;
+    Lgssm4<Real> f;
+    f.q = (Real)(p.size() > 0 ? p[0] : 0.1);
+    f.r = (Real)(p.size() > 1 ? p[1] : 0.5);
+    f.x0 = (Real)(p.size() > 2 ? p[2] : 1.0);
+    f.ln_r = (Real)std::log((double)f.r);
+    return f;
+}
+template <typename Real> Spiral<Real> make_spiral(const mpl_model& m) {
+    const auto& p = m.params;
+    Spiral<Real> f;
+    double dr = p.size() > 0 ? p[0] : 0.1, dm = p.size() > 1 ? p[1] : 0.4, ds = p.size() > 2 ? p[2] : 0.2, ov = p.size() > 3 ? p[3] : 0.001;
+    f.dr_std = (Real)dr; f.dth_mean = (Real)dm; f.dth_std = (Real)ds;
+    // nalgebra 2x2 closed forms (mvnormal.rs:17-18), hoisted
+    double det = ov * ov - 0. * 0.;
+    f.prec[0] = ov / det; f.prec[1] = -0. / det; f.prec[2] = -0. / det; f.prec[3] = ov / det;
+    f.log_norm = 2. * std::log(2. * kPi) + std::log(det);
+    f.inv_var = (Real)(1. / ov);
+    f.log_norm_r = (Real)(2. * std::log(2. * kPi) + std::log(ov * ov));
+    return f;
+}
+template <typename Real> StochVol<Real> make_sv(const mpl_model& m) {
+    const auto& p = m.params;
+    StochVol<Real> f;
+    f.mu = (Real)(p.size() > 0 ? p[0] : -1.024);
+    f.phi = (Real)(p.size() > 1 ? p[1] : 0.9702);
+    f.sig = (Real)(p.size() > 2 ? p[2] : 0.178);
+    f.sd0 = f.sig / std::sqrt(1 - f.phi * f.phi);
+    return f;
+}
+template <typename Real> Hmm<Real> make_hmm(const mpl_model& m) {
+    const auto& p = m.params;
+    Hmm<Real> f;
+    std::memset(&f, 0, sizeof f);
+    f.K = (int)p[0]; f.M = (int)p[1];
+    for (int k = 0; k < f.K; ++k) f.prior[k] = p[2 + k];
+    for (int i = 0; i < f.M * f.K; ++i) f.log_emis[i] = std::log(p[2 + f.K + i]);
+    for (int i = 0; i < f.K * f.K; ++i) f.trans[i] = p[2 + f.K + f.M * f.K + i];
+    return f;
+}
+
+// ---- launch bookkeeping ----------------------------------------------------------------------------------
+struct ScopedLaunch {
+    mpl_ps* ps; const char* name; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ScopedLaunch(mpl_ps* p, const char* n) : ps(p), name(n) {
+        ps->launch_count++;
+        if (ps->profile) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ps->stream); }
+    }
+    ~ScopedLaunch() {
+        if (ps->profile) { cudaEventRecord(e1, ps->stream); ps->timers[name].pending.push_back({e0, e1}); }
+    }
+};
+
+static int flush_timers(mpl_ps* ps) {
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    for (auto& kv : ps->timers) {
+        for (auto& pr : kv.second.pending) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pr.first, pr.second);
+            kv.second.total_ms += ms; kv.second.launches++;
+            cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+        }
+        kv.second.pending.clear();
+    }
+    return MPL_OK;
+}
+
+static size_t elem_size(const mpl_ps* ps) { return ps->dtype == MPL_F64 ? 8 : 4; }
+
+static int grid_for(size_t work_items, int per_block, int max_blocks) {
+    size_t b = (work_items + per_block - 1) / per_block;
+    if (b < 1) b = 1;
+    if (b > (size_t)max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+// ---- extend dispatch ----------------------------------------------------------------------------------------
+template <class Model, typename Real>
+static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& obs, bool from_dev_obs, bool dev_t) {
+    ExtendArgs<Real> a;
+    a.state_in = (const Real*)ps->state[ps->cur];
+    a.state_out = (Real*)ps->state[mode == EXT_INIT || mode == EXT_ACCUM ? ps->cur : ps->cur ^ 1];
+    a.lw = (Real*)ps->lw;
+    a.anc = ps->anc;
+    a.n = ps->n; a.ld = ps->ld;
+    a.seed = ps->seed; a.gid_offset = ps->gid_offset;
+    a.t = dev_t ? -1 : ps->t;
+    a.obs = obs;
+    a.obs_dev = from_dev_obs ? ps->obs_dev : nullptr;
+    a.nobs = ps->model.obs_dim;
+    a.stats = ps->stats;
+    a.partials = ps->partials;
+    if (mode == EXT_DYNAMIC) a.state_out = (Real*)ps->state[ps->cur ^ 1];
+    const int grid = ps->grid_extend;
+    {
+        ScopedLaunch sl(ps, mode == EXT_INIT ? "init" : "extend");
+        switch (mode) {
+            case EXT_INIT: pf_extend_kernel<Model, Real, EXT_INIT><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
+            case EXT_ACCUM: pf_extend_kernel<Model, Real, EXT_ACCUM><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
+            case EXT_GATHER: pf_extend_kernel<Model, Real, EXT_GATHER><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
+            default: pf_extend_kernel<Model, Real, EXT_DYNAMIC><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
+        }
+    }
+    MPL_CUDA_OK(cudaGetLastError());
+    if (mode == EXT_GATHER || mode == EXT_DYNAMIC) ps->cur ^= 1;
+    return MPL_OK;
+}
+
+static int launch_extend(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs, bool dev_t) {
+    const mpl_model& m = ps->model;
+    if (ps->dtype == MPL_F32) {
+        switch (m.kind) {
+            case M_LGSSM4: return launch_extend_t<Lgssm4<float>, float>(ps, make_lgssm4<float>(m), mode, obs, from_dev_obs, dev_t);
+            case M_SPIRAL: return launch_extend_t<Spiral<float>, float>(ps, make_spiral<float>(m), mode, obs, from_dev_obs, dev_t);
+            case M_SV: return launch_extend_t<StochVol<float>, float>(ps, make_sv<float>(m), mode, obs, from_dev_obs, dev_t);
+            case M_HMM: return launch_extend_t<Hmm<float>, float>(ps, make_hmm<float>(m), mode, obs, from_dev_obs, dev_t);
+        }
+    } else {
+        switch (m.kind) {
+            case M_LGSSM4: return launch_extend_t<Lgssm4<double>, double>(ps, make_lgssm4<double>(m), mode, obs, from_dev_obs, dev_t);
+            case M_SPIRAL: return launch_extend_t<Spiral<double>, double>(ps, make_spiral<double>(m), mode, obs, from_dev_obs, dev_t);
+            case M_SV: return launch_extend_t<StochVol<double>, double>(ps, make_sv<double>(m), mode, obs, from_dev_obs, dev_t);
+            case M_HMM: return launch_extend_t<Hmm<double>, double>(ps, make_hmm<double>(m), mode, obs, from_dev_obs, dev_t);
+        }
+    }
+    return fail(MPL_ERR_INVALID, "model is not an Unfold model");
+}
+
+static int ensure_stats(mpl_ps* ps) {
+    if (ps->stats_valid) return MPL_OK;
+    {
+        ScopedLaunch sl(ps, "weight_reduce");
+        if (ps->dtype == MPL_F32) weight_reduce_kernel<float><<<ps->grid_reduce, 256, 0, ps->stream>>>((const float*)ps->lw, ps->n, ps->stats, ps->partials);
+        else weight_reduce_kernel<double><<<ps->grid_reduce, 256, 0, ps->stream>>>((const double*)ps->lw, ps->n, ps->stats, ps->partials);
+    }
+    MPL_CUDA_OK(cudaGetLastError());
+    ps->stats_valid = true;
+    return MPL_OK;
+}
+
+static int fetch_stats(mpl_ps* ps) {
+    MPL_CUDA_OK(cudaMemcpyAsync(ps->stats_host, ps->stats, sizeof(DeviceStats), cudaMemcpyDeviceToHost, ps->stream));
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    return MPL_OK;
+}
+
+// materialise a pending ancestor gather (only needed when the host looks at / overwrites state between resample and step)
+static int materialise(mpl_ps* ps) {
+    if (!ps->pending_gather) return MPL_OK;
+    const int grid = grid_for(ps->n, 256, kNumSMs * 8);
+    {
+        ScopedLaunch sl(ps, "gather");
+        if (ps->dtype == MPL_F32) {
+            gather_kernel<float><<<grid, 256, 0, ps->stream>>>((const float*)ps->state[ps->cur], (float*)ps->state[ps->cur ^ 1], ps->anc, ps->n, ps->ld, ps->D);
+            fill_kernel<float><<<grid, 256, 0, ps->stream>>>((float*)ps->lw, ps->n, 0.f);
+        } else {
+            gather_kernel<double><<<grid, 256, 0, ps->stream>>>((const double*)ps->state[ps->cur], (double*)ps->state[ps->cur ^ 1], ps->anc, ps->n, ps->ld, ps->D);
+            fill_kernel<double><<<grid, 256, 0, ps->stream>>>((double*)ps->lw, ps->n, 0.);
+        }
+    }
+    ps->launch_count++;
+    MPL_CUDA_OK(cudaGetLastError());
+    ps->cur ^= 1;
+    ps->pending_gather = false;
+    ps->stats_valid = false;
+    return MPL_OK;
+}
+
+template <typename Real>
+static FixedArgs<Real> fixed_args(mpl_ps* ps, bool dynamic, bool dev_t) {
+    FixedArgs<Real> a;
+    a.lw = (const Real*)ps->lw;
+    a.n = ps->n;
+    a.kbits = fixed_kbits(ps->n_global);
+    a.n_out = ps->n_global;
+    a.c_offset = 0;
+    a.out_base = ps->gid_offset;
+    a.n_out_local = ps->n;
+    a.log_n_global = std::log((double)ps->n_global);
+    a.anc = ps->anc;
+    a.src_base = 0;
+    a.desc = ps->desc;
+    a.overflow = ps->overflow;
+    a.stats = ps->stats;
+    a.partials = ps->ipartials;
+    a.seed = ps->seed;
+    a.rt = dev_t ? -1 : ps->t - 1;
+    a.accumulate_lml = 1;
+    a.dynamic = dynamic ? 1 : 0;
+    return a;
+}
+
+template <typename Real>
+static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
+    FixedArgs<Real> a = fixed_args<Real>(ps, dynamic, dev_t);
+    const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
+    {
+        ScopedLaunch sl(ps, "fixed_reduce");
+        fixed_reduce_kernel<Real><<<ps->grid_reduce, 256, 0, ps->stream>>>(a, num_tiles);
+    }
+    MPL_CUDA_OK(cudaGetLastError());
+    if (scheme == MPL_RESAMPLE_SYSTEMATIC_FIXED) {
+        {
+            ScopedLaunch sl(ps, "fixed_scan");
+            fixed_scan_kernel<Real><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
+        }
+        MPL_CUDA_OK(cudaGetLastError());
+        {
+            ScopedLaunch sl(ps, "fixed_overflow");
+            fixed_overflow_kernel<Real><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a);
+        }
+        MPL_CUDA_OK(cudaGetLastError());
+    } else {
+        if (!ps->icum) MPL_CUDA_OK(cudaMalloc(&ps->icum, ps->ld * sizeof(unsigned long long)));
+        {
+            ScopedLaunch sl(ps, "fixed_cumsum");
+            fixed_cumsum_kernel<Real><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, ps->icum);
+        }
+        MPL_CUDA_OK(cudaGetLastError());
+        {
+            ScopedLaunch sl(ps, "fixed_search");
+            fixed_multinomial_search_kernel<<<grid_for(ps->n, 256, kNumSMs * 16), 256, 0, ps->stream>>>(ps->icum, ps->n, ps->n, ps->stats, ps->seed, ps->gid_offset,
+                                                                                                      (uint32_t)(ps->t - 1), ps->anc);
+        }
+        MPL_CUDA_OK(cudaGetLastError());
+    }
+    return MPL_OK;
+}
+
+static int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream);
+
+static int resample_exact(mpl_ps* ps, int scheme) {
+    if (!ps->probs) {
+        MPL_CUDA_OK(cudaMalloc(&ps->probs, ps->ld * sizeof(double)));
+        MPL_CUDA_OK(cudaMalloc(&ps->cums, ps->ld * sizeof(double)));
+    }
+    const int grid = grid_for(ps->n, 256, kNumSMs * 8);
+    {
+        ScopedLaunch sl(ps, "normalize");
+        if (ps->dtype == MPL_F32) normalize_kernel<float><<<grid, 256, 0, ps->stream>>>((const float*)ps->lw, ps->n, ps->probs, ps->stats, std::log((double)ps->n_global), 1);
+        else normalize_kernel<double><<<grid, 256, 0, ps->stream>>>((const double*)ps->lw, ps->n, ps->probs, ps->stats, std::log((double)ps->n_global), 1);
+    }
+    MPL_CUDA_OK(cudaGetLastError());
+    int rc = launch_cumsum_exact(ps, ps->probs, ps->n, ps->cums, ps->stream);
+    if (rc) return rc;
+    {
+        ScopedLaunch sl(ps, "search");
+        search_kernel<int32_t><<<grid, 256, 0, ps->stream>>>(ps->cums, ps->n, ps->n, scheme == MPL_RESAMPLE_MULTINOMIAL ? 2 : 3, nullptr, ps->seed, ps->gid_offset,
+                                                             (uint32_t)(ps->t - 1), ps->anc);
+    }
+    MPL_CUDA_OK(cudaGetLastError());
+    return MPL_OK;
+}
+
+static int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream) {
+    if (ps) ps->launch_count++;
+    cumsum_seq_kernel<<<1, 256, 0, stream>>>(probs, n, out);
+    MPL_CUDA_OK(cudaGetLastError());
+    return MPL_OK;
+}
+
+static int do_resample(mpl_ps* ps, int scheme) {
+    if (!ps->initialised) return fail(MPL_ERR_INVALID, "resample before init_step");
+    if (ps->world > 1 && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED) return fail(MPL_ERR_UNSUPPORTED, "sharded particle systems support MPL_RESAMPLE_SYSTEMATIC_FIXED only");
+    int rc = materialise(ps);   // resample twice in a row: apply the first one
+    if (rc) return rc;
+    rc = ensure_stats(ps);
+    if (rc) return rc;
+    switch (scheme) {
+        case MPL_RESAMPLE_MULTINOMIAL:
+        case MPL_RESAMPLE_SYSTEMATIC: rc = resample_exact(ps, scheme); break;
+        case MPL_RESAMPLE_SYSTEMATIC_FIXED:
+        case MPL_RESAMPLE_MULTINOMIAL_FIXED:
+            rc = ps->dtype == MPL_F32 ? resample_fixed_t<float>(ps, scheme, false, false) : resample_fixed_t<double>(ps, scheme, false, false);
+            break;
+        default: return fail(MPL_ERR_INVALID, "unknown resampling scheme");
+    }
+    if (rc) return rc;
+    ps->pending_gather = true;
+    ps->stats_valid = false;
+    return MPL_OK;
+}
+
+}  // namespace mpl
+
+using namespace mpl;
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" const char* mpl_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* mpl_version(void) { return "modppl_b200 0.1 (sm_100a)"; }
+extern "C" int mpl_device_count(int* count) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; return fail(MPL_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *count = c;
+    return MPL_OK;
+}
+
+extern "C" mpl_model* mpl_model_create(const char* name, const double* params, size_t n_params) {
+    if (!name) { fail(MPL_ERR_INVALID, "null model name"); return nullptr; }
+    int kind = model_from_name(name);
+    if (kind < 0) { fail(MPL_ERR_INVALID, std::string("unknown model: ") + name); return nullptr; }
+    auto* m = new mpl_model;
+    m->kind = kind; m->name = name;
+    if (params && n_params) m->params.assign(params, params + n_params);
+    m->num_latents = 0;
+    switch (kind) {
+        case M_LGSSM4: m->state_dim = 4; m->obs_dim = 2; break;
+        case M_SPIRAL: m->state_dim = 2; m->obs_dim = 2; break;
+        case M_SV: m->state_dim = 1; m->obs_dim = 1; break;
+        case M_HMM: {
+            m->state_dim = 1; m->obs_dim = 1;
+            bool ok = n_params >= 2;
+            int K = ok ? (int)params[0] : 0, M = ok ? (int)params[1] : 0;
+            ok = ok && K >= 1 && K <= kHmmMaxK && M >= 1 && M <= kHmmMaxK && n_params == (size_t)(2 + K + M * K + K * K);
+            if (!ok) { delete m; fail(MPL_ERR_INVALID, "hmm params: {K, M, prior[K], emission[M*K], transition[K*K]} with K, M <= 8"); return nullptr; }
+            break;
+        }
+        case M_LINE: m->state_dim = 0; m->obs_dim = (int)n_params; m->num_latents = 2; break;
+        case M_HIER: m->state_dim = 0; m->obs_dim = (int)n_params; m->num_latents = 4; break;
+        case M_POINTED:
+            m->state_dim = 0; m->obs_dim = 2; m->num_latents = 2;
+            if (n_params != 8) { delete m; fail(MPL_ERR_INVALID, "pointed params: {xmin,xmax,ymin,ymax, cov[4]}"); return nullptr; }
+            if (!(params[1] > params[0]) || !(params[3] > params[2])) { delete m; fail(MPL_ERR_INVALID, "pointed bounds: max must exceed min (types_2d.rs:24-25)"); return nullptr; }
+            break;
+    }
+    return m;
+}
+extern "C" void mpl_model_destroy(mpl_model* m) { delete m; }
+extern "C" int mpl_model_state_dim(const mpl_model* m) { return m ? m->state_dim : MPL_ERR_INVALID; }
+extern "C" int mpl_model_obs_dim(const mpl_model* m) { return m ? m->obs_dim : MPL_ERR_INVALID; }
+extern "C" int mpl_model_num_latents(const mpl_model* m) { return m ? m->num_latents : MPL_ERR_INVALID; }
+
+extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_particles, const mpl_pf_config* cfg) {
+    if (!model || model->state_dim <= 0) { fail(MPL_ERR_INVALID, "particle system needs an Unfold model"); return nullptr; }
+    if (num_particles == 0 || num_particles > (1ull << 31)) { fail(MPL_ERR_INVALID, "num_particles must be in [1, 2^31]"); return nullptr; }
+    mpl_pf_config c;
+    if (cfg) c = *cfg; else { c.dtype = MPL_F64; c.device = -1; c.seed = 0; c.gid_offset = 0; c.n_global = 0; }
+    if (c.dtype != MPL_F32 && c.dtype != MPL_F64) { fail(MPL_ERR_INVALID, "dtype"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); fail(MPL_ERR_CUDA, "no CUDA device: modppl_b200 has no CPU fallback"); return nullptr; }
+    if (c.device >= 0) { if (cudaSetDevice(c.device) != cudaSuccess) { fail(MPL_ERR_CUDA, "cudaSetDevice failed"); return nullptr; } }
+    auto* ps = new mpl_ps();
+    ps->model_ref = model; ps->model = *model;
+    ps->dtype = c.dtype;
+    cudaGetDevice(&ps->device);
+    ps->n = num_particles;
+    ps->ld = (num_particles + kScanTile - 1) / kScanTile * kScanTile;
+    ps->seed = c.seed; ps->gid_offset = c.gid_offset; ps->n_global = c.n_global ? c.n_global : num_particles;
+    ps->D = model->state_dim;
+    ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false;
+    ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1;
+    ps->probs = nullptr; ps->cums = nullptr; ps->icum = nullptr; ps->obs_dev = nullptr; ps->obs_steps = 0; ps->staging = nullptr;
+    const size_t es = elem_size(ps);
+    const size_t num_tiles = ps->ld / kScanTile;
+    ps->overflow_cap = ps->n_global / kHeavyCap + 4;
+    const int V = ps->dtype == MPL_F32 ? 4 : 2;
+    ps->grid_extend = grid_for(ps->n, kExtendThreads * V, kNumSMs * 8);
+    ps->grid_reduce = grid_for(ps->n, 256 * 4, kNumSMs * 8);
+    bool ok = cudaStreamCreateWithFlags(&ps->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->state[0], ps->D * ps->ld * es) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->state[1], ps->D * ps->ld * es) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->lw, ps->ld * es) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->anc, ps->ld * sizeof(int32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->desc, num_tiles * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->overflow, ps->overflow_cap * sizeof(OverflowEntry)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->stats, sizeof(DeviceStats)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ps->stats_host, sizeof(DeviceStats)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->partials, kNumSMs * 8 * sizeof(Lse3<double>)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->ipartials, kNumSMs * 8 * sizeof(unsigned long long)) == cudaSuccess;
+    if (ok) {
+        // particle_filter.rs:44-57: zero log-weights, zero log-ML.  ESS of the all-zero stale buffer is 1/N (quirk Q1).
+        DeviceStats init;
+        std::memset(&init, 0, sizeof init);
+        init.ess_stale = 1. / (double)ps->n_global;
+        init.max = 0.; init.sumexp = (double)ps->n_global; init.sumexp2 = (double)ps->n_global; init.ess = (double)ps->n_global;
+        ok = cudaMemcpyAsync(ps->stats, &init, sizeof init, cudaMemcpyHostToDevice, ps->stream) == cudaSuccess;
+        ok = ok && cudaMemsetAsync(ps->state[0], 0, ps->D * ps->ld * es, ps->stream) == cudaSuccess;
+        ok = ok && cudaMemsetAsync(ps->state[1], 0, ps->D * ps->ld * es, ps->stream) == cudaSuccess;
+        ok = ok && cudaMemsetAsync(ps->lw, 0, ps->ld * es, ps->stream) == cudaSuccess;
+        ok = ok && cudaMemsetAsync(ps->anc, 0, ps->ld * sizeof(int32_t), ps->stream) == cudaSuccess;
+        ok = ok && cudaStreamSynchronize(ps->stream) == cudaSuccess;
+    }
+    if (!ok) {
+        fail(MPL_ERR_CUDA, std::string("particle system allocation failed: ") + cudaGetErrorString(cudaGetLastError()));
+        mpl_ps_destroy(ps);
+        return nullptr;
+    }
+    return ps;
+}
+
+extern "C" void mpl_ps_destroy(mpl_ps* ps) {
+    if (!ps) return;
+    if (ps->stream) cudaStreamSynchronize(ps->stream);
+    for (auto& kv : ps->timers) for (auto& pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    cudaFree(ps->state[0]); cudaFree(ps->state[1]); cudaFree(ps->lw); cudaFree(ps->anc); cudaFree(ps->desc); cudaFree(ps->overflow);
+    cudaFree(ps->stats); cudaFreeHost(ps->stats_host); cudaFree(ps->partials); cudaFree(ps->ipartials);
+    cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
+    if (ps->stream) cudaStreamDestroy(ps->stream);
+    delete ps;
+}
+
+static int pack_obs(const mpl_ps* ps, const double* obs, size_t n_obs, Obs& o) {
+    if (!obs || n_obs < (size_t)ps->model.obs_dim) return fail(MPL_ERR_INVALID, "observation vector too short for this model");
+    for (int k = 0; k < 4; ++k) o.v[k] = (k < ps->model.obs_dim) ? obs[k] : 0.;
+    if (ps->model.kind == M_HMM) {
+        int sym = (int)obs[0];
+        if (sym < 0 || sym >= (int)ps->model.params[1]) return fail(MPL_ERR_INVALID, "hmm observation symbol out of range");
+    }
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_init_step(mpl_ps* ps, const double* obs, size_t n_obs) {
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    Obs o;
+    int rc = pack_obs(ps, obs, n_obs, o);
+    if (rc) return rc;
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    ps->t = 0;   // quirk Q4: init_step resets instead of pushing a second population
+    ps->pending_gather = false;
+    rc = launch_extend(ps, EXT_INIT, o, false, false);
+    if (rc) return rc;
+    ps->t = 1; ps->initialised = true; ps->stats_valid = true;
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_step(mpl_ps* ps, const double* obs, size_t n_obs) {
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    if (!ps->initialised) return fail(MPL_ERR_INVALID, "step before init_step");
+    Obs o;
+    int rc = pack_obs(ps, obs, n_obs, o);
+    if (rc) return rc;
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, o, false, false);
+    if (rc) return rc;
+    ps->pending_gather = false;
+    ps->t += 1; ps->stats_valid = true;
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_effective_sample_size(mpl_ps* ps, int stale_like_reference, double* out) {
+    if (!ps || !out) return fail(MPL_ERR_INVALID, "null argument");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    int rc;
+    if (!stale_like_reference) {
+        if (ps->pending_gather) { *out = (double)ps->n_global; return MPL_OK; }   // all weights are zero
+        if ((rc = ensure_stats(ps))) return rc;
+    }
+    if ((rc = fetch_stats(ps))) return rc;
+    *out = stale_like_reference ? ps->stats_host->ess_stale : ps->stats_host->ess;
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_resample(mpl_ps* ps, int scheme, double* log_total_weight) {
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    int rc = do_resample(ps, scheme);
+    if (rc) return rc;
+    if (log_total_weight) {
+        if ((rc = fetch_stats(ps))) return rc;
+        *log_total_weight = ps->stats_host->lse;
+        if (ps->stats_host->degenerate) return fail(MPL_ERR_DEGENERATE, "all particle weights are -inf");
+    }
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_log_marginal_likelihood_estimate(mpl_ps* ps, double* out) {
+    if (!ps || !out) return fail(MPL_ERR_INVALID, "null argument");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    int rc;
+    if (!ps->pending_gather && (rc = ensure_stats(ps))) return rc;
+    if ((rc = fetch_stats(ps))) return rc;
+    const DeviceStats& s = *ps->stats_host;
+    // particle_filter.rs:119-121 ; after a resample the weights are all zero: logsumexp(0..0) - ln N = 0
+    *out = ps->pending_gather ? s.lml_acc : s.lml_acc + (s.max + std::log(s.sumexp)) - std::log((double)ps->n_global);
+    return MPL_OK;
+}
+
+static int ensure_staging(mpl_ps* ps) {
+    if (!ps->staging) MPL_CUDA_OK(cudaMalloc(&ps->staging, (size_t)ps->D * ps->ld * sizeof(double)));
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_read(mpl_ps* ps, int what, void* host_dst, size_t bytes) {
+    if (!ps || !host_dst) return fail(MPL_ERR_INVALID, "null argument");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    int rc;
+    const int grid = grid_for(ps->n, 256, kNumSMs * 8);
+    if (what == MPL_READ_PARENTS) {
+        if (bytes != ps->n * sizeof(int64_t)) return fail(MPL_ERR_INVALID, "parents buffer must be int64[N]");
+        if ((rc = ensure_staging(ps))) return rc;
+        i32_to_i64_kernel<<<grid, 256, 0, ps->stream>>>(ps->anc, (long long*)ps->staging, ps->n);
+        MPL_CUDA_OK(cudaGetLastError());
+        MPL_CUDA_OK(cudaMemcpyAsync(host_dst, ps->staging, bytes, cudaMemcpyDeviceToHost, ps->stream));
+        MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+        return MPL_OK;
+    }
+    if ((rc = materialise(ps))) return rc;
+    if ((rc = ensure_staging(ps))) return rc;
+    if (what == MPL_READ_LOG_WEIGHTS) {
+        if (bytes != ps->n * sizeof(double)) return fail(MPL_ERR_INVALID, "log-weight buffer must be double[N]");
+        if (ps->dtype == MPL_F32) to_f64_kernel<float><<<grid, 256, 0, ps->stream>>>((const float*)ps->lw, ps->staging, ps->n);
+        else to_f64_kernel<double><<<grid, 256, 0, ps->stream>>>((const double*)ps->lw, ps->staging, ps->n);
+        MPL_CUDA_OK(cudaGetLastError());
+        MPL_CUDA_OK(cudaMemcpyAsync(host_dst, ps->staging, bytes, cudaMemcpyDeviceToHost, ps->stream));
+    } else if (what == MPL_READ_STATE) {
+        if (bytes != (size_t)ps->D * ps->n * sizeof(double)) return fail(MPL_ERR_INVALID, "state buffer must be double[D*N]");
+        for (int d = 0; d < ps->D; ++d) {
+            if (ps->dtype == MPL_F32) to_f64_kernel<float><<<grid, 256, 0, ps->stream>>>((const float*)ps->state[ps->cur] + (size_t)d * ps->ld, ps->staging + (size_t)d * ps->ld, ps->n);
+            else to_f64_kernel<double><<<grid, 256, 0, ps->stream>>>((const double*)ps->state[ps->cur] + (size_t)d * ps->ld, ps->staging + (size_t)d * ps->ld, ps->n);
+            MPL_CUDA_OK(cudaMemcpyAsync((double*)host_dst + (size_t)d * ps->n, ps->staging + (size_t)d * ps->ld, ps->n * sizeof(double), cudaMemcpyDeviceToHost, ps->stream));
+        }
+        MPL_CUDA_OK(cudaGetLastError());
+    } else return fail(MPL_ERR_INVALID, "unknown read selector");
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_write(mpl_ps* ps, int what, const void* host_src, size_t bytes) {
+    if (!ps || !host_src) return fail(MPL_ERR_INVALID, "null argument");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    int rc;
+    if ((rc = materialise(ps))) return rc;
+    if ((rc = ensure_staging(ps))) return rc;
+    const int grid = grid_for(ps->n, 256, kNumSMs * 8);
+    if (what == MPL_READ_LOG_WEIGHTS) {
+        if (bytes != ps->n * sizeof(double)) return fail(MPL_ERR_INVALID, "log-weight buffer must be double[N]");
+        MPL_CUDA_OK(cudaMemcpyAsync(ps->staging, host_src, bytes, cudaMemcpyHostToDevice, ps->stream));
+        if (ps->dtype == MPL_F32) from_f64_kernel<float><<<grid, 256, 0, ps->stream>>>(ps->staging, (float*)ps->lw, ps->n);
+        else from_f64_kernel<double><<<grid, 256, 0, ps->stream>>>(ps->staging, (double*)ps->lw, ps->n);
+        ps->stats_valid = false;
+    } else if (what == MPL_READ_STATE) {
+        if (bytes != (size_t)ps->D * ps->n * sizeof(double)) return fail(MPL_ERR_INVALID, "state buffer must be double[D*N]");
+        for (int d = 0; d < ps->D; ++d) {
+            MPL_CUDA_OK(cudaMemcpyAsync(ps->staging + (size_t)d * ps->ld, (const double*)host_src + (size_t)d * ps->n, ps->n * sizeof(double), cudaMemcpyHostToDevice, ps->stream));
+            if (ps->dtype == MPL_F32) from_f64_kernel<float><<<grid, 256, 0, ps->stream>>>(ps->staging + (size_t)d * ps->ld, (float*)ps->state[ps->cur] + (size_t)d * ps->ld, ps->n);
+            else from_f64_kernel<double><<<grid, 256, 0, ps->stream>>>(ps->staging + (size_t)d * ps->ld, (double*)ps->state[ps->cur] + (size_t)d * ps->ld, ps->n);
+        }
+        if (!ps->initialised) { ps->initialised = true; if (ps->t == 0) ps->t = 1; }
+    } else return fail(MPL_ERR_INVALID, "unknown write selector");
+    MPL_CUDA_OK(cudaGetLastError());
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_num_particles(const mpl_ps* ps, uint64_t* out) {
+    if (!ps || !out) return fail(MPL_ERR_INVALID, "null argument");
+    *out = ps->n;
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_sync(mpl_ps* ps) {
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_upload_observations(mpl_ps* ps, const double* obs, size_t n_steps, size_t n_obs) {
+    if (!ps || !obs) return fail(MPL_ERR_INVALID, "null argument");
+    if (n_obs != (size_t)ps->model.obs_dim) return fail(MPL_ERR_INVALID, "n_obs must equal the model's observation dimension");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    cudaFree(ps->obs_dev); ps->obs_dev = nullptr;
+    MPL_CUDA_OK(cudaMalloc(&ps->obs_dev, n_steps * n_obs * sizeof(double)));
+    MPL_CUDA_OK(cudaMemcpy(ps->obs_dev, obs, n_steps * n_obs * sizeof(double), cudaMemcpyHostToDevice));
+    ps->obs_steps = n_steps;
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int scheme, double ess_threshold, float* elapsed_ms) {
+    // n_steps x (step(obs[t]); resample) entirely on the device: observation t is read from HBM by the extend kernel.
+    // first_step == 0 starts with init_step(obs[0]) followed by a resample, like tests/smc.rs:63-70.
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    if (!ps->obs_dev) return fail(MPL_ERR_INVALID, "mpl_ps_upload_observations first");
+    if (first_step + n_steps > ps->obs_steps) return fail(MPL_ERR_INVALID, "run exceeds the uploaded observations");
+    if (first_step > 0 && (long long)first_step != ps->t) return fail(MPL_ERR_INVALID, "first_step must equal the filter's current time index");
+    if (ess_threshold > 0.) return fail(MPL_ERR_UNSUPPORTED, "ESS-triggered device loop: not in this build");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (elapsed_ms) { MPL_CUDA_OK(cudaEventCreate(&e0)); MPL_CUDA_OK(cudaEventCreate(&e1)); MPL_CUDA_OK(cudaEventRecord(e0, ps->stream)); }
+    Obs dummy; std::memset(&dummy, 0, sizeof dummy);
+    int rc = MPL_OK;
+    for (size_t k = 0; k < n_steps && rc == MPL_OK; ++k) {
+        size_t tt = first_step + k;
+        if (tt == 0) {
+            ps->t = 0; ps->pending_gather = false;
+            rc = launch_extend(ps, EXT_INIT, dummy, true, false);
+            ps->t = 1; ps->initialised = true; ps->stats_valid = true;
+        } else {
+            rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false);
+            ps->pending_gather = false; ps->t += 1; ps->stats_valid = true;
+        }
+        if (rc == MPL_OK) rc = do_resample(ps, scheme);
+    }
+    if (elapsed_ms) {
+        cudaEventRecord(e1, ps->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e == cudaSuccess) cudaEventElapsedTime(elapsed_ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (e != cudaSuccess) return fail(MPL_ERR_CUDA, std::string("run: ") + cudaGetErrorString(e));
+    }
+    return rc;
+}
+
+extern "C" int mpl_ps_profile_enable(mpl_ps* ps, int on) {
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    int rc = flush_timers(ps);
+    ps->profile = on != 0;
+    if (on) ps->timers.clear();
+    return rc;
+}
+extern "C" int mpl_ps_profile_get(mpl_ps* ps, const char* kernel, double* total_ms, uint64_t* launches) {
+    if (!ps || !kernel) return fail(MPL_ERR_INVALID, "null argument");
+    int rc = flush_timers(ps);
+    if (rc) return rc;
+    auto it = ps->timers.find(kernel);
+    if (total_ms) *total_ms = it == ps->timers.end() ? 0. : it->second.total_ms;
+    if (launches) *launches = it == ps->timers.end() ? 0 : it->second.launches;
+    return MPL_OK;
+}
+extern "C" int mpl_ps_launch_count(mpl_ps* ps, uint64_t* out) {
+    if (!ps || !out) return fail(MPL_ERR_INVALID, "null argument");
+    *out = ps->launch_count;
+    return MPL_OK;
+}
+
+// ---- parity hooks -----------------------------------------------------------------------------------------------
+static int require_device() {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(MPL_ERR_CUDA, "no CUDA device: modppl_b200 has no CPU fallback"); }
+    return MPL_OK;
+}
+
+extern "C" int mpl_cumsum_sequential(const double* probs, uint64_t n, double* out) {
+    if (!probs || !out || n == 0) return fail(MPL_ERR_INVALID, "bad argument");
+    int rc = require_device();
+    if (rc) return rc;
+    double *dp = nullptr, *ds = nullptr;
+    MPL_CUDA_OK(cudaMalloc(&dp, n * 8));
+    MPL_CUDA_OK(cudaMalloc(&ds, n * 8));
+    MPL_CUDA_OK(cudaMemcpy(dp, probs, n * 8, cudaMemcpyHostToDevice));
+    rc = launch_cumsum_exact(nullptr, dp, n, ds, 0);
+    if (rc == MPL_OK) { cudaError_t e = cudaMemcpy(out, ds, n * 8, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(MPL_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaFree(dp); cudaFree(ds);
+    return rc;
+}
+
+extern "C" int mpl_resample_indices(const double* probs, const double* uniforms, uint64_t n, uint64_t n_draws, int scheme, int64_t* parents) {
+    if (!probs || !uniforms || !parents || n == 0) return fail(MPL_ERR_INVALID, "bad argument");
+    if (scheme != MPL_RESAMPLE_MULTINOMIAL && scheme != MPL_RESAMPLE_SYSTEMATIC) return fail(MPL_ERR_INVALID, "scheme must be MULTINOMIAL or SYSTEMATIC");
+    int rc = require_device();
+    if (rc) return rc;
+    if (n_draws == 0) return MPL_OK;
+    double *dp = nullptr, *ds = nullptr, *du = nullptr; long long* dpar = nullptr;
+    size_t nu = scheme == MPL_RESAMPLE_MULTINOMIAL ? n_draws : 1;
+    MPL_CUDA_OK(cudaMalloc(&dp, n * 8));
+    MPL_CUDA_OK(cudaMalloc(&ds, n * 8));
+    MPL_CUDA_OK(cudaMalloc(&du, nu * 8));
+    MPL_CUDA_OK(cudaMalloc(&dpar, n_draws * 8));
+    MPL_CUDA_OK(cudaMemcpy(dp, probs, n * 8, cudaMemcpyHostToDevice));
+    MPL_CUDA_OK(cudaMemcpy(du, uniforms, nu * 8, cudaMemcpyHostToDevice));
+    rc = launch_cumsum_exact(nullptr, dp, n, ds, 0);
+    if (rc == MPL_OK) {
+        search_kernel<long long><<<grid_for(n_draws, 256, kNumSMs * 8), 256>>>(ds, n, n_draws, scheme == MPL_RESAMPLE_MULTINOMIAL ? 0 : 1, du, 0, 0, 0, dpar);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpy(parents, dpar, n_draws * 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = fail(MPL_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(dp); cudaFree(ds); cudaFree(du); cudaFree(dpar);
+    return rc;
+}
+
+extern "C" int mpl_logsumexp_stats(const void* lw, uint64_t n, int dtype, double* lse, double* ess, double* mx) {
+    if (!lw || n == 0) return fail(MPL_ERR_INVALID, "bad argument");
+    int rc = require_device();
+    if (rc) return rc;
+    size_t es = dtype == MPL_F64 ? 8 : 4;
+    void* d = nullptr; DeviceStats* st = nullptr; Lse3<double>* part = nullptr;
+    int grid = grid_for(n, 256 * 4, kNumSMs * 8);
+    MPL_CUDA_OK(cudaMalloc(&d, n * es));
+    MPL_CUDA_OK(cudaMalloc(&st, sizeof(DeviceStats)));
+    MPL_CUDA_OK(cudaMalloc(&part, grid * sizeof(Lse3<double>)));
+    MPL_CUDA_OK(cudaMemset(st, 0, sizeof(DeviceStats)));
+    MPL_CUDA_OK(cudaMemcpy(d, lw, n * es, cudaMemcpyHostToDevice));
+    if (dtype == MPL_F64) weight_reduce_kernel<double><<<grid, 256>>>((const double*)d, n, st, part);
+    else weight_reduce_kernel<float><<<grid, 256>>>((const float*)d, n, st, part);
+    DeviceStats h;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(&h, st, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(st); cudaFree(part);
+    if (e != cudaSuccess) return fail(MPL_ERR_CUDA, cudaGetErrorString(e));
+    if (lse) *lse = (h.max == -INFINITY) ? -INFINITY : h.max + std::log(h.sumexp);   // lib.rs:36-37
+    if (ess) *ess = h.ess;
+    if (mx) *mx = h.max;
+    return MPL_OK;
+}
+
+extern "C" int mpl_fixed_resample(const float* lw, uint64_t n, int scheme, uint64_t rand_word_or_seed, uint32_t t, int32_t* anc, double* lse, uint64_t* total_weight) {
+    // integer-weight resampling of injected f32 log-weights through a scratch particle system (D = 1)
+    if (!lw || !anc || n == 0) return fail(MPL_ERR_INVALID, "bad argument");
+    if (scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED && scheme != MPL_RESAMPLE_MULTINOMIAL_FIXED) return fail(MPL_ERR_INVALID, "scheme must be a *_FIXED scheme");
+    int rc = require_device();
+    if (rc) return rc;
+    double svp[3] = {0., 0.5, 1.};
+    mpl_model* m = mpl_model_create("sv", svp, 3);
+    mpl_pf_config c; c.dtype = MPL_F32; c.device = -1; c.seed = rand_word_or_seed; c.gid_offset = 0; c.n_global = 0;
+    mpl_ps* ps = mpl_particle_system_new(m, n, &c);
+    if (!ps) { mpl_model_destroy(m); return MPL_ERR_CUDA; }
+    ps->initialised = true; ps->t = (long long)t + 1;
+    cudaError_t e = cudaMemcpyAsync(ps->lw, lw, n * 4, cudaMemcpyHostToDevice, ps->stream);
+    if (e == cudaSuccess) {
+        ps->stats_valid = false;
+        rc = do_resample(ps, scheme);
+        if (rc == MPL_OK) rc = fetch_stats(ps);
+        if (rc == MPL_OK) {
+            e = cudaMemcpy(anc, ps->anc, n * 4, cudaMemcpyDeviceToHost);
+            if (lse) *lse = ps->stats_host->lse;
+            if (total_weight) *total_weight = ps->stats_host->W;
+        }
+    }
+    if (e != cudaSuccess) rc = fail(MPL_ERR_CUDA, cudaGetErrorString(e));
+    mpl_ps_destroy(ps); mpl_model_destroy(m);
+    return rc;
+}

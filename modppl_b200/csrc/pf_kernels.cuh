@@ -1,0 +1,774 @@
+// pf_kernels.cuh -- particle-filter kernels for sm_100a.
+//
+//   pf_extend_kernel     K1/K2 (+K6 fused): ancestor gather -> Philox extend -> observation log-likelihood ->
+//                        SoA stores, with an online (max, sum exp, sum exp^2) epilogue (K3) and a last-block
+//                        finalisation.  Replaces the per-particle generate/update loops of
+//                        reference modppl/src/inference/particle_filter.rs:65-69,76-82.
+//   weight_reduce_kernel K3 stand-alone: lib.rs:34-45 + particle_filter.rs:27-35,98-100 in one pass.
+//   fixed_reduce_kernel / fixed_scan_kernel / fixed_overflow_kernel
+//                        K5: integer-weight systematic resampling -- quantise, decoupled-lookback prefix scan,
+//                        in-tile expansion (run heads + max-scan in shared memory) that writes ancestors coalesced.
+//   normalize / cumsum_seq / search kernels
+//                        K4: the reference's multinomial routine (categorical.rs:22-32) with its SEQUENTIAL f64
+//                        running sum, bit-exact.
+//   gather_kernel        K6 stand-alone (only when the host reads state right after a resample).
+#pragma once
+#include "common.cuh"
+#include "models.cuh"
+
+namespace mpl {
+
+typedef unsigned __int128 u128;
+
+// device-resident bookkeeping of one ParticleSystem (reference particle_filter.rs:8-24 scalars)
+struct DeviceStats {
+    double max, sumexp, sumexp2;   // of the current log-weights
+    double lse;                    // log total weight at the last normalisation (return value of resample())
+    double lml_acc;                // log_ml_estimate                                  (particle_filter.rs:23)
+    double ess;                    // fresh ESS of the current weights
+    double ess_stale;              // ESS as of the last normalize_weights()            (quirk Q1)
+    unsigned long long W;          // total integer weight (fixed schemes)
+    unsigned long long rand_word;  // systematic offset word of this resample
+    long long t;                   // next kernel time index (device copy, for mpl_ps_run)
+    unsigned int max_ordered;      // atomicMax target for the exact global max (float path)
+    unsigned int blocks_done;      // last-block-done counter of the extend epilogue
+    unsigned int ticket;           // tile ticket of the scan
+    unsigned int overflow_count;
+    int degenerate;                // all weights -inf seen
+    int resampled;                 // 1: ancestors pending (next extend gathers, weights are zero)
+    int do_resample;               // ESS trigger decision for the dynamic path
+    int pad;
+};
+
+struct OverflowEntry {
+    unsigned long long tile_excl;
+    unsigned long long n_start;
+    unsigned int tile;
+    unsigned int total;
+};
+
+template <typename Real> struct VecOf;
+template <> struct VecOf<float> { typedef float4 type; static constexpr int N = 4; };
+template <> struct VecOf<double> { typedef double2 type; static constexpr int N = 2; };
+
+template <typename Real> __device__ __forceinline__ void vec_load(const Real* p, Real (&v)[VecOf<Real>::N]);
+template <> __device__ __forceinline__ void vec_load<float>(const float* p, float (&v)[4]) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+template <> __device__ __forceinline__ void vec_load<double>(const double* p, double (&v)[2]) { double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y; }
+template <typename Real> __device__ __forceinline__ void vec_store(Real* p, const Real (&v)[VecOf<Real>::N]);
+template <> __device__ __forceinline__ void vec_store<float>(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void vec_store<double>(double* p, const double (&v)[2]) { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+
+// ================================================================================================
+// K1/K2/K6/K3: extend
+// ================================================================================================
+enum ExtendMode : int { EXT_INIT = 0, EXT_ACCUM = 1, EXT_GATHER = 2, EXT_DYNAMIC = 3 };
+
+template <typename Real>
+struct ExtendArgs {
+    const Real* state_in;    // D x ld
+    Real* state_out;         // D x ld
+    Real* lw;                // ld
+    const int32_t* anc;      // ld (local parent index)
+    size_t n, ld;
+    uint64_t seed, gid_offset;
+    long long t;             // kernel time index; < 0: read stats->t (device-resident loop)
+    Obs obs;
+    const double* obs_dev;   // if non-null: observations of step t at obs_dev[t * nobs ...]
+    int nobs;
+    DeviceStats* stats;
+    Lse3<double>* partials;  // gridDim.x
+};
+
+constexpr int kExtendThreads = 256;
+
+template <class Model, typename Real, int MODE>
+__global__ void __launch_bounds__(kExtendThreads) pf_extend_kernel(ExtendArgs<Real> a, Model model) {
+    constexpr int D = Model::D;
+    constexpr int V = VecOf<Real>::N;
+    typedef Real Acc;
+    const int tid = threadIdx.x;
+
+    long long t = a.t;
+    if (t < 0) t = a.stats->t;
+    Obs obs = a.obs;
+    if (a.obs_dev != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) obs.v[k] = (k < a.nobs) ? a.obs_dev[(size_t)t * a.nobs + k] : 0.;
+    }
+    bool gather = (MODE == EXT_GATHER);
+    bool accum = (MODE == EXT_ACCUM);
+    if (MODE == EXT_DYNAMIC) {
+        gather = a.stats->resampled != 0;
+        accum = !gather;
+    }
+
+    Lse3<Acc> run = lse3_identity<Acc>();
+    const size_t stride = (size_t)gridDim.x * kExtendThreads * V;
+    for (size_t base = ((size_t)blockIdx.x * kExtendThreads + tid) * V; base < a.n; base += stride) {
+        Real x[V][D];
+        Real w[V];
+        int32_t par[V];
+        const bool full = base + V <= a.n;
+        if (gather) {
+            if constexpr (V == 4) { int4 p = *reinterpret_cast<const int4*>(a.anc + base); par[0] = p.x; par[1] = p.y; par[2] = p.z; par[3] = p.w; }
+            else { int2 p = *reinterpret_cast<const int2*>(a.anc + base); par[0] = p.x; par[1] = p.y; }
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                size_t src = (full || base + v < a.n) ? (size_t)par[v] : 0;
+#pragma unroll
+                for (int d = 0; d < D; ++d) x[v][d] = __ldg(a.state_in + (size_t)d * a.ld + src);
+            }
+        } else if (MODE != EXT_INIT) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                Real tmp[V];
+                vec_load<Real>(a.state_in + (size_t)d * a.ld + base, tmp);
+#pragma unroll
+                for (int v = 0; v < V; ++v) x[v][d] = tmp[v];
+            }
+        }
+        if (accum) vec_load<Real>(a.lw + base, w);
+        else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) w[v] = 0;
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            Stream s(a.seed, a.gid_offset + base + v, (uint32_t)t, P_MODEL);
+            w[v] += model.kernel(t, s, x[v], obs);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            Real tmp[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) tmp[v] = x[v][d];
+            vec_store<Real>(a.state_out + (size_t)d * a.ld + base, tmp);
+        }
+        vec_store<Real>(a.lw + base, w);
+
+        // online (max, sum exp, sum exp^2)
+        Acc m = (Acc)-INFINITY;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            bool ok = (full || base + v < a.n) && (w[v] == w[v]);
+            w[v] = ok ? w[v] : (Real)-INFINITY;
+            m = fmax(m, (Acc)w[v]);
+        }
+        if (m > (Acc)-INFINITY) {
+            Acc s1 = 0, s2 = 0;
+#pragma unroll
+            for (int v = 0; v < V; ++v) { Acc e = exp((Acc)w[v] - m); s1 += e; s2 += e * e; }
+            run = lse3_combine(run, Lse3<Acc>{m, s1, s2});
+        }
+    }
+
+    // block reduction -> partial -> last block finalises (deterministic order)
+    __shared__ Lse3<double> warp_part[kExtendThreads / 32];
+    __shared__ bool is_last;
+    Lse3<Acc> wr = lse3_warp_reduce(run);
+    if ((tid & 31) == 0) warp_part[tid >> 5] = Lse3<double>{(double)wr.m, (double)wr.s, (double)wr.s2};
+    __syncthreads();
+    if (tid == 0) {
+        Lse3<double> b = warp_part[0];
+        for (int i = 1; i < kExtendThreads / 32; ++i) b = lse3_combine(b, warp_part[i]);
+        a.partials[blockIdx.x] = b;
+        __threadfence();
+        unsigned int done = atomicAdd(&a.stats->blocks_done, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        Lse3<double> acc = lse3_identity<double>();
+        for (unsigned int i = tid; i < gridDim.x; i += kExtendThreads) acc = lse3_combine(acc, a.partials[i]);
+        acc = lse3_warp_reduce(acc);
+        if ((tid & 31) == 0) warp_part[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            Lse3<double> b = warp_part[0];
+            for (int i = 1; i < kExtendThreads / 32; ++i) b = lse3_combine(b, warp_part[i]);
+            DeviceStats* st = a.stats;
+            st->max = b.m; st->sumexp = b.s; st->sumexp2 = b.s2;
+            st->ess = (b.s2 > 0.) ? (b.s * b.s) / b.s2 : 0.;
+            st->degenerate = (b.m == -INFINITY) ? 1 : 0;
+            st->blocks_done = 0;
+            st->resampled = 0;
+            st->t = t + 1;
+        }
+    }
+}
+
+// ================================================================================================
+// K3 stand-alone weight reduction (also the parity hook mpl_logsumexp_stats)
+// ================================================================================================
+template <typename Real>
+__global__ void __launch_bounds__(256) weight_reduce_kernel(const Real* __restrict__ lw, size_t n, DeviceStats* stats, Lse3<double>* partials) {
+    typedef Real Acc;
+    const int tid = threadIdx.x;
+    Lse3<Acc> run = lse3_identity<Acc>();
+    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n; i += (size_t)gridDim.x * 256) {
+        Real w = lw[i];
+        if (w == w && w > (Real)-INFINITY) {
+            if ((Acc)w <= run.m) { Acc e = exp((Acc)w - run.m); run.s += e; run.s2 += e * e; }
+            else { Acc e = exp(run.m - (Acc)w); run.s = run.s * e + 1; run.s2 = run.s2 * e * e + 1; run.m = (Acc)w; }
+        }
+    }
+    __shared__ Lse3<double> warp_part[8];
+    __shared__ bool is_last;
+    Lse3<Acc> wr = lse3_warp_reduce(run);
+    if ((tid & 31) == 0) warp_part[tid >> 5] = Lse3<double>{(double)wr.m, (double)wr.s, (double)wr.s2};
+    __syncthreads();
+    if (tid == 0) {
+        Lse3<double> b = warp_part[0];
+        for (int i = 1; i < 8; ++i) b = lse3_combine(b, warp_part[i]);
+        partials[blockIdx.x] = b;
+        __threadfence();
+        is_last = (atomicAdd(&stats->blocks_done, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        Lse3<double> acc = lse3_identity<double>();
+        for (unsigned int i = tid; i < gridDim.x; i += 256) acc = lse3_combine(acc, partials[i]);
+        acc = lse3_warp_reduce(acc);
+        if ((tid & 31) == 0) warp_part[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            Lse3<double> b = warp_part[0];
+            for (int i = 1; i < 8; ++i) b = lse3_combine(b, warp_part[i]);
+            stats->max = b.m; stats->sumexp = b.s; stats->sumexp2 = b.s2;
+            stats->ess = (b.s2 > 0.) ? (b.s * b.s) / b.s2 : 0.;
+            stats->degenerate = (b.m == -INFINITY) ? 1 : 0;
+            stats->blocks_done = 0;
+        }
+    }
+}
+
+// ================================================================================================
+// K5: integer-weight systematic resampling
+// ================================================================================================
+constexpr int kScanThreads = 256;
+constexpr int kScanRounds = 4;
+constexpr int kScanTile = kScanThreads * 4 * kScanRounds;   // 4096 particles per tile
+constexpr unsigned int kHeavyCap = 32u * kScanTile;        // tiles with more offspring than this go to the overflow pass
+constexpr unsigned long long kDescAggregate = 1ull << 62, kDescInclusive = 2ull << 62, kDescMask = (1ull << 62) - 1;
+
+template <typename Real>
+struct FixedArgs {
+    const Real* lw;
+    size_t n;                 // local particles
+    int kbits;
+    unsigned long long n_out; // global number of offspring (N_global)
+    unsigned long long c_offset;   // integer weight of all lower-ranked shards
+    unsigned long long out_base;   // global index of this shard's first output slot
+    unsigned long long n_out_local;
+    double log_n_global;
+    int32_t* anc;             // local output slots [out_base, out_base + n_out_local)
+    int32_t src_base;         // value written for local particle 0 (global id of it, or 0)
+    unsigned long long* desc;
+    OverflowEntry* overflow;
+    DeviceStats* stats;
+    unsigned long long* partials;   // gridDim.x of the reduce kernel
+    uint64_t seed;
+    long long rt;             // RNG tag of this resample (step whose weights are resampled); < 0: stats->t - 1
+    int accumulate_lml;
+    int dynamic;              // 1: skip unless stats->do_resample (ESS-triggered, device-resident loop)
+};
+
+__device__ __forceinline__ unsigned long long resample_rand_word(uint64_t seed, long long rt, const DeviceStats* st) {
+    if (rt < 0) rt = st->t - 1;
+    Stream s(seed, 0, (uint32_t)rt, P_RESAMPLE_OFFSET);
+    uint4 x = s.block(0);
+    return ((unsigned long long)x.x << 32) | x.y;
+}
+
+// 4 consecutive log-weights -> 4 integer weights; out-of-range lanes give 0
+template <typename Real>
+__device__ __forceinline__ void load_q4(const Real* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4]);
+template <>
+__device__ __forceinline__ void load_q4<float>(const float* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4]) {
+    float4 v = *reinterpret_cast<const float4*>(lw + idx);
+    float w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = (idx + j < n) ? fixed_weight(__fsub_rn(w[j], mx), kbits) : 0ull;
+}
+template <>
+__device__ __forceinline__ void load_q4<double>(const double* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4]) {
+    double2 a = *reinterpret_cast<const double2*>(lw + idx), b = *reinterpret_cast<const double2*>(lw + idx + 2);
+    double w[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) q[j] = (idx + j < n) ? fixed_weight(__fsub_rn((float)w[j], mx), kbits) : 0ull;
+}
+
+// R1: W = sum of integer weights (exact, order-independent); also resets the scan's descriptors.
+template <typename Real>
+__global__ void __launch_bounds__(256) fixed_reduce_kernel(FixedArgs<Real> a, size_t num_tiles) {
+    if (a.dynamic && !a.stats->do_resample) return;
+    const size_t gtid = (size_t)blockIdx.x * 256 + threadIdx.x;
+    for (size_t i = gtid; i < num_tiles; i += (size_t)gridDim.x * 256) a.desc[i] = 0ull;
+    const float mx = (float)a.stats->max;
+    unsigned long long sum = 0;
+    for (size_t idx = gtid * 4; idx < a.n; idx += (size_t)gridDim.x * 256 * 4) {
+        unsigned long long q[4];
+        load_q4<Real>(a.lw, idx, a.n, mx, a.kbits, q);
+        sum += q[0] + q[1] + q[2] + q[3];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ unsigned long long ws[8];
+    __shared__ bool is_last;
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long b = 0;
+        for (int i = 0; i < 8; ++i) b += ws[i];
+        a.partials[blockIdx.x] = b;
+        __threadfence();
+        is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        unsigned long long t = 0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) t += a.partials[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = t;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long b = 0;
+            for (int i = 0; i < 8; ++i) b += ws[i];
+            DeviceStats* st = a.stats;
+            st->W = b; st->ticket = 0; st->overflow_count = 0; st->blocks_done = 0;
+        }
+    }
+}
+
+// number of output slots j in [0, n_out) with j*W + U < C*n_out
+__device__ __forceinline__ unsigned long long count_below(unsigned long long C, unsigned long long W, unsigned long long U, unsigned long long n_out, double inv_w) {
+    u128 lhs = (u128)C * n_out;
+    if (lhs <= (u128)U) return 0ull;
+    u128 X = lhs - U - 1;   // count = floor(X / W) + 1
+    double xd = (double)C * (double)n_out - (double)U;
+    double ed = xd * inv_w;
+    unsigned long long e = ed <= 0. ? 0ull : (ed >= (double)n_out ? n_out : (unsigned long long)ed);
+    u128 p = (u128)e * W;
+    while (p > X) { --e; p -= W; }
+    while (p + W <= X) { ++e; p += W; }
+    return e + 1;
+}
+
+struct ScanShared {
+    unsigned long long warp_tot[kScanRounds][kScanThreads / 32];
+    unsigned long long tile_excl;
+    unsigned int nloc[kScanTile];             // inclusive offspring counts, relative to the tile's first output slot
+    __align__(16) unsigned short head[kScanTile];   // expansion buffer: (local parent + 1) at the first slot of each run
+    unsigned int warp_max[kScanThreads / 32];
+    unsigned int carry;
+    unsigned int tile;
+};
+
+// Loads a tile, quantises, and leaves in excl[r] the tile-local exclusive prefix of this thread's round-r chunk.
+// Returns the tile aggregate.  Element order inside the tile: e = r*1024 + 4*tid + j.
+template <typename Real>
+__device__ __forceinline__ unsigned long long tile_local_scan(const FixedArgs<Real>& a, ScanShared& sh, unsigned int tile, float mx,
+                                                              unsigned long long (&q)[kScanRounds][4], unsigned long long (&excl)[kScanRounds]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t tile_base = (size_t)tile * kScanTile;
+    unsigned long long incl[kScanRounds];
+#pragma unroll
+    for (int r = 0; r < kScanRounds; ++r) {
+        size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
+        if (idx < a.n) load_q4<Real>(a.lw, idx, a.n, mx, a.kbits, q[r]);
+        else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0ull; }
+        incl[r] = q[r][0] + q[r][1] + q[r][2] + q[r][3];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int r = 0; r < kScanRounds; ++r) {
+            unsigned long long up = __shfl_up_sync(0xffffffffu, incl[r], o);
+            if (lane >= o) incl[r] += up;
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int r = 0; r < kScanRounds; ++r) sh.warp_tot[r][warp] = incl[r];
+    }
+    __syncthreads();
+    unsigned long long carry = 0, aggregate = 0;
+#pragma unroll
+    for (int r = 0; r < kScanRounds; ++r) {
+        unsigned long long before = 0, round_tot = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) {
+            unsigned long long v = sh.warp_tot[r][w];
+            if (w < warp) before += v;
+            round_tot += v;
+        }
+        unsigned long long own = q[r][0] + q[r][1] + q[r][2] + q[r][3];
+        excl[r] = carry + before + incl[r] - own;
+        carry += round_tot;
+    }
+    aggregate = carry;
+    return aggregate;
+}
+
+// nloc[e] = (#offspring of all particles up to and including element e) - n_start
+template <typename Real>
+__device__ __forceinline__ void tile_fill_nloc(const FixedArgs<Real>& a, ScanShared& sh, unsigned long long tile_excl, unsigned long long n_start,
+                                               unsigned long long W, unsigned long long U, double inv_w,
+                                               const unsigned long long (&q)[kScanRounds][4], const unsigned long long (&excl)[kScanRounds]) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < kScanRounds; ++r) {
+        unsigned long long c = a.c_offset + tile_excl + excl[r];
+        unsigned int prev = 0;
+        bool have_prev = false;
+        uint4 out;
+        unsigned int* o = reinterpret_cast<unsigned int*>(&out);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            c += q[r][j];
+            if (q[r][j] == 0ull && have_prev) o[j] = prev;
+            else { o[j] = (unsigned int)(count_below(c, W, U, a.n_out, inv_w) - n_start); prev = o[j]; have_prev = true; }
+        }
+        *reinterpret_cast<uint4*>(&sh.nloc[r * (kScanThreads * 4) + tid * 4]) = out;
+    }
+}
+
+// Expands one chunk of kScanTile consecutive output slots of a tile: slots [chunk_base, chunk_base + kScanTile) of the
+// tile-local offspring range.  Every particle with >= 1 offspring drops (its local index + 1) at the first slot of its
+// run; an inclusive max-scan propagates it along the run (local indices increase with the slot); the result is
+// written with coalesced 4-byte stores.  All threads of the block must call this.
+template <typename Real>
+__device__ __forceinline__ void expand_chunk(const FixedArgs<Real>& a, ScanShared& sh, unsigned int tile, unsigned long long n_start,
+                                             unsigned int chunk_base, unsigned int total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint4* head4 = reinterpret_cast<uint4*>(sh.head);
+    head4[tid * 2] = make_uint4(0, 0, 0, 0);
+    head4[tid * 2 + 1] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {   // parent of the chunk's first slot: first element e with nloc[e] > chunk_base
+        unsigned int lo = 0, hi = kScanTile - 1;
+        while (lo < hi) { unsigned int mid = (lo + hi) >> 1; if (sh.nloc[mid] > chunk_base) hi = mid; else lo = mid + 1; }
+        sh.carry = lo + 1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kScanRounds; ++r) {
+        const unsigned int e0 = r * (kScanThreads * 4) + tid * 4;
+        uint4 cur = *reinterpret_cast<const uint4*>(&sh.nloc[e0]);
+        unsigned int prev = (e0 == 0) ? 0u : sh.nloc[e0 - 1];
+        const unsigned int c[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned int rel = prev - chunk_base;   // wraps when prev < chunk_base
+            if (c[j] > prev && rel < (unsigned int)kScanTile) sh.head[rel] = (unsigned short)(e0 + j + 1);
+            prev = c[j];
+        }
+    }
+    __syncthreads();
+    // blocked max-scan: thread owns slots [16*tid, 16*tid + 16)
+    uint4 h0 = head4[tid * 2], h1 = head4[tid * 2 + 1];
+    unsigned int v[16] = {h0.x & 0xffffu, h0.x >> 16, h0.y & 0xffffu, h0.y >> 16, h0.z & 0xffffu, h0.z >> 16, h0.w & 0xffffu, h0.w >> 16,
+                          h1.x & 0xffffu, h1.x >> 16, h1.y & 0xffffu, h1.y >> 16, h1.z & 0xffffu, h1.z >> 16, h1.w & 0xffffu, h1.w >> 16};
+#pragma unroll
+    for (int i = 1; i < 16; ++i) v[i] = max(v[i], v[i - 1]);
+    unsigned int incl = v[15];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = max(incl, up); }
+    if (lane == 31) sh.warp_max[warp] = incl;
+    unsigned int before = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) before = 0;
+    __syncthreads();
+    unsigned int pre = max(before, sh.carry);
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) if (w < warp) pre = max(pre, sh.warp_max[w]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = max(v[i], pre);
+    head4[tid * 2] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+    head4[tid * 2 + 1] = make_uint4(v[8] | (v[9] << 16), v[10] | (v[11] << 16), v[12] | (v[13] << 16), v[14] | (v[15] << 16));
+    __syncthreads();
+    const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile) - 1;
+    const unsigned long long slot0 = n_start + chunk_base;
+#pragma unroll
+    for (int k = 0; k < kScanTile / kScanThreads; ++k) {
+        unsigned int o = k * kScanThreads + tid;
+        unsigned long long slot = slot0 + o;
+        if (chunk_base + o < total && slot >= a.out_base && slot < a.out_base + a.n_out_local)
+            a.anc[slot - a.out_base] = src0 + (int32_t)sh.head[o];
+    }
+    __syncthreads();
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(kScanThreads) fixed_scan_kernel(FixedArgs<Real> a, unsigned int num_tiles) {
+    __shared__ ScanShared sh;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (a.dynamic && !a.stats->do_resample) return;
+    if (tid == 0) sh.tile = atomicAdd(&a.stats->ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = sh.tile;
+    DeviceStats* st = a.stats;
+    const unsigned long long W = st->W;
+    const float mx = (float)st->max;
+    if (W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors, flagged
+        for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
+        if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; }
+        return;
+    }
+    const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
+    const double inv_w = 1. / (double)W;
+
+    unsigned long long q[kScanRounds][4], excl[kScanRounds];
+    const unsigned long long aggregate = tile_local_scan<Real>(a, sh, tile, mx, q, excl);
+
+    // ---- decoupled look-back (single pass): publish aggregate, walk predecessors, publish inclusive prefix
+    if (tid < 32) {
+        unsigned long long exclusive = 0;
+        if (tile == 0) {
+            if (lane == 0) atomicExch(&a.desc[0], kDescInclusive | aggregate);
+        } else {
+            if (lane == 0) atomicExch(&a.desc[tile], kDescAggregate | aggregate);
+            long long pred = (long long)tile - 1 - lane;
+            while (true) {
+                unsigned long long d = kDescInclusive;   // virtual tile -1: inclusive 0
+                if (pred >= 0) {
+                    volatile unsigned long long* p = a.desc + pred;
+                    do { d = *p; } while ((d >> 62) == 0ull);
+                }
+                unsigned int incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+                unsigned long long v = d & kDescMask;
+                int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+                if (lane > first) v = 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                exclusive += v;
+                if (incl_mask) break;
+                pred -= 32;
+            }
+            if (lane == 0) atomicExch(&a.desc[tile], kDescInclusive | (exclusive + aggregate));
+        }
+        if (lane == 0) sh.tile_excl = exclusive;
+    }
+    __syncthreads();
+    const unsigned long long tile_excl = sh.tile_excl;
+    const unsigned long long n_start = count_below(a.c_offset + tile_excl, W, U, a.n_out, inv_w);
+    const unsigned long long n_end = count_below(a.c_offset + tile_excl + aggregate, W, U, a.n_out, inv_w);
+    const unsigned long long total = n_end - n_start;
+
+    if (tile == 0 && tid == 0) {   // scalar bookkeeping of resample(): particle_filter.rs:104-105,114
+        double lse = (double)mx + log((double)W) - (double)a.kbits * 0.6931471805599453;
+        st->lse = lse;
+        st->ess_stale = st->ess;
+        if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
+        st->resampled = 1;
+    }
+    if (total == 0ull) return;
+    if (total > (unsigned long long)kHeavyCap) {
+        if (tid == 0) {
+            unsigned int slot = atomicAdd(&st->overflow_count, 1u);
+            a.overflow[slot] = OverflowEntry{tile_excl, n_start, tile, (unsigned int)total};
+        }
+        return;
+    }
+    tile_fill_nloc<Real>(a, sh, tile_excl, n_start, W, U, inv_w, q, excl);
+    __syncthreads();
+    for (unsigned int chunk_base = 0; chunk_base < (unsigned int)total; chunk_base += kScanTile)
+        expand_chunk<Real>(a, sh, tile, n_start, chunk_base, (unsigned int)total);
+}
+
+// heavy tiles (a few particles own a large share of the offspring): the whole grid expands each of them
+template <typename Real>
+__global__ void __launch_bounds__(kScanThreads) fixed_overflow_kernel(FixedArgs<Real> a) {
+    __shared__ ScanShared sh;
+    DeviceStats* st = a.stats;
+    if (a.dynamic && !st->do_resample) return;
+    const unsigned int count = st->overflow_count;
+    if (count == 0u) return;
+    const unsigned long long W = st->W;
+    const float mx = (float)st->max;
+    const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
+    const double inv_w = 1. / (double)W;
+    for (unsigned int k = 0; k < count; ++k) {
+        const OverflowEntry e = a.overflow[k];
+        unsigned long long q[kScanRounds][4], excl[kScanRounds];
+        __syncthreads();
+        tile_local_scan<Real>(a, sh, e.tile, mx, q, excl);
+        tile_fill_nloc<Real>(a, sh, e.tile_excl, e.n_start, W, U, inv_w, q, excl);
+        __syncthreads();
+        for (unsigned long long chunk_base = (unsigned long long)blockIdx.x * kScanTile; chunk_base < e.total; chunk_base += (unsigned long long)gridDim.x * kScanTile)
+            expand_chunk<Real>(a, sh, e.tile, e.n_start, (unsigned int)chunk_base, e.total);
+    }
+}
+
+// ================================================================================================
+// K4: the reference's multinomial routine, bit-exact
+// ================================================================================================
+// normalize_weights (particle_filter.rs:27-35): probs = exp(lw - lse); also the scalar bookkeeping of resample()
+template <typename Real>
+__global__ void __launch_bounds__(256) normalize_kernel(const Real* __restrict__ lw, size_t n, double* __restrict__ probs, DeviceStats* st,
+                                                        double log_n, int accumulate_lml) {
+    const double lse = st->max + log(st->sumexp);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        double lnw = (double)lw[i] - lse;
+        probs[i] = exp(lnw);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->lse = lse;
+        st->ess_stale = st->ess;
+        if (accumulate_lml) st->lml_acc += lse - log_n;
+        st->resampled = 1;
+    }
+}
+
+// Sequential f64 running sum S_k = fl(S_{k-1} + p_k) (categorical.rs:25-30).  One block: all threads stage chunks
+// through shared memory (coalesced), thread 0 performs the dependent adds in index order.
+constexpr int kSeqChunk = 2048;
+static __global__ void __launch_bounds__(256) cumsum_seq_kernel(const double* __restrict__ p, size_t n, double* __restrict__ out) {
+    __shared__ double buf[2][kSeqChunk];
+    __shared__ double carry;
+    const int tid = threadIdx.x;
+    if (tid == 0) carry = 0.;
+    size_t nchunks = (n + kSeqChunk - 1) / kSeqChunk;
+    for (int i = tid; i < kSeqChunk; i += 256) buf[0][i] = ((size_t)i < n) ? p[i] : 0.;
+    __syncthreads();
+    for (size_t c = 0; c < nchunks; ++c) {
+        int cur = c & 1;
+        size_t base = c * kSeqChunk;
+        if (tid == 0) {
+            double t = carry;
+            double* b = buf[cur];
+            size_t cnt = min((size_t)kSeqChunk, n - base);
+            for (size_t i = 0; i < cnt; ++i) { t = __dadd_rn(t, b[i]); b[i] = t; }
+            carry = t;
+        } else if (c + 1 < nchunks) {   // the other threads prefetch the next chunk meanwhile
+            size_t nb = base + kSeqChunk;
+            for (int i = tid - 1; i < kSeqChunk; i += 255) buf[cur ^ 1][i] = (nb + i < n) ? p[nb + i] : 0.;
+        }
+        __syncthreads();
+        for (int i = tid; i < kSeqChunk; i += 256) if (base + i < n) out[base + i] = buf[cur][i];
+        __syncthreads();
+    }
+}
+
+// parent = min{k : S_k >= u}, clamped to [0, n-1] (quirk Q2)
+__device__ __forceinline__ long long search_cumsum(const double* __restrict__ S, size_t n, double u) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (S[mid] >= u) hi = mid; else lo = mid + 1; }
+    return (long long)(lo >= n ? n - 1 : lo);
+}
+
+// mode 0: injected uniforms; 1: systematic from injected u0; 2: Philox multinomial; 3: Philox systematic
+template <typename Out>
+__global__ void __launch_bounds__(256) search_kernel(const double* __restrict__ S, size_t n, size_t n_draws, int mode, const double* __restrict__ uniforms,
+                                                     uint64_t seed, uint64_t gid_offset, uint32_t t, Out* __restrict__ parents) {
+    double u0 = 0.;
+    if (mode == 1) u0 = uniforms[0];
+    if (mode == 3) { Stream s(seed, 0, t, P_RESAMPLE_OFFSET); uint4 x = s.block(0); u0 = u01_co64(x.x, x.y); }
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n_draws; i += (size_t)gridDim.x * 256) {
+        double u;
+        if (mode == 0) u = uniforms[i];
+        else if (mode == 2) { Stream s(seed, gid_offset + i, t, P_RESAMPLE_U); uint4 x = s.block(0); u = u01_co64(x.x, x.y); }
+        else u = (u0 + (double)i) / (double)n_draws;
+        parents[i] = (Out)search_cumsum(S, n, u);
+    }
+}
+
+// integer multinomial: materialised integer cumsum + per-output search
+template <typename Real>
+__global__ void __launch_bounds__(kScanThreads) fixed_cumsum_kernel(FixedArgs<Real> a, unsigned long long* __restrict__ C) {
+    // single pass with the same look-back machinery, writing inclusive integer prefix sums
+    __shared__ ScanShared sh;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) sh.tile = atomicAdd(&a.stats->ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = sh.tile;
+    const float mx = (float)a.stats->max;
+    unsigned long long q[kScanRounds][4], excl[kScanRounds];
+    const unsigned long long aggregate = tile_local_scan<Real>(a, sh, tile, mx, q, excl);
+    if (tid < 32) {
+        unsigned long long exclusive = 0;
+        if (tile == 0) { if (lane == 0) atomicExch(&a.desc[0], kDescInclusive | aggregate); }
+        else {
+            if (lane == 0) atomicExch(&a.desc[tile], kDescAggregate | aggregate);
+            long long pred = (long long)tile - 1 - lane;
+            while (true) {
+                unsigned long long d = kDescInclusive;
+                if (pred >= 0) { volatile unsigned long long* p = a.desc + pred; do { d = *p; } while ((d >> 62) == 0ull); }
+                unsigned int incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
+                unsigned long long v = d & kDescMask;
+                int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+                if (lane > first) v = 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                exclusive += v;
+                if (incl_mask) break;
+                pred -= 32;
+            }
+            if (lane == 0) atomicExch(&a.desc[tile], kDescInclusive | (exclusive + aggregate));
+        }
+        if (lane == 0) sh.tile_excl = exclusive;
+    }
+    __syncthreads();
+    const unsigned long long tile_excl = sh.tile_excl;
+#pragma unroll
+    for (int r = 0; r < kScanRounds; ++r) {
+        size_t idx = (size_t)tile * kScanTile + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
+        unsigned long long c = tile_excl + excl[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { c += q[r][j]; if (idx + j < a.n) C[idx + j] = c; }
+    }
+    if (tile == 0 && tid == 0) {
+        DeviceStats* st = a.stats;
+        double lse = (double)mx + log((double)st->W) - (double)a.kbits * 0.6931471805599453;
+        st->lse = lse; st->ess_stale = st->ess;
+        if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
+        st->resampled = 1;
+    }
+}
+
+static __global__ void __launch_bounds__(256) fixed_multinomial_search_kernel(const unsigned long long* __restrict__ C, size_t n, size_t n_draws, const DeviceStats* st,
+                                                                       uint64_t seed, uint64_t gid_offset, uint32_t t, int32_t* __restrict__ anc) {
+    const unsigned long long W = st->W;
+    for (size_t j = (size_t)blockIdx.x * 256 + threadIdx.x; j < n_draws; j += (size_t)gridDim.x * 256) {
+        if (W == 0ull) { anc[j] = (int32_t)j; continue; }
+        Stream s(seed, gid_offset + j, t, P_RESAMPLE_U);
+        uint4 x = s.block(0);
+        unsigned long long T = __umul64hi(((unsigned long long)x.x << 32) | x.y, W);
+        size_t lo = 0, hi = n;   // min{k : C_k > T}
+        while (lo < hi) { size_t mid = (lo + hi) >> 1; if (C[mid] > T) hi = mid; else lo = mid + 1; }
+        anc[j] = (int32_t)(lo >= n ? n - 1 : lo);
+    }
+}
+
+// ================================================================================================
+// K6 stand-alone gather (trace clone loop, particle_filter.rs:109-113) -- only the live state (quirk Q11)
+// ================================================================================================
+template <typename Real>
+__global__ void __launch_bounds__(256) gather_kernel(const Real* __restrict__ in, Real* __restrict__ out, const int32_t* __restrict__ anc, size_t n, size_t ld, int D) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        size_t src = (size_t)anc[i];
+        for (int d = 0; d < D; ++d) out[(size_t)d * ld + i] = __ldg(in + (size_t)d * ld + src);
+    }
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) fill_kernel(Real* p, size_t n, Real v) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) p[i] = v;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(256) to_f64_kernel(const Real* __restrict__ in, double* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (double)in[i];
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) from_f64_kernel(const double* __restrict__ in, Real* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (Real)in[i];
+}
+static __global__ void __launch_bounds__(256) i32_to_i64_kernel(const int32_t* __restrict__ in, long long* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (long long)in[i];
+}
+
+}  // namespace mpl

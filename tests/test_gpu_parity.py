@@ -1,0 +1,320 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Integer / index results are bit-exact; floating point within the tolerance BASELINE.json's north_star states
+(1e-9 relative in fp64, 1e-4 in fp32), written beside each assert."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_golden import HMM3, hmm_params
+from test_oracle import lgssm_data
+
+pytestmark = pytest.mark.gpu
+
+m = pytest.importorskip("modppl_b200")
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(1.0, np.abs(np.asarray(b))))
+
+
+# ------------------------------------------------------------------------------------------------- log-densities
+def test_logpdf_known_answers_on_device():           # tests/dists.rs:120-176, tests/test_pointed.rs:20
+    P = m.parity
+    assert abs(P.logpdf("normal", 1.4, [0.9, 0.5]) - -0.7257913526447272) <= 1e-9
+    assert abs(P.logpdf("normal", 2.8, [1.8, 1.0]) - -1.4189385332046727) <= 1e-9
+    assert abs(P.logpdf("normal", -3.14, [8.0, 20.0]) - -4.069795306758664) <= 1e-9
+    assert abs(P.logpdf("mvnormal2", [1.1, 5.8], [1.3, 5.6, 1.0, -0.81, -0.81, 2.5]) - -2.1642100746383357) <= 1e-9
+    assert abs(P.logpdf("mvnormal2", [30.1, -46.8], [0.0, 6.0, 496.0, 0.13, 0.13, 500.0]) - -11.750458919763666) <= 1e-9
+    assert abs(P.logpdf("bernoulli", 1.0, [0.11]) - math.log(0.11)) <= 1e-15
+    assert abs(P.logpdf("bernoulli", 0.0, [0.11]) - math.log(0.89)) <= 1e-15
+    assert abs(P.logpdf("uniform", 0.9, [0.5, 3.14]) - math.log(1 / 2.64)) <= 1e-15
+    assert P.logpdf("uniform", 0.4, [0.5, 3.14]) == -math.inf
+    assert abs(P.logpdf("uniform_2d", [1.0, -0.5], [0.0, 2.5, -1.0, 0.25]) - -1.1394342831883648) <= 1e-15
+    assert P.logpdf("uniform_2d", [-1.0, 0.0], [0.0, 2.5, -1.0, 0.25]) == -math.inf
+
+
+# ------------------------------------------------------------------------------------------------- K3 weight reduction
+@pytest.mark.parametrize("n", [1, 7, 1000, 100003, 1 << 20])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_logsumexp_stats(n, dtype):
+    rng = np.random.default_rng(n)
+    lw = (rng.normal(size=n) * 25).astype(dtype)
+    lse, ess, mx = m.parity.logsumexp_stats(lw)
+    lw64 = lw.astype(np.float64)
+    ref = O.logsumexp(lw64)
+    ref_ess = math.exp(-O.logsumexp(2.0 * (lw64 - ref)))
+    tol = 1e-9 if dtype == np.float64 else 1e-4
+    assert abs(lse - ref) <= tol * max(1.0, abs(ref))
+    assert abs(ess - ref_ess) <= tol * 10 * ref_ess
+    assert mx == lw64.max()
+
+
+def test_logsumexp_stats_guards():                   # lib.rs:36-37 and quirk Q9
+    lse, ess, mx = m.parity.logsumexp_stats(np.full(100, -np.inf))
+    assert lse == -math.inf
+    lw = np.array([0.0, np.nan, -1.0, -np.inf])
+    lse, _, _ = m.parity.logsumexp_stats(lw)
+    assert abs(lse - math.log(1 + math.exp(-1))) < 1e-12     # NaN counted as -inf
+
+
+# ------------------------------------------------------------------------------------------------- K4 exact resampling
+def weight_cases(n, rng):
+    yield "lognormal", np.exp(rng.normal(size=n) * 3)
+    yield "uniform", rng.random(n)
+    w = rng.random(n) * 1e-12
+    w[n // 3] = 1.0
+    yield "one_dominant", w
+    w = rng.random(n)
+    w[: n // 2] = 0.0
+    yield "leading_zeros", w
+    yield "tiny_then_big", np.concatenate([np.full(n // 2, 1e-300), rng.random(n - n // 2)])
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 50000])
+def test_cumsum_sequential_bit_exact(n):
+    rng = np.random.default_rng(10 + n)
+    for name, w in weight_cases(max(n, 3), rng):
+        p = (w / w.sum())[:n] if n >= 3 else (w / w.sum())[:n]
+        got = m.parity.cumsum_sequential(p)
+        assert np.array_equal(got, O.cumsum_sequential(p)), name
+
+
+@pytest.mark.parametrize("scheme", [0, 1])
+@pytest.mark.parametrize("n", [1, 5, 1000, 65537])
+def test_resample_indices_bit_exact(scheme, n):
+    rng = np.random.default_rng(20 + n + scheme)
+    for name, w in weight_cases(max(n, 3), rng):
+        p = w[:n] / w[:n].sum() if w[:n].sum() > 0 else np.full(n, 1.0 / n)
+        u = rng.random(n if scheme == 0 else 1)
+        got = m.parity.resample_indices(p, u, n_draws=n, scheme=scheme)
+        ref = O.resample_indices(p, u, n_draws=n, scheme=scheme)
+        assert np.array_equal(got, ref), (name, np.nonzero(got != ref)[0][:5])
+
+
+def test_resample_indices_edge_cases():              # quirk Q2: u == 0 and u beyond the running total are clamped
+    p = np.array([0.0, 0.0, 1.0, 0.0])
+    assert list(m.parity.resample_indices(p, [0.0, 0.5, 1.0, 1.5])) == [0, 2, 2, 3]
+    assert list(m.parity.resample_indices([1.0], [0.3, 0.0])) == [0, 0]
+    # more draws than particles / fewer draws than particles (importance_resampling, importance.rs:47)
+    rng = np.random.default_rng(1)
+    p = rng.random(100); p /= p.sum()
+    u = rng.random(1000)
+    assert np.array_equal(m.parity.resample_indices(p, u), O.resample_indices(p, u))
+    assert np.array_equal(m.parity.resample_indices(p, u[:10]), O.resample_indices(p, u[:10]))
+
+
+def test_resample_indices_full_size_properties():    # 2^24 (BASELINE config 4): size-independent properties + sampled oracle check
+    n = 1 << 24
+    rng = np.random.default_rng(99)
+    w = np.exp(rng.normal(size=n))
+    p = w / w.sum()
+    u = rng.random(n)
+    got = m.parity.resample_indices(p, u)
+    assert got.min() >= 0 and got.max() < n
+    S = np.cumsum(p)                                   # numpy's f64 cumsum is the same sequential loop
+    ref = np.minimum(np.searchsorted(S, u, side="left"), n - 1)
+    assert np.array_equal(got, ref)
+    sy = m.parity.resample_indices(p, [0.37], n_draws=n, scheme=1)
+    assert np.all(np.diff(sy) >= 0)                    # sortedness
+    counts = np.bincount(sy, minlength=n)
+    assert np.all(np.abs(counts - n * p) < 1.0 + 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------- K5 integer resampling
+@pytest.mark.parametrize("n", [1, 3, 1000, 4096, 4097, 100000, (1 << 20) + 5])
+def test_fixed_systematic_bit_exact(n):
+    rng = np.random.default_rng(30 + n)
+    cases = {
+        "normal": rng.normal(size=n) * 2,
+        "flat": np.zeros(n),
+        "peaked": np.where(np.arange(n) == n // 2, 0.0, -60.0),
+        "half_dead": np.where(rng.random(n) < 0.5, -np.inf, rng.normal(size=n)),
+        "heavy_tail": -np.abs(rng.standard_cauchy(size=n)) * 5,
+    }
+    for name, lw in cases.items():
+        lw = lw.astype(np.float32)
+        if not np.isfinite(lw).any():
+            lw[0] = 0.0
+        anc, lse, W = m.parity.fixed_resample(lw, scheme=2, seed=77, t=5)
+        ref_anc, ref_lse, ref_W = O.fixed_systematic(lw, O.resample_offset_word(77, 5))
+        assert W == ref_W, name
+        assert np.array_equal(anc, ref_anc), (name, np.nonzero(anc != ref_anc)[0][:5])
+        assert abs(lse - ref_lse) <= 1e-12 * max(1.0, abs(ref_lse))
+
+
+@pytest.mark.parametrize("n", [1, 1000, 70000])
+def test_fixed_multinomial_bit_exact(n):
+    rng = np.random.default_rng(40 + n)
+    lw = (rng.normal(size=n) * 2).astype(np.float32)
+    anc, lse, W = m.parity.fixed_resample(lw, scheme=3, seed=5, t=2)
+    ref_anc, ref_lse, ref_W = O.fixed_multinomial(lw, 5, 2)
+    assert W == ref_W and np.array_equal(anc, ref_anc)
+
+
+def test_fixed_systematic_full_size_properties():
+    n = 1 << 24
+    rng = np.random.default_rng(7)
+    lw = (rng.normal(size=n) * 1.5).astype(np.float32)
+    anc, lse, W = m.parity.fixed_resample(lw, scheme=2, seed=3, t=9)
+    assert np.all(np.diff(anc) >= 0) and anc[0] >= 0 and anc[-1] < n
+    w = np.exp(lw.astype(np.float64) - float(lw.max()))
+    counts = np.bincount(anc, minlength=n)
+    assert counts.sum() == n
+    assert np.all(np.abs(counts - n * w / w.sum()) < 1.0 + 1e-3)
+    assert abs(lse - (float(lw.max()) + math.log(w.sum()))) < 1e-5
+    # a degenerate population: one particle takes all 2^24 offspring (exercises the heavy-tile path)
+    lw2 = np.full(n, -80.0, dtype=np.float32)
+    lw2[12345678] = 0.0
+    anc2, _, _ = m.parity.fixed_resample(lw2, scheme=2, seed=3, t=9)
+    assert np.all(anc2 == 12345678)
+
+
+# ------------------------------------------------------------------------------------------------- K1/K2 extend + whole filter
+MODELS = {
+    "lgssm4": ([0.1, 0.5, 1.0], lambda T: lgssm_data(T)),
+    "spiral": ([0.1, 0.4, 0.2, 0.001], lambda T: np.stack([0.4 * np.cos(0.3 * np.arange(T)), 0.4 * np.sin(0.3 * np.arange(T))], 1)),
+    "sv": ([-1.024, 0.9702, 0.178], lambda T: np.random.default_rng(5).normal(size=(T, 1)) * 0.6),
+    "hmm": (hmm_params(), lambda T: np.array(HMM3["obs"] * (T // 4 + 1), float)[:T, None]),
+}
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_init_and_step_match_oracle(name, dtype):
+    params, gen = MODELS[name]
+    ys = gen(3)
+    n = 5000
+    tol = 1e-9 if dtype == "f64" else 1e-4
+    ps = m.ParticleSystem(m.Model(name, params), n, seed=21, dtype=dtype)
+    ref = O.OraclePS(name, params, n, dtype=dtype, seed=21)
+    ps.init_step(ys[0]); ref.init_step(ys[0])
+    assert rel(ps.traces, ref.traces) <= tol
+    assert rel(ps.log_weights, ref.log_weights) <= tol
+    # inject the oracle's state so that one step is compared from identical inputs (weights accumulate: particle_filter.rs:81)
+    ps.write_state(ref.traces); ps.write_log_weights(ref.log_weights)
+    ps.step(ys[1]); ref.step(ys[1])
+    assert rel(ps.traces, ref.traces) <= tol
+    assert rel(ps.log_weights, ref.log_weights) <= tol * 10
+    assert abs(ps.log_marginal_likelihood_estimate() - ref.log_marginal_likelihood_estimate()) <= tol * 10
+    assert abs(ps.effective_sample_size(False) - ref.effective_sample_size(False)) <= 1e-3 * ref.effective_sample_size(False) if dtype == "f32" else 1e-8 * n
+
+
+@pytest.mark.parametrize("scheme,dtype", [(0, "f64"), (1, "f64"), (2, "f32"), (3, "f32"), (2, "f64")])
+def test_resample_inside_particle_system(scheme, dtype):
+    n = 3000
+    params, gen = MODELS["lgssm4"]
+    ys = gen(3)
+    ps = m.ParticleSystem(m.lgssm4(*params), n, seed=8, dtype=dtype)
+    ref = O.OraclePS("lgssm4", params, n, dtype=dtype, seed=8)
+    ps.init_step(ys[0]); ref.init_step(ys[0])
+    pre_state, pre_lw = ref.traces, ref.log_weights
+    # identical weights and states in both, then resample
+    ps.write_state(pre_state); ps.write_log_weights(pre_lw)
+    assert abs(ps.effective_sample_size(True) - 1.0 / n) < 1e-12          # quirk Q1
+    lse = ps.resample(scheme)
+    ref_lse = ref.resample(scheme)
+    assert abs(lse - ref_lse) <= (1e-9 if dtype == "f64" and scheme < 2 else 2e-6) * max(1.0, abs(ref_lse))
+    assert np.array_equal(ps.parents, ref.parents)                         # ancestors: bit-exact
+    gathered = ps.traces
+    assert np.array_equal(gathered, ref.traces)                            # gathered state: bit-exact copy
+    assert np.all(ps.log_weights == 0.0)                                   # particle_filter.rs:114
+    assert abs(ps.effective_sample_size(False) - n) < 1e-9
+    assert abs(ps.log_marginal_likelihood_estimate() - ref.log_marginal_likelihood_estimate()) <= 2e-6
+    # the fused path (step right after resample gathers through the pending ancestors) == step from the materialised state
+    fused = m.ParticleSystem(m.lgssm4(*params), n, seed=8, dtype=dtype)
+    fused.init_step(ys[0]); fused.write_state(pre_state); fused.write_log_weights(pre_lw)
+    fused.resample(scheme)
+    fused.step(ys[1])
+    ps.step(ys[1])
+    assert np.array_equal(fused.traces, ps.traces)
+    assert np.array_equal(fused.log_weights, ps.log_weights)
+
+
+def test_particle_filter_hmm_end_to_end():            # tests/particle_filter.rs:35-79 through the drop-in API
+    expected = math.log(O.hmm_forward(HMM3["prior"], HMM3["emission"], HMM3["transition"], HMM3["obs"]))
+    assert abs(expected - -4.87645083351704) < 1e-12
+    model = m.hmm(HMM3["prior"], HMM3["emission"], HMM3["transition"])
+    for scheme, dtype in [(m.MULTINOMIAL, "f64"), (m.SYSTEMATIC_FIXED, "f32")]:
+        f = m.ParticleSystem(model, 10000, seed=1000, dtype=dtype)
+        obs = HMM3["obs"]
+        f.init_step([obs[0]])
+        for o in obs[1:]:
+            f = f.step([o])
+            f.effective_sample_size()
+            f.resample(scheme)
+        assert abs(f.log_marginal_likelihood_estimate() - expected) <= 0.03
+        # and the oracle run with the same seed gives the same estimate (same Philox stream, same ancestors)
+        r = O.OraclePS("hmm", hmm_params(), 10000, dtype=dtype, seed=1000)
+        r.init_step([obs[0]])
+        for o in obs[1:]:
+            r.step([o]); r.resample(scheme)
+        assert abs(f.log_marginal_likelihood_estimate() - r.log_marginal_likelihood_estimate()) <= 1e-6
+
+
+def test_spiral_filter_config1_tracks_oracle():       # config 1: spiral model, N = 1000, T = 100, fp64, multinomial
+    T, n = 100, 1000
+    th = 2 * math.pi * np.arange(T) / T + 0.7
+    ys = np.stack([0.4 * np.cos(th), 0.4 * np.sin(th)], 1)
+    f = m.ParticleSystem(m.spiral_model(), n, seed=1, dtype="f64")
+    r = O.OraclePS("spiral", [0.1, 0.4, 0.2, 0.001], n, dtype="f64", seed=1)
+    f.init_step(ys[0]); r.init_step(ys[0])
+    f.resample(m.MULTINOMIAL); r.resample(0)
+    same = True
+    for t in range(1, T):
+        f.step(ys[t]); r.step(ys[t])
+        lf, lr = f.resample(m.MULTINOMIAL), r.resample(0)
+        if same and np.array_equal(f.parents, r.parents):
+            assert abs(lf - lr) <= 1e-9 * max(1.0, abs(lr))
+            assert rel(f.traces, r.traces) <= 1e-9
+        else:
+            same = False     # a 1-ulp exp/sincos difference flipped one ancestor: the runs are now different samples
+    assert t == T - 1
+    assert abs(f.log_marginal_likelihood_estimate() - r.log_marginal_likelihood_estimate()) < (1e-6 if same else 25.0)
+
+
+def test_lgssm_filter_vs_kalman_large():              # config 4 shape at 2^20 particles, T = 30: log-ML within MC error of Kalman
+    T, n = 30, 1 << 20
+    ys = lgssm_data(T)
+    truth = O.kalman_lml_lgssm4(0.1, 0.5, 1.0, ys)
+    f = m.ParticleSystem(m.lgssm4(), n, seed=3, dtype="f32")
+    f.init_step(ys[0]); f.resample(m.SYSTEMATIC_FIXED)
+    for y in ys[1:]:
+        f.step(y); f.resample(m.SYSTEMATIC_FIXED, sync=False)
+    est = f.log_marginal_likelihood_estimate()
+    assert abs(est - truth) < 0.35          # std ~0.07 at this N (0.4 at N = 2e4 scales with 1/sqrt(N))
+    st = f.traces
+    assert np.all(np.isfinite(st))
+    # device-resident loop gives the same answer as the call-per-step API
+    g = m.ParticleSystem(m.lgssm4(), n, seed=3, dtype="f32")
+    g.upload_observations(ys)
+    g.run(0, T, m.SYSTEMATIC_FIXED)
+    assert g.log_marginal_likelihood_estimate() == est
+    assert np.array_equal(g.traces, st)
+
+
+def test_shard_invariance_of_rng():                   # Philox keyed by global id => shards reproduce the whole
+    n, G = 8192, 4
+    ys = lgssm_data(2)
+    whole = m.ParticleSystem(m.lgssm4(), n, seed=5, dtype="f32")
+    whole.init_step(ys[0])
+    W = whole.traces
+    for g in range(G):
+        part = m.ParticleSystem(m.lgssm4(), n // G, seed=5, dtype="f32", gid_offset=g * (n // G), n_global=n)
+        part.init_step(ys[0])
+        assert np.array_equal(part.traces, W[:, g * (n // G):(g + 1) * (n // G)])
+
+
+def test_error_paths():
+    ps = m.ParticleSystem(m.lgssm4(), 100)
+    with pytest.raises(m.MplError):
+        ps.step([0.0, 0.0])                 # step before init_step
+    with pytest.raises(m.MplError):
+        ps.init_step([0.0])                 # observation too short
+    ps.init_step([0.0, 0.0])
+    with pytest.raises(m.MplError):
+        ps.resample(17)
+    ps.write_log_weights(np.full(100, -np.inf))
+    with pytest.raises(m.MplError, match="-inf"):
+        ps.resample(m.SYSTEMATIC_FIXED)
