@@ -359,10 +359,10 @@ __device__ __forceinline__ unsigned long long count_below(unsigned long long C, 
     return e + 1;
 }
 
-struct ScanShared {
+struct __align__(16) ScanShared {
     unsigned long long warp_tot[kScanRounds][kScanThreads / 32];
     unsigned long long tile_excl;
-    unsigned int nloc[kScanTile];             // inclusive offspring counts, relative to the tile's first output slot
+    __align__(16) unsigned int nloc[kScanTile];             // inclusive offspring counts, relative to the tile's first output slot
     __align__(16) unsigned short head[kScanTile];   // expansion buffer: (local parent + 1) at the first slot of each run
     unsigned int warp_max[kScanThreads / 32];
     unsigned int carry;
