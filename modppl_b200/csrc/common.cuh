@@ -64,12 +64,26 @@ __host__ __device__ __forceinline__ double u01_oc64(uint32_t hi, uint32_t lo) { 
 __host__ __device__ __forceinline__ float u01_co32(uint32_t x) { return (float)(x >> 8) * 0x1.0p-24f; }
 __host__ __device__ __forceinline__ float u01_oc32(uint32_t x) { return (float)((x >> 8) + 1) * 0x1.0p-24f; }
 
+// fp32 Box-Muller on the SFU path (the extend kernel is instruction-issue bound, not HBM bound, with libm-grade
+// logf/sincospif): -2 ln(u1) from MUFU.LG2 with a 3-term series where u1 is within 2^-6 of 1 (there MUFU.LG2's
+// absolute error would dominate the tiny result), sqrt.approx, MUFU.SIN/COS on an argument folded into [-pi, pi).
+// Absolute error of a normal deviate ~1e-6, far inside the 1e-4 fp32 parity tolerance.
+__device__ __forceinline__ float neg2log_fast(float u1) {
+    float l = __log2f(u1) * -1.3862943611198906f;                    // -2 ln2 lg2(u1)
+    float v = 1.0f - u1;                                              // exact
+    float s = v * fmaf(v, fmaf(v, 0.66666667f, 1.0f), 2.0f);         // -2 ln(1 - v) = 2v + v^2 + (2/3) v^3 + O(v^4)
+    return (v < 0.015625f) ? s : l;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void box_muller(float u1, float u2, float& z0, float& z1) {
-    float r = sqrtf(-2.f * logf(u1));
-    float s, c;
-    sincospif(2.f * u2, &s, &c);
-    z0 = r * c;
-    z1 = r * s;
+    float r = -sqrt_approx(neg2log_fast(u1));
+    float a = fmaf(u2, 6.283185307179586f, -3.141592653589793f);    // 2 pi u2 - pi in [-pi, pi)
+    z0 = r * __cosf(a);                                               // cos(2 pi u2) = -cos(a)
+    z1 = r * __sinf(a);
 }
 __device__ __forceinline__ void box_muller(double u1, double u2, double& z0, double& z1) {
     double r = sqrt(-2. * log(u1));
@@ -174,11 +188,16 @@ struct Lse3 {
 };
 template <typename Acc>
 __host__ __device__ __forceinline__ Lse3<Acc> lse3_identity() { return Lse3<Acc>{(Acc)-INFINITY, (Acc)0, (Acc)0}; }
+// exp for weight statistics: fp32 uses MUFU.EX2 (the sums carry ~1e-6 relative error in fp32 anyway; the integer
+// resampler never reads them), fp64 stays libm-grade.
+__device__ __forceinline__ float stat_exp(float x) { return __expf(x); }
+__device__ __forceinline__ double stat_exp(double x) { return exp(x); }
+
 template <typename Acc>
 __device__ __forceinline__ Lse3<Acc> lse3_combine(const Lse3<Acc>& a, const Lse3<Acc>& b) {
     Acc m = fmax(a.m, b.m);   // fmax ignores NaN like f64::max (lib.rs:35)
     if (m == (Acc)-INFINITY) return Lse3<Acc>{m, (Acc)0, (Acc)0};
-    Acc ea = exp(a.m - m), eb = exp(b.m - m);
+    Acc ea = stat_exp(a.m - m), eb = stat_exp(b.m - m);
     return Lse3<Acc>{m, a.s * ea + b.s * eb, a.s2 * ea * ea + b.s2 * eb * eb};
 }
 template <typename Acc>
@@ -232,12 +251,14 @@ __device__ __forceinline__ uint64_t fixed_weight(float d, int kbits) {
     float y = __fmul_rn(d, 1.44269504088896341f);
     float n = rintf(y);
     float f = __fsub_rn(y, n);
-    float p = exp2_poly(f);
-    int shift = kbits + (int)n;
-    if (shift < -2) return 0;
-    // p * 2^shift, exactly, then round-half-even to integer
-    double v = (double)p * __longlong_as_double((long long)(1023 + shift) << 52);
-    return (uint64_t)__double2ull_rn(v);
+    float p = exp2_poly(f);                                  // in [0.70, 1.42]
+    // floor(p * 2^(kbits + n) + 1/2) in integer arithmetic: p = m * 2^(e - 23), m a 24-bit integer
+    uint32_t bits = __float_as_uint(p);
+    uint32_t m = (bits & 0x7fffffu) | 0x800000u;
+    int s = kbits + (int)n + (int)(bits >> 23) - 127 - 23;
+    if (s >= 0) return (uint64_t)m << s;
+    if (s < -25) return 0;
+    return (uint64_t)((m + (1u << (-s - 1))) >> (-s));
 }
 inline int fixed_kbits(uint64_t n_total) {
     int lg = 0;

@@ -20,7 +20,7 @@ template <typename Real>
 struct Lgssm4 {
     static constexpr int D = 4;
     static constexpr int NOBS = 2;
-    Real q, r, x0, ln_r;
+    Real q, r, x0, ln_r, inv_r;
     __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
         Real z[4];
         draw_normals<4>(s, 0, z);
@@ -36,7 +36,7 @@ struct Lgssm4 {
         Real lw = 0;
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
-            Real zz = ((Real)obs.v[d] - x[d]) / r;
+            Real zz = ((Real)obs.v[d] - x[d]) * inv_r;                  // z = (x - mu) / std with 1/std hoisted
             lw += -(zz * zz + (Real)1.8378770664093453) / 2 - ln_r;   // normal.rs:13-17
         }
         return lw;

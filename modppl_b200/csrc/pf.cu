@@ -1,4 +1,5 @@
 // pf.cu -- ParticleSystem host driver + C ABI (reference modppl/src/inference/particle_filter.rs:8-121).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -29,6 +30,7 @@ template <typename Real> Lgssm4<Real> make_lgssm4(const mpl_model& m) {
     f.r = (Real)(p.size() > 1 ? p[1] : 0.5);
     f.x0 = (Real)(p.size() > 2 ? p[2] : 1.0);
     f.ln_r = (Real)std::log((double)f.r);
+    f.inv_r = (Real)1 / f.r;
     return f;
 }
 template <typename Real> Spiral<Real> make_spiral(const mpl_model& m) {
@@ -221,7 +223,7 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
     const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
     {
         ScopedLaunch sl(ps, "fixed_reduce");
-        fixed_reduce_kernel<Real><<<ps->grid_reduce, 256, 0, ps->stream>>>(a, num_tiles);
+        fixed_reduce_kernel<Real><<<(unsigned int)std::min<size_t>(num_tiles, (size_t)kNumSMs * 8), kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (scheme == MPL_RESAMPLE_SYSTEMATIC_FIXED) {

@@ -6,7 +6,7 @@
 //                        reference modppl/src/inference/particle_filter.rs:65-69,76-82.
 //   weight_reduce_kernel K3 stand-alone: lib.rs:34-45 + particle_filter.rs:27-35,98-100 in one pass.
 //   fixed_reduce_kernel / fixed_scan_kernel / fixed_overflow_kernel
-//                        K5: integer-weight systematic resampling -- quantise, decoupled-lookback prefix scan,
+//                        K5: integer-weight systematic resampling -- quantise, two-level exact integer prefix scan,
 //                        in-tile expansion (run heads + max-scan in shared memory) that writes ancestors coalesced.
 //   normalize / cumsum_seq / search kernels
 //                        K4: the reference's multinomial routine (categorical.rs:22-32) with its SEQUENTIAL f64
@@ -32,7 +32,7 @@ struct DeviceStats {
     long long t;                   // next kernel time index (device copy, for mpl_ps_run)
     unsigned int max_ordered;      // atomicMax target for the exact global max (float path)
     unsigned int blocks_done;      // last-block-done counter of the extend epilogue
-    unsigned int ticket;           // tile ticket of the scan
+    unsigned int ticket;           // (unused)
     unsigned int overflow_count;
     int degenerate;                // all weights -inf seen
     int resampled;                 // 1: ancestors pending (next extend gathers, weights are zero)
@@ -41,7 +41,7 @@ struct DeviceStats {
 };
 
 struct OverflowEntry {
-    unsigned long long tile_excl;
+    unsigned long long rem;
     unsigned long long n_start;
     unsigned int tile;
     unsigned int total;
@@ -82,7 +82,7 @@ struct ExtendArgs {
 constexpr int kExtendThreads = 256;
 
 template <class Model, typename Real, int MODE>
-__global__ void __launch_bounds__(kExtendThreads) pf_extend_kernel(ExtendArgs<Real> a, Model model) {
+__global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs<Real> a, Model model) {
     constexpr int D = Model::D;
     constexpr int V = VecOf<Real>::N;
     typedef Real Acc;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kExtendThreads) pf_extend_kernel(ExtendArgs<Re
         if (m > (Acc)-INFINITY) {
             Acc s1 = 0, s2 = 0;
 #pragma unroll
-            for (int v = 0; v < V; ++v) { Acc e = exp((Acc)w[v] - m); s1 += e; s2 += e * e; }
+            for (int v = 0; v < V; ++v) { Acc e = stat_exp((Acc)w[v] - m); s1 += e; s2 += e * e; }
             run = lse3_combine(run, Lse3<Acc>{m, s1, s2});
         }
     }
@@ -247,11 +247,6 @@ __global__ void __launch_bounds__(256) weight_reduce_kernel(const Real* __restri
 // ================================================================================================
 // K5: integer-weight systematic resampling
 // ================================================================================================
-constexpr int kScanThreads = 256;
-constexpr int kScanRounds = 4;
-constexpr int kScanTile = kScanThreads * 4 * kScanRounds;   // 4096 particles per tile
-constexpr unsigned int kHeavyCap = 32u * kScanTile;        // tiles with more offspring than this go to the overflow pass
-constexpr unsigned long long kDescAggregate = 1ull << 62, kDescInclusive = 2ull << 62, kDescMask = (1ull << 62) - 1;
 
 template <typename Real>
 struct FixedArgs {
@@ -300,68 +295,123 @@ __device__ __forceinline__ void load_q4<double>(const double* lw, size_t idx, si
     for (int j = 0; j < 4; ++j) q[j] = (idx + j < n) ? fixed_weight(__fsub_rn((float)w[j], mx), kbits) : 0ull;
 }
 
-// R1: W = sum of integer weights (exact, order-independent); also resets the scan's descriptors.
+// R1: per-tile integer weight sums; the last block to finish turns them into exclusive tile prefixes (in place, in
+// `desc`) and the grand total W.  Integer addition is associative, so W and every prefix are exact and independent of
+// the order in which blocks run (and of how particles are sharded).  One tile (kScanTile particles) per block.
+constexpr int kScanThreads = 256;
+constexpr int kScanRounds = 4;
+constexpr int kScanTile = kScanThreads * 4 * kScanRounds;   // 4096 particles per tile
+constexpr unsigned int kHeavyCap = 32u * kScanTile;        // tiles with more offspring than this go to the overflow pass
+
 template <typename Real>
-__global__ void __launch_bounds__(256) fixed_reduce_kernel(FixedArgs<Real> a, size_t num_tiles) {
+__global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Real> a, unsigned int num_tiles) {
     if (a.dynamic && !a.stats->do_resample) return;
-    const size_t gtid = (size_t)blockIdx.x * 256 + threadIdx.x;
-    for (size_t i = gtid; i < num_tiles; i += (size_t)gridDim.x * 256) a.desc[i] = 0ull;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float mx = (float)a.stats->max;
-    unsigned long long sum = 0;
-    for (size_t idx = gtid * 4; idx < a.n; idx += (size_t)gridDim.x * 256 * 4) {
-        unsigned long long q[4];
-        load_q4<Real>(a.lw, idx, a.n, mx, a.kbits, q);
-        sum += q[0] + q[1] + q[2] + q[3];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __shared__ unsigned long long ws[8];
+    __shared__ unsigned long long ws[kScanThreads / 32];
+    __shared__ unsigned long long carry_s;
     __shared__ bool is_last;
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long b = 0;
-        for (int i = 0; i < 8; ++i) b += ws[i];
-        a.partials[blockIdx.x] = b;
+    for (unsigned int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        unsigned long long sum = 0;
+        const size_t tile_base = (size_t)tile * kScanTile;
+#pragma unroll
+        for (int r = 0; r < kScanRounds; ++r) {
+            size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
+            if (idx < a.n) {
+                unsigned long long q[4];
+                load_q4<Real>(a.lw, idx, a.n, mx, a.kbits, q);
+                sum += q[0] + q[1] + q[2] + q[3];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __syncthreads();
+        if (lane == 0) ws[warp] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long b = 0;
+#pragma unroll
+            for (int i = 0; i < kScanThreads / 32; ++i) b += ws[i];
+            a.desc[tile] = b;
+        }
+    }
+    if (tid == 0) {
         __threadfence();
         is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
+        carry_s = 0ull;
     }
     __syncthreads();
-    if (is_last) {
-        __threadfence();
-        unsigned long long t = 0;
-        for (unsigned int i = threadIdx.x; i < gridDim.x; i += 256) t += a.partials[i];
+    if (!is_last) return;
+    __threadfence();
+    // exclusive scan of the tile sums, 4 consecutive tiles per thread per pass
+    for (unsigned int base = 0; base < num_tiles; base += kScanThreads * 4) {
+        unsigned long long v[4], tot = 0;
+        const unsigned int first = base + tid * 4;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        for (int i = 0; i < 4; ++i) { v[i] = (first + i < num_tiles) ? a.desc[first + i] : 0ull; tot += v[i]; }
+        unsigned long long incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = t;
+        if (lane == 31) ws[warp] = incl;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long b = 0;
-            for (int i = 0; i < 8; ++i) b += ws[i];
-            DeviceStats* st = a.stats;
-            st->W = b; st->ticket = 0; st->overflow_count = 0; st->blocks_done = 0;
-        }
+        unsigned long long pre = carry_s + incl - tot, all = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) { unsigned long long x = ws[w]; if (w < warp) pre += x; all += x; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { if (first + i < num_tiles) a.desc[first + i] = pre; pre += v[i]; }
+        __syncthreads();
+        if (tid == 0) carry_s += all;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        DeviceStats* st = a.stats;
+        st->W = carry_s; st->overflow_count = 0; st->blocks_done = 0;
     }
 }
 
-// number of output slots j in [0, n_out) with j*W + U < C*n_out
-__device__ __forceinline__ unsigned long long count_below(unsigned long long C, unsigned long long W, unsigned long long U, unsigned long long n_out, double inv_w) {
+// Offspring arithmetic.  Output slot j (0 <= j < n_out) sits at integer position j*W + U (U in [0, W)); a particle whose
+// inclusive integer prefix is C owns every slot below C*n_out.  #slots below C*n_out = floor(X / W) + 1 with
+// X = C*n_out - U - 1 (0 when X < 0).  Per tile the quotient/remainder of the tile's exclusive prefix are found once,
+// exactly, in 128-bit arithmetic: X_t = Q*W + R with Q = n_start - 1 (Q = -1, R = X_t + W when X_t < 0).
+struct TileBase {
+    unsigned long long n_start;   // slots owned by everything before the tile
+    unsigned long long rem;       // R
+};
+__device__ __forceinline__ TileBase tile_base_exact(unsigned long long C, unsigned long long W, unsigned long long U, unsigned long long n_out, double inv_w) {
     u128 lhs = (u128)C * n_out;
-    if (lhs <= (u128)U) return 0ull;
-    u128 X = lhs - U - 1;   // count = floor(X / W) + 1
-    double xd = (double)C * (double)n_out - (double)U;
-    double ed = xd * inv_w;
+    if (lhs <= (u128)U) return TileBase{0ull, (unsigned long long)(lhs + W - U - 1)};
+    u128 X = lhs - U - 1;
+    double ed = ((double)C * (double)n_out - (double)U) * inv_w;
     unsigned long long e = ed <= 0. ? 0ull : (ed >= (double)n_out ? n_out : (unsigned long long)ed);
     u128 p = (u128)e * W;
     while (p > X) { --e; p -= W; }
     while (p + W <= X) { ++e; p += W; }
-    return e + 1;
+    return TileBase{e + 1, (unsigned long long)(X - p)};
+}
+// Slots owned by the tile's particles up to local inclusive prefix c: floor((R + c*n_out) / W).  fp64 gets this right
+// unless the quotient lands within 2^-16 of an integer (the estimate's error is < 2^-19 even for 2^31 offspring); only
+// then is the exact 128-bit form evaluated (a ~3e-5 fraction of particles).
+__device__ __forceinline__ unsigned int local_count(unsigned long long c, unsigned long long rem, double rem_d, unsigned long long W, double n_out_d,
+                                                    unsigned long long n_out, double inv_w) {
+    double fd = fma((double)c, n_out_d, rem_d) * inv_w;
+    double fl = floor(fd);
+    double frac = fd - fl;
+    unsigned long long f = (unsigned long long)fl;
+    if (frac < 0x1.0p-16 || frac > 1. - 0x1.0p-16) {
+        u128 y = (u128)c * n_out + rem;
+        u128 p = (u128)f * W;
+        while (p > y) { --f; p -= W; }
+        while (p + W <= y) { ++f; p += W; }
+    }
+    return (unsigned int)f;
 }
 
 struct __align__(16) ScanShared {
     unsigned long long warp_tot[kScanRounds][kScanThreads / 32];
     unsigned long long tile_excl;
+    unsigned long long rand_word;
+    TileBase base;
     __align__(16) unsigned int nloc[kScanTile];             // inclusive offspring counts, relative to the tile's first output slot
     __align__(16) unsigned short head[kScanTile];   // expansion buffer: (local parent + 1) at the first slot of each run
     unsigned int warp_max[kScanThreads / 32];
@@ -417,22 +467,19 @@ __device__ __forceinline__ unsigned long long tile_local_scan(const FixedArgs<Re
 
 // nloc[e] = (#offspring of all particles up to and including element e) - n_start
 template <typename Real>
-__device__ __forceinline__ void tile_fill_nloc(const FixedArgs<Real>& a, ScanShared& sh, unsigned long long tile_excl, unsigned long long n_start,
-                                               unsigned long long W, unsigned long long U, double inv_w,
+__device__ __forceinline__ void tile_fill_nloc(const FixedArgs<Real>& a, ScanShared& sh, const TileBase& base, unsigned long long W, double inv_w,
                                                const unsigned long long (&q)[kScanRounds][4], const unsigned long long (&excl)[kScanRounds]) {
     const int tid = threadIdx.x;
+    const double rem_d = (double)base.rem, n_out_d = (double)a.n_out;
 #pragma unroll
     for (int r = 0; r < kScanRounds; ++r) {
-        unsigned long long c = a.c_offset + tile_excl + excl[r];
-        unsigned int prev = 0;
-        bool have_prev = false;
+        unsigned long long c = excl[r];
         uint4 out;
         unsigned int* o = reinterpret_cast<unsigned int*>(&out);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             c += q[r][j];
-            if (q[r][j] == 0ull && have_prev) o[j] = prev;
-            else { o[j] = (unsigned int)(count_below(c, W, U, a.n_out, inv_w) - n_start); prev = o[j]; have_prev = true; }
+            o[j] = local_count(c, base.rem, rem_d, W, n_out_d, a.n_out, inv_w);
         }
         *reinterpret_cast<uint4*>(&sh.nloc[r * (kScanThreads * 4) + tid * 4]) = out;
     }
@@ -503,14 +550,12 @@ __device__ __forceinline__ void expand_chunk(const FixedArgs<Real>& a, ScanShare
 }
 
 template <typename Real>
-__global__ void __launch_bounds__(kScanThreads) fixed_scan_kernel(FixedArgs<Real> a, unsigned int num_tiles) {
+__global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<Real> a, unsigned int num_tiles) {
     __shared__ ScanShared sh;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     if (a.dynamic && !a.stats->do_resample) return;
-    if (tid == 0) sh.tile = atomicAdd(&a.stats->ticket, 1u);
-    __syncthreads();
-    const unsigned int tile = sh.tile;
     DeviceStats* st = a.stats;
+    const unsigned int tile = blockIdx.x;
     const unsigned long long W = st->W;
     const float mx = (float)st->max;
     if (W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors, flagged
@@ -518,45 +563,17 @@ __global__ void __launch_bounds__(kScanThreads) fixed_scan_kernel(FixedArgs<Real
         if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; }
         return;
     }
-    const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
     const double inv_w = 1. / (double)W;
-
-    unsigned long long q[kScanRounds][4], excl[kScanRounds];
-    const unsigned long long aggregate = tile_local_scan<Real>(a, sh, tile, mx, q, excl);
-
-    // ---- decoupled look-back (single pass): publish aggregate, walk predecessors, publish inclusive prefix
-    if (tid < 32) {
-        unsigned long long exclusive = 0;
-        if (tile == 0) {
-            if (lane == 0) atomicExch(&a.desc[0], kDescInclusive | aggregate);
-        } else {
-            if (lane == 0) atomicExch(&a.desc[tile], kDescAggregate | aggregate);
-            long long pred = (long long)tile - 1 - lane;
-            while (true) {
-                unsigned long long d = kDescInclusive;   // virtual tile -1: inclusive 0
-                if (pred >= 0) {
-                    volatile unsigned long long* p = a.desc + pred;
-                    do { d = *p; } while ((d >> 62) == 0ull);
-                }
-                unsigned int incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-                unsigned long long v = d & kDescMask;
-                int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
-                if (lane > first) v = 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                exclusive += v;
-                if (incl_mask) break;
-                pred -= 32;
-            }
-            if (lane == 0) atomicExch(&a.desc[tile], kDescInclusive | (exclusive + aggregate));
-        }
-        if (lane == 0) sh.tile_excl = exclusive;
+    if (tid == 0) {   // exclusive prefix of the tile (from the reduce pass) -> exact slot base of the tile
+        const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
+        sh.base = tile_base_exact(a.c_offset + a.desc[tile], W, U, a.n_out, inv_w);
     }
+    unsigned long long q[kScanRounds][4], excl[kScanRounds];
+    tile_local_scan<Real>(a, sh, tile, mx, q, excl);   // (contains the barrier that publishes sh.base)
+    const TileBase base = sh.base;
+    tile_fill_nloc<Real>(a, sh, base, W, inv_w, q, excl);
     __syncthreads();
-    const unsigned long long tile_excl = sh.tile_excl;
-    const unsigned long long n_start = count_below(a.c_offset + tile_excl, W, U, a.n_out, inv_w);
-    const unsigned long long n_end = count_below(a.c_offset + tile_excl + aggregate, W, U, a.n_out, inv_w);
-    const unsigned long long total = n_end - n_start;
+    const unsigned int total = sh.nloc[kScanTile - 1];
 
     if (tile == 0 && tid == 0) {   // scalar bookkeeping of resample(): particle_filter.rs:104-105,114
         double lse = (double)mx + log((double)W) - (double)a.kbits * 0.6931471805599453;
@@ -565,18 +582,16 @@ __global__ void __launch_bounds__(kScanThreads) fixed_scan_kernel(FixedArgs<Real
         if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
         st->resampled = 1;
     }
-    if (total == 0ull) return;
-    if (total > (unsigned long long)kHeavyCap) {
+    if (total == 0u) return;
+    if (total > kHeavyCap) {
         if (tid == 0) {
             unsigned int slot = atomicAdd(&st->overflow_count, 1u);
-            a.overflow[slot] = OverflowEntry{tile_excl, n_start, tile, (unsigned int)total};
+            a.overflow[slot] = OverflowEntry{base.rem, base.n_start, tile, total};
         }
         return;
     }
-    tile_fill_nloc<Real>(a, sh, tile_excl, n_start, W, U, inv_w, q, excl);
-    __syncthreads();
-    for (unsigned int chunk_base = 0; chunk_base < (unsigned int)total; chunk_base += kScanTile)
-        expand_chunk<Real>(a, sh, tile, n_start, chunk_base, (unsigned int)total);
+    for (unsigned int chunk_base = 0; chunk_base < total; chunk_base += kScanTile)
+        expand_chunk<Real>(a, sh, tile, base.n_start, chunk_base, total);
 }
 
 // heavy tiles (a few particles own a large share of the offspring): the whole grid expands each of them
@@ -589,14 +604,13 @@ __global__ void __launch_bounds__(kScanThreads) fixed_overflow_kernel(FixedArgs<
     if (count == 0u) return;
     const unsigned long long W = st->W;
     const float mx = (float)st->max;
-    const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
     const double inv_w = 1. / (double)W;
     for (unsigned int k = 0; k < count; ++k) {
         const OverflowEntry e = a.overflow[k];
         unsigned long long q[kScanRounds][4], excl[kScanRounds];
         __syncthreads();
         tile_local_scan<Real>(a, sh, e.tile, mx, q, excl);
-        tile_fill_nloc<Real>(a, sh, e.tile_excl, e.n_start, W, U, inv_w, q, excl);
+        tile_fill_nloc<Real>(a, sh, TileBase{e.n_start, e.rem}, W, inv_w, q, excl);
         __syncthreads();
         for (unsigned long long chunk_base = (unsigned long long)blockIdx.x * kScanTile; chunk_base < e.total; chunk_base += (unsigned long long)gridDim.x * kScanTile)
             expand_chunk<Real>(a, sh, e.tile, e.n_start, (unsigned int)chunk_base, e.total);
@@ -679,40 +693,14 @@ __global__ void __launch_bounds__(256) search_kernel(const double* __restrict__ 
 // integer multinomial: materialised integer cumsum + per-output search
 template <typename Real>
 __global__ void __launch_bounds__(kScanThreads) fixed_cumsum_kernel(FixedArgs<Real> a, unsigned long long* __restrict__ C) {
-    // single pass with the same look-back machinery, writing inclusive integer prefix sums
+    // inclusive integer prefix sums: tile prefix from the reduce pass + tile-local scan
     __shared__ ScanShared sh;
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid == 0) sh.tile = atomicAdd(&a.stats->ticket, 1u);
-    __syncthreads();
-    const unsigned int tile = sh.tile;
+    const int tid = threadIdx.x;
+    const unsigned int tile = blockIdx.x;
     const float mx = (float)a.stats->max;
     unsigned long long q[kScanRounds][4], excl[kScanRounds];
-    const unsigned long long aggregate = tile_local_scan<Real>(a, sh, tile, mx, q, excl);
-    if (tid < 32) {
-        unsigned long long exclusive = 0;
-        if (tile == 0) { if (lane == 0) atomicExch(&a.desc[0], kDescInclusive | aggregate); }
-        else {
-            if (lane == 0) atomicExch(&a.desc[tile], kDescAggregate | aggregate);
-            long long pred = (long long)tile - 1 - lane;
-            while (true) {
-                unsigned long long d = kDescInclusive;
-                if (pred >= 0) { volatile unsigned long long* p = a.desc + pred; do { d = *p; } while ((d >> 62) == 0ull); }
-                unsigned int incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2ull);
-                unsigned long long v = d & kDescMask;
-                int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
-                if (lane > first) v = 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                exclusive += v;
-                if (incl_mask) break;
-                pred -= 32;
-            }
-            if (lane == 0) atomicExch(&a.desc[tile], kDescInclusive | (exclusive + aggregate));
-        }
-        if (lane == 0) sh.tile_excl = exclusive;
-    }
-    __syncthreads();
-    const unsigned long long tile_excl = sh.tile_excl;
+    tile_local_scan<Real>(a, sh, tile, mx, q, excl);
+    const unsigned long long tile_excl = a.desc[tile];
 #pragma unroll
     for (int r = 0; r < kScanRounds; ++r) {
         size_t idx = (size_t)tile * kScanTile + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
