@@ -246,19 +246,22 @@ __device__ __forceinline__ float exp2_poly(float f) {
     return p;
 }
 __device__ __forceinline__ uint64_t fixed_weight(float d, int kbits) {
-    if (!(d > -88.0f)) return 0;   // also NaN / -inf
-    d = fminf(d, 0.f);
+    // branch-free; d = lw - max.  NaN and anything below -100 (incl. -inf) end up as 0 through the shift clamp.
+    d = fminf(fmaxf(d, -100.0f), 0.f);                       // fmaxf(NaN, x) = x
     float y = __fmul_rn(d, 1.44269504088896341f);
-    float n = rintf(y);
-    float f = __fsub_rn(y, n);
+    float t = __fadd_rn(y, 12582912.0f);                     // 1.5 * 2^23: rounds y to the nearest integer (ties to even)
+    float n = __fsub_rn(t, 12582912.0f);
+    int ni = __float_as_int(t) - 0x4B400000;                 // the same integer, from the mantissa bits
+    float f = __fsub_rn(y, n);                               // exact, in [-0.5, 0.5]
     float p = exp2_poly(f);                                  // in [0.70, 1.42]
     // floor(p * 2^(kbits + n) + 1/2) in integer arithmetic: p = m * 2^(e - 23), m a 24-bit integer
     uint32_t bits = __float_as_uint(p);
     uint32_t m = (bits & 0x7fffffu) | 0x800000u;
-    int s = kbits + (int)n + (int)(bits >> 23) - 127 - 23;
-    if (s >= 0) return (uint64_t)m << s;
-    if (s < -25) return 0;
-    return (uint64_t)((m + (1u << (-s - 1))) >> (-s));
+    int s = kbits + ni + (int)(bits >> 23) - 150;
+    uint64_t hi = (uint64_t)m << max(s, 0);
+    int ns = min(max(-s, 1), 26);                            // >= 26: (m + 2^25) >> 26 == 0
+    uint32_t lo = (m + (1u << (ns - 1))) >> ns;
+    return s >= 0 ? hi : (uint64_t)lo;
 }
 inline int fixed_kbits(uint64_t n_total) {
     int lg = 0;

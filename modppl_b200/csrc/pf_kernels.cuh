@@ -13,6 +13,7 @@
 //                        running sum, bit-exact.
 //   gather_kernel        K6 stand-alone (only when the host reads state right after a resample).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "models.cuh"
 
@@ -104,14 +105,21 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
 
     Lse3<Acc> run = lse3_identity<Acc>();
     const size_t stride = (size_t)gridDim.x * kExtendThreads * V;
-    for (size_t base = ((size_t)blockIdx.x * kExtendThreads + tid) * V; base < a.n; base += stride) {
+    typedef typename std::conditional<V == 4, int4, int2>::type AncVec;
+    size_t base = ((size_t)blockIdx.x * kExtendThreads + tid) * V;
+    AncVec anc_next = AncVec();
+    if (gather && base < a.n) anc_next = *reinterpret_cast<const AncVec*>(a.anc + base);
+    for (; base < a.n; base += stride) {
         Real x[V][D];
         Real w[V];
         int32_t par[V];
         const bool full = base + V <= a.n;
         if (gather) {
-            if constexpr (V == 4) { int4 p = *reinterpret_cast<const int4*>(a.anc + base); par[0] = p.x; par[1] = p.y; par[2] = p.z; par[3] = p.w; }
-            else { int2 p = *reinterpret_cast<const int2*>(a.anc + base); par[0] = p.x; par[1] = p.y; }
+            // software pipeline: this iteration's ancestors were loaded one iteration ago; fetch the next ones now and
+            // pull the parents' cache lines towards L2 so the dependent gather of the next iteration starts warm
+            par[0] = anc_next.x; par[1] = anc_next.y;
+            if constexpr (V == 4) { par[2] = anc_next.z; par[3] = anc_next.w; }
+            if (base + stride < a.n) anc_next = *reinterpret_cast<const AncVec*>(a.anc + base + stride);
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 size_t src = (full || base + v < a.n) ? (size_t)par[v] : 0;
@@ -145,6 +153,12 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             vec_store<Real>(a.state_out + (size_t)d * a.ld + base, tmp);
         }
         vec_store<Real>(a.lw + base, w);
+
+        if (gather && base + stride < a.n) {
+            const size_t nsrc = (size_t)anc_next.x;
+#pragma unroll
+            for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state_in + (size_t)d * a.ld + nsrc));
+        }
 
         // online (max, sum exp, sum exp^2)
         Acc m = (Acc)-INFINITY;
@@ -277,22 +291,22 @@ __device__ __forceinline__ unsigned long long resample_rand_word(uint64_t seed, 
     return ((unsigned long long)x.x << 32) | x.y;
 }
 
-// 4 consecutive log-weights -> 4 integer weights; out-of-range lanes give 0
-template <typename Real>
-__device__ __forceinline__ void load_q4(const Real* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4]);
-template <>
-__device__ __forceinline__ void load_q4<float>(const float* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4]) {
-    float4 v = *reinterpret_cast<const float4*>(lw + idx);
-    float w[4] = {v.x, v.y, v.z, v.w};
+// 4 consecutive log-weights -> 4 integer weights; out-of-range lanes give 0 (FULL: the whole tile is in range)
+template <typename Real, bool FULL>
+__device__ __forceinline__ void load_q4(const Real* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4]) {
+    float w[4];
+    if constexpr (sizeof(Real) == 4) {
+        float4 v = *reinterpret_cast<const float4*>(lw + idx);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        double2 a = *reinterpret_cast<const double2*>(lw + idx), b = *reinterpret_cast<const double2*>(lw + idx + 2);
+        w[0] = (float)a.x; w[1] = (float)a.y; w[2] = (float)b.x; w[3] = (float)b.y;
+    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = (idx + j < n) ? fixed_weight(__fsub_rn(w[j], mx), kbits) : 0ull;
-}
-template <>
-__device__ __forceinline__ void load_q4<double>(const double* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4]) {
-    double2 a = *reinterpret_cast<const double2*>(lw + idx), b = *reinterpret_cast<const double2*>(lw + idx + 2);
-    double w[4] = {a.x, a.y, b.x, b.y};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) q[j] = (idx + j < n) ? fixed_weight(__fsub_rn((float)w[j], mx), kbits) : 0ull;
+    for (int j = 0; j < 4; ++j) {
+        unsigned long long v = fixed_weight(__fsub_rn(w[j], mx), kbits);
+        q[j] = (FULL || idx + j < n) ? v : 0ull;
+    }
 }
 
 // R1: per-tile integer weight sums; the last block to finish turns them into exclusive tile prefixes (in place, in
@@ -314,13 +328,22 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
     for (unsigned int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         unsigned long long sum = 0;
         const size_t tile_base = (size_t)tile * kScanTile;
+        if (tile_base + kScanTile <= a.n) {
 #pragma unroll
-        for (int r = 0; r < kScanRounds; ++r) {
-            size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
-            if (idx < a.n) {
+            for (int r = 0; r < kScanRounds; ++r) {
                 unsigned long long q[4];
-                load_q4<Real>(a.lw, idx, a.n, mx, a.kbits, q);
+                load_q4<Real, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q);
                 sum += q[0] + q[1] + q[2] + q[3];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kScanRounds; ++r) {
+                size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
+                if (idx < a.n) {
+                    unsigned long long q[4];
+                    load_q4<Real, false>(a.lw, idx, a.n, mx, a.kbits, q);
+                    sum += q[0] + q[1] + q[2] + q[3];
+                }
             }
         }
 #pragma unroll
@@ -427,12 +450,20 @@ __device__ __forceinline__ unsigned long long tile_local_scan(const FixedArgs<Re
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t tile_base = (size_t)tile * kScanTile;
     unsigned long long incl[kScanRounds];
+    if (tile_base + kScanTile <= a.n) {
 #pragma unroll
-    for (int r = 0; r < kScanRounds; ++r) {
-        size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
-        if (idx < a.n) load_q4<Real>(a.lw, idx, a.n, mx, a.kbits, q[r]);
-        else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0ull; }
-        incl[r] = q[r][0] + q[r][1] + q[r][2] + q[r][3];
+        for (int r = 0; r < kScanRounds; ++r) {
+            load_q4<Real, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q[r]);
+            incl[r] = q[r][0] + q[r][1] + q[r][2] + q[r][3];
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kScanRounds; ++r) {
+            size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
+            if (idx < a.n) load_q4<Real, false>(a.lw, idx, a.n, mx, a.kbits, q[r]);
+            else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0ull; }
+            incl[r] = q[r][0] + q[r][1] + q[r][2] + q[r][3];
+        }
     }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -539,12 +570,21 @@ __device__ __forceinline__ void expand_chunk(const FixedArgs<Real>& a, ScanShare
     __syncthreads();
     const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile) - 1;
     const unsigned long long slot0 = n_start + chunk_base;
+    const unsigned int valid = min((unsigned int)kScanTile, total - chunk_base);
+    if (slot0 >= a.out_base && slot0 + valid <= a.out_base + a.n_out_local) {   // whole chunk lands in this shard (always, on one GPU)
+        int32_t* dst = a.anc + (slot0 - a.out_base);
 #pragma unroll
-    for (int k = 0; k < kScanTile / kScanThreads; ++k) {
-        unsigned int o = k * kScanThreads + tid;
-        unsigned long long slot = slot0 + o;
-        if (chunk_base + o < total && slot >= a.out_base && slot < a.out_base + a.n_out_local)
-            a.anc[slot - a.out_base] = src0 + (int32_t)sh.head[o];
+        for (int k = 0; k < kScanTile / kScanThreads; ++k) {
+            unsigned int o = k * kScanThreads + tid;
+            if (o < valid) dst[o] = src0 + (int32_t)sh.head[o];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanTile / kScanThreads; ++k) {
+            unsigned int o = k * kScanThreads + tid;
+            unsigned long long slot = slot0 + o;
+            if (o < valid && slot >= a.out_base && slot < a.out_base + a.n_out_local) a.anc[slot - a.out_base] = src0 + (int32_t)sh.head[o];
+        }
     }
     __syncthreads();
 }

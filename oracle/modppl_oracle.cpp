@@ -300,7 +300,7 @@ extern "C" float mo_exp2_poly(float f) {
 }
 
 extern "C" uint64_t mo_fixed_weight(float d, int kbits) {
-    if (!(d > -88.0f)) return 0;           // also NaN, -inf
+    if (!(d > -100.0f)) d = -100.0f;       // also NaN, -inf (they come out as 0 below)
     if (d > 0.f) d = 0.f;
     float y = d * 1.44269504088896341f;    // single rounding
     float n = std::rint(y);                // ties-to-even
@@ -311,7 +311,7 @@ extern "C" uint64_t mo_fixed_weight(float d, int kbits) {
     uint32_t m = (bits & 0x7fffffu) | 0x800000u;
     int s = kbits + (int)n + (int)(bits >> 23) - 127 - 23;
     if (s >= 0) return (uint64_t)m << s;
-    if (s < -25) return 0;
+    if (s < -25) return 0;                 // (m + 2^25) >> 26 == 0
     return (uint64_t)((m + (1u << (-s - 1))) >> (-s));
 }
 
