@@ -246,22 +246,16 @@ __device__ __forceinline__ float exp2_poly(float f) {
     return p;
 }
 __device__ __forceinline__ uint64_t fixed_weight(float d, int kbits) {
-    // branch-free; d = lw - max.  NaN and anything below -100 (incl. -inf) end up as 0 through the shift clamp.
-    d = fminf(fmaxf(d, -100.0f), 0.f);                       // fmaxf(NaN, x) = x
+    // branch-free; d = lw - max <= 0.  NaN and anything below -100 (incl. -inf) come out as 0.
+    d = fmaxf(d, -100.0f);                                   // fmaxf(NaN, x) = x
     float y = __fmul_rn(d, 1.44269504088896341f);
     float t = __fadd_rn(y, 12582912.0f);                     // 1.5 * 2^23: rounds y to the nearest integer (ties to even)
     float n = __fsub_rn(t, 12582912.0f);
     int ni = __float_as_int(t) - 0x4B400000;                 // the same integer, from the mantissa bits
     float f = __fsub_rn(y, n);                               // exact, in [-0.5, 0.5]
     float p = exp2_poly(f);                                  // in [0.70, 1.42]
-    // floor(p * 2^(kbits + n) + 1/2) in integer arithmetic: p = m * 2^(e - 23), m a 24-bit integer
-    uint32_t bits = __float_as_uint(p);
-    uint32_t m = (bits & 0x7fffffu) | 0x800000u;
-    int s = kbits + ni + (int)(bits >> 23) - 150;
-    uint64_t hi = (uint64_t)m << max(s, 0);
-    int ns = min(max(-s, 1), 26);                            // >= 26: (m + 2^25) >> 26 == 0
-    uint32_t lo = (m + (1u << (ns - 1))) >> ns;
-    return s >= 0 ? hi : (uint64_t)lo;
+    float scale = __int_as_float((127 + kbits + ni) << 23);  // 2^(kbits + n): exponent >= 127 + 36 - 145 > 0, never denormal
+    return __float2ull_rn(__fmul_rn(p, scale));              // exact product, then round-to-nearest-even to an integer
 }
 inline int fixed_kbits(uint64_t n_total) {
     int lg = 0;

@@ -223,7 +223,7 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
     const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
     {
         ScopedLaunch sl(ps, "fixed_reduce");
-        fixed_reduce_kernel<Real><<<(unsigned int)std::min<size_t>(num_tiles, (size_t)kNumSMs * 8), kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
+        fixed_reduce_kernel<Real><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (scheme == MPL_RESAMPLE_SYSTEMATIC_FIXED) {
@@ -392,6 +392,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ok = ok && cudaMalloc(&ps->lw, ps->ld * es) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->anc, ps->ld * sizeof(int32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->desc, num_tiles * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(ps->desc, 0, num_tiles * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->overflow, ps->overflow_cap * sizeof(OverflowEntry)) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->stats, sizeof(DeviceStats)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ps->stats_host, sizeof(DeviceStats)) == cudaSuccess;

@@ -319,13 +319,16 @@ constexpr unsigned int kHeavyCap = 32u * kScanTile;        // tiles with more of
 
 template <typename Real>
 __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Real> a, unsigned int num_tiles) {
+    // one tile per block; warps add their partial sums straight into desc[tile] (zeroed by the previous scan pass), so
+    // the only block-wide barrier is the one in front of the last-block test
     if (a.dynamic && !a.stats->do_resample) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float mx = (float)a.stats->max;
     __shared__ unsigned long long ws[kScanThreads / 32];
     __shared__ unsigned long long carry_s;
     __shared__ bool is_last;
-    for (unsigned int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    {
+        const unsigned int tile = blockIdx.x;
         unsigned long long sum = 0;
         const size_t tile_base = (size_t)tile * kScanTile;
         if (tile_base + kScanTile <= a.n) {
@@ -348,16 +351,9 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        __syncthreads();
-        if (lane == 0) ws[warp] = sum;
-        __syncthreads();
-        if (tid == 0) {
-            unsigned long long b = 0;
-#pragma unroll
-            for (int i = 0; i < kScanThreads / 32; ++i) b += ws[i];
-            a.desc[tile] = b;
-        }
+        if (lane == 0 && sum) atomicAdd(&a.desc[tile], sum);
     }
+    __syncthreads();
     if (tid == 0) {
         __threadfence();
         is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
@@ -520,19 +516,24 @@ __device__ __forceinline__ void tile_fill_nloc(const FixedArgs<Real>& a, ScanSha
 // tile-local offspring range.  Every particle with >= 1 offspring drops (its local index + 1) at the first slot of its
 // run; an inclusive max-scan propagates it along the run (local indices increase with the slot); the result is
 // written with coalesced 4-byte stores.  All threads of the block must call this.
+__device__ __forceinline__ void clear_heads(ScanShared& sh) {
+    uint4* head4 = reinterpret_cast<uint4*>(sh.head);
+    head4[threadIdx.x * 2] = make_uint4(0, 0, 0, 0);
+    head4[threadIdx.x * 2 + 1] = make_uint4(0, 0, 0, 0);
+}
+// `cleared`: the caller already zeroed sh.head and a barrier has passed since (saves one barrier for the first chunk).
+// On return every thread may still be reading sh.head: the caller must put a barrier before the next clear.
 template <typename Real>
 __device__ __forceinline__ void expand_chunk(const FixedArgs<Real>& a, ScanShared& sh, unsigned int tile, unsigned long long n_start,
-                                             unsigned int chunk_base, unsigned int total) {
+                                             unsigned int chunk_base, unsigned int total, bool cleared) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint4* head4 = reinterpret_cast<uint4*>(sh.head);
-    head4[tid * 2] = make_uint4(0, 0, 0, 0);
-    head4[tid * 2 + 1] = make_uint4(0, 0, 0, 0);
+    if (!cleared) { __syncthreads(); clear_heads(sh); __syncthreads(); }
     if (tid == 0) {   // parent of the chunk's first slot: first element e with nloc[e] > chunk_base
         unsigned int lo = 0, hi = kScanTile - 1;
         while (lo < hi) { unsigned int mid = (lo + hi) >> 1; if (sh.nloc[mid] > chunk_base) hi = mid; else lo = mid + 1; }
         sh.carry = lo + 1;
     }
-    __syncthreads();
 #pragma unroll
     for (int r = 0; r < kScanRounds; ++r) {
         const unsigned int e0 = r * (kScanThreads * 4) + tid * 4;
@@ -586,7 +587,6 @@ __device__ __forceinline__ void expand_chunk(const FixedArgs<Real>& a, ScanShare
             if (o < valid && slot >= a.out_base && slot < a.out_base + a.n_out_local) a.anc[slot - a.out_base] = src0 + (int32_t)sh.head[o];
         }
     }
-    __syncthreads();
 }
 
 template <typename Real>
@@ -607,9 +607,11 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
     if (tid == 0) {   // exclusive prefix of the tile (from the reduce pass) -> exact slot base of the tile
         const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
         sh.base = tile_base_exact(a.c_offset + a.desc[tile], W, U, a.n_out, inv_w);
+        a.desc[tile] = 0ull;   // ready for the next reduce pass
     }
+    clear_heads(sh);
     unsigned long long q[kScanRounds][4], excl[kScanRounds];
-    tile_local_scan<Real>(a, sh, tile, mx, q, excl);   // (contains the barrier that publishes sh.base)
+    tile_local_scan<Real>(a, sh, tile, mx, q, excl);   // (contains the barrier that publishes sh.base and the cleared heads)
     const TileBase base = sh.base;
     tile_fill_nloc<Real>(a, sh, base, W, inv_w, q, excl);
     __syncthreads();
@@ -631,7 +633,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
         return;
     }
     for (unsigned int chunk_base = 0; chunk_base < total; chunk_base += kScanTile)
-        expand_chunk<Real>(a, sh, tile, base.n_start, chunk_base, total);
+        expand_chunk<Real>(a, sh, tile, base.n_start, chunk_base, total, chunk_base == 0);
 }
 
 // heavy tiles (a few particles own a large share of the offspring): the whole grid expands each of them
@@ -653,7 +655,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_overflow_kernel(FixedArgs<
         tile_fill_nloc<Real>(a, sh, TileBase{e.n_start, e.rem}, W, inv_w, q, excl);
         __syncthreads();
         for (unsigned long long chunk_base = (unsigned long long)blockIdx.x * kScanTile; chunk_base < e.total; chunk_base += (unsigned long long)gridDim.x * kScanTile)
-            expand_chunk<Real>(a, sh, e.tile, e.n_start, (unsigned int)chunk_base, e.total);
+            expand_chunk<Real>(a, sh, e.tile, e.n_start, (unsigned int)chunk_base, e.total, false);
     }
 }
 
@@ -741,6 +743,8 @@ __global__ void __launch_bounds__(kScanThreads) fixed_cumsum_kernel(FixedArgs<Re
     unsigned long long q[kScanRounds][4], excl[kScanRounds];
     tile_local_scan<Real>(a, sh, tile, mx, q, excl);
     const unsigned long long tile_excl = a.desc[tile];
+    __syncthreads();
+    if (tid == 0) a.desc[tile] = 0ull;   // ready for the next reduce pass
 #pragma unroll
     for (int r = 0; r < kScanRounds; ++r) {
         size_t idx = (size_t)tile * kScanTile + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;

@@ -306,13 +306,9 @@ extern "C" uint64_t mo_fixed_weight(float d, int kbits) {
     float n = std::rint(y);                // ties-to-even
     float f = y - n;                       // exact
     float p = mo_exp2_poly(f);
-    // floor(p * 2^(kbits + n) + 1/2), exactly: p = m * 2^(e - 23) with m a 24-bit integer
-    uint32_t bits; std::memcpy(&bits, &p, 4);
-    uint32_t m = (bits & 0x7fffffu) | 0x800000u;
-    int s = kbits + (int)n + (int)(bits >> 23) - 127 - 23;
-    if (s >= 0) return (uint64_t)m << s;
-    if (s < -25) return 0;                 // (m + 2^25) >> 26 == 0
-    return (uint64_t)((m + (1u << (-s - 1))) >> (-s));
+    float scale = std::ldexp(1.0f, kbits + (int)n);      // 2^(kbits + n), a normal float (n >= -145)
+    float v = p * scale;                                  // exact
+    return (uint64_t)std::llrint(v);                      // ties-to-even
 }
 
 extern "C" int mo_fixed_kbits(uint64_t n_total) {
