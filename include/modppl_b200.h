@@ -139,9 +139,9 @@ int mpl_resample_indices(const double* probs, const double* uniforms, uint64_t n
 int mpl_cumsum_sequential(const double* probs, uint64_t n, double* out);       /* the exact running sum itself */
 /* lib.rs:34-45 + particle_filter.rs:27-35,98-100 in one pass: lse, ESS = 1/sum(w~^2), max. dtype of lw. */
 int mpl_logsumexp_stats(const void* lw, uint64_t n, int dtype, double* lse, double* ess, double* max);
-/* integer-weight resamplers on injected f32 log-weights (rand_word: the 64-bit offset word for systematic; for
- * multinomial the per-output words come from Philox(seed, t)). */
-int mpl_fixed_resample(const float* lw, uint64_t n, int scheme, uint64_t rand_word_or_seed, uint32_t t, int32_t* anc,
+/* integer-weight resamplers on injected f32 log-weights; the systematic offset word and the multinomial per-output
+ * words come from Philox(seed, t) exactly as inside a particle system resampling the weights of step t. */
+int mpl_fixed_resample(const float* lw, uint64_t n, int scheme, uint64_t seed, uint32_t t, int32_t* anc,
                        double* lse, uint64_t* total_weight);
 /* built-in log-densities evaluated on the device (tests/dists.rs known answers) */
 int mpl_logpdf(const char* dist, const double* x, const double* params, size_t n_params, double* out);
@@ -153,6 +153,12 @@ int mpl_logpdf(const char* dist, const double* x, const double* params, size_t n
 int mpl_ps_peer_export(mpl_ps*, void* blob /* MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_attach(mpl_ps*, int rank, int world, const void* blobs /* world * MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_detach(mpl_ps*);
+int mpl_ps_peer_error(mpl_ps*, int* out);   /* 1 if a kernel gave up waiting for a peer (bounded spin) */
+/* Test hook: `world` shards emulated on ONE GPU run the multi-GPU kernels phase by phase (remote loads/stores become
+ * local).  init + resample, then steps with a resample after each except the last; outputs the final state
+ * double[D * n_global] (SoA), log-weights double[n_global] and the log-ML estimate. */
+int mpl_test_virtual_shards(const mpl_model*, uint64_t n_global, int world, int dtype, uint64_t seed, const double* obs,
+                            size_t n_steps, size_t n_obs, double* state_out, double* lw_out, double* lml_out);
 
 #ifdef __cplusplus
 }

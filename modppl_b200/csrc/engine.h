@@ -57,6 +57,17 @@ struct mpl_ps {
     bool profile;
     std::map<std::string, mpl::KernelTimer> timers;
     uint64_t launch_count;
-    // multi-GPU
+    // multi-GPU (multi_gpu.cu): peer table handed to every kernel; world == 1 on a single GPU
     int rank, world;
+    mpl::PeerTable peer;
+    mpl::Mailbox* mailbox;            // device memory of this rank, written by every rank
+    void* ipc_opened[4][mpl::kMaxPeers];   // pointers obtained from cudaIpcOpenMemHandle (to close on detach)
+    bool peer_virtual;                // peers live in this process (single-GPU emulation used by the tests)
 };
+
+namespace mpl {
+// step phases, callable separately so that shards emulated on one GPU can be advanced phase by phase
+int ps_phase_extend(mpl_ps* ps, bool init);
+int ps_phase_reduce(mpl_ps* ps);
+int ps_phase_scan(mpl_ps* ps);
+}

@@ -117,6 +117,8 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     a.nobs = ps->model.obs_dim;
     a.stats = ps->stats;
     a.partials = ps->partials;
+    a.peer = ps->peer;
+    a.cur = ps->cur;
     if (mode == EXT_DYNAMIC) a.state_out = (Real*)ps->state[ps->cur ^ 1];
     const int grid = ps->grid_extend;
     {
@@ -155,6 +157,7 @@ static int launch_extend(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs
 
 static int ensure_stats(mpl_ps* ps) {
     if (ps->stats_valid) return MPL_OK;
+    if (ps->world > 1) return fail(MPL_ERR_UNSUPPORTED, "sharded particle system: weight statistics come from the step itself (injected weights are single-GPU only)");
     {
         ScopedLaunch sl(ps, "weight_reduce");
         if (ps->dtype == MPL_F32) weight_reduce_kernel<float><<<ps->grid_reduce, 256, 0, ps->stream>>>((const float*)ps->lw, ps->n, ps->stats, ps->partials);
@@ -174,6 +177,7 @@ static int fetch_stats(mpl_ps* ps) {
 // materialise a pending ancestor gather (only needed when the host looks at / overwrites state between resample and step)
 static int materialise(mpl_ps* ps) {
     if (!ps->pending_gather) return MPL_OK;
+    if (ps->world > 1) return fail(MPL_ERR_UNSUPPORTED, "sharded particle system: read or write state after the next step (ancestors point into other shards)");
     const int grid = grid_for(ps->n, 256, kNumSMs * 8);
     {
         ScopedLaunch sl(ps, "gather");
@@ -205,7 +209,9 @@ static FixedArgs<Real> fixed_args(mpl_ps* ps, bool dynamic, bool dev_t) {
     a.n_out_local = ps->n;
     a.log_n_global = std::log((double)ps->n_global);
     a.anc = ps->anc;
-    a.src_base = 0;
+    a.src_base = (int32_t)ps->gid_offset;   // ancestors are global ids (== local indices on a single GPU)
+    a.peer = ps->peer;
+    a.epoch = dev_t ? -1 : ps->t;
     a.desc = ps->desc;
     a.overflow = ps->overflow;
     a.stats = ps->stats;
@@ -308,6 +314,43 @@ static int do_resample(mpl_ps* ps, int scheme) {
     return MPL_OK;
 }
 
+int ps_phase_extend(mpl_ps* ps, bool init) {
+    Obs dummy; std::memset(&dummy, 0, sizeof dummy);
+    int rc;
+    if (init) {
+        ps->t = 0; ps->pending_gather = false;
+        rc = launch_extend(ps, EXT_INIT, dummy, true, false);
+        ps->t = 1; ps->initialised = true; ps->stats_valid = true;
+    } else {
+        rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false);
+        ps->pending_gather = false; ps->t += 1; ps->stats_valid = true;
+    }
+    return rc;
+}
+int ps_phase_reduce(mpl_ps* ps) {
+    const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
+    ScopedLaunch sl(ps, "fixed_reduce");
+    if (ps->dtype == MPL_F32) { auto a = fixed_args<float>(ps, false, false); fixed_reduce_kernel<float><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
+    else { auto a = fixed_args<double>(ps, false, false); fixed_reduce_kernel<double><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
+    MPL_CUDA_OK(cudaGetLastError());
+    return MPL_OK;
+}
+int ps_phase_scan(mpl_ps* ps) {
+    const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
+    if (ps->dtype == MPL_F32) {
+        auto a = fixed_args<float>(ps, false, false);
+        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan_kernel<float><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
+        { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow_kernel<float><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a); }
+    } else {
+        auto a = fixed_args<double>(ps, false, false);
+        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan_kernel<double><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
+        { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow_kernel<double><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a); }
+    }
+    MPL_CUDA_OK(cudaGetLastError());
+    ps->pending_gather = true; ps->stats_valid = false;
+    return MPL_OK;
+}
+
 }  // namespace mpl
 
 using namespace mpl;
@@ -378,7 +421,8 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->seed = c.seed; ps->gid_offset = c.gid_offset; ps->n_global = c.n_global ? c.n_global : num_particles;
     ps->D = model->state_dim;
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false;
-    ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1;
+    ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
+    std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
     ps->probs = nullptr; ps->cums = nullptr; ps->icum = nullptr; ps->obs_dev = nullptr; ps->obs_steps = 0; ps->staging = nullptr;
     const size_t es = elem_size(ps);
     const size_t num_tiles = ps->ld / kScanTile;
@@ -425,6 +469,8 @@ extern "C" void mpl_ps_destroy(mpl_ps* ps) {
     for (auto& kv : ps->timers) for (auto& pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaFree(ps->state[0]); cudaFree(ps->state[1]); cudaFree(ps->lw); cudaFree(ps->anc); cudaFree(ps->desc); cudaFree(ps->overflow);
     cudaFree(ps->stats); cudaFreeHost(ps->stats_host); cudaFree(ps->partials); cudaFree(ps->ipartials);
+    if (ps->world > 1 && !ps->peer_virtual) mpl_ps_peer_detach(ps);
+    cudaFree(ps->mailbox);
     cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
     if (ps->stream) cudaStreamDestroy(ps->stream);
     delete ps;

@@ -48,6 +48,42 @@ struct OverflowEntry {
     unsigned int total;
 };
 
+// ---- multi-GPU: one process per GPU, peers reached through NVLink-mapped pointers (CUDA IPC) ----------------------------
+// Every rank owns a Mailbox; rank g writes column g of every peer's mailbox (remote stores), then a flag carrying the
+// step number, and kernels on the receiving GPU spin on their LOCAL copy of the flags.  No host round trip, no NCCL call
+// on the data path: (max, sum exp, sum exp^2) after the extend, the integer weight total after the reduce pass, and a
+// "my ancestors are written" flag after the scan.
+constexpr int kMaxPeers = 8;
+struct Mailbox {
+    double smax[kMaxPeers], ssum[kMaxPeers], ssum2[kMaxPeers];
+    unsigned long long W[kMaxPeers];
+    long long flag_stats[kMaxPeers], flag_w[kMaxPeers], flag_done[kMaxPeers];
+    int error;
+    int pad;
+};
+struct PeerTable {
+    int world, rank;
+    unsigned int n_loc;   // particles per shard (equal shards)
+    int shift;            // log2(n_loc) when it is a power of two, else -1
+    const void* state[2][kMaxPeers];   // [buffer][rank]: SoA state of every shard
+    int32_t* anc[kMaxPeers];           // ancestor slots of every shard
+    Mailbox* mail[kMaxPeers];
+};
+__device__ __forceinline__ unsigned int peer_owner(const PeerTable& p, unsigned int gid) { return p.shift >= 0 ? gid >> p.shift : gid / p.n_loc; }
+
+// one thread: wait until every rank's flag has reached `epoch` (bounded: ~2 s of spinning sets Mailbox::error)
+__device__ __forceinline__ void peer_wait(const PeerTable& p, const long long* flags, long long epoch) {
+    const volatile long long* f = flags;
+    const long long t0 = clock64();
+    for (int h = 0; h < p.world; ++h) {
+        while (f[h] < epoch) {
+            if (clock64() - t0 > 4000000000ll) { p.mail[p.rank]->error = 1; return; }
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+
 template <typename Real> struct VecOf;
 template <> struct VecOf<float> { typedef float4 type; static constexpr int N = 4; };
 template <> struct VecOf<double> { typedef double2 type; static constexpr int N = 2; };
@@ -78,6 +114,8 @@ struct ExtendArgs {
     int nobs;
     DeviceStats* stats;
     Lse3<double>* partials;  // gridDim.x
+    PeerTable peer;          // world == 1: single GPU
+    int cur;                 // which state buffer is the input (index into peer.state)
 };
 
 constexpr int kExtendThreads = 256;
@@ -102,6 +140,11 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
         gather = a.stats->resampled != 0;
         accum = !gather;
     }
+    const bool sharded = a.peer.world > 1;
+    if (sharded && gather) {   // every shard must have finished writing ancestors (and reading the buffer we overwrite)
+        if (tid == 0) peer_wait(a.peer, a.peer.mail[a.peer.rank]->flag_done, t);
+        __syncthreads();
+    }
 
     Lse3<Acc> run = lse3_identity<Acc>();
     const size_t stride = (size_t)gridDim.x * kExtendThreads * V;
@@ -120,11 +163,22 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             par[0] = anc_next.x; par[1] = anc_next.y;
             if constexpr (V == 4) { par[2] = anc_next.z; par[3] = anc_next.w; }
             if (base + stride < a.n) anc_next = *reinterpret_cast<const AncVec*>(a.anc + base + stride);
+            if (!sharded) {
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                size_t src = (full || base + v < a.n) ? (size_t)par[v] : 0;
+                for (int v = 0; v < V; ++v) {
+                    size_t src = (full || base + v < a.n) ? (size_t)par[v] : 0;
 #pragma unroll
-                for (int d = 0; d < D; ++d) x[v][d] = __ldg(a.state_in + (size_t)d * a.ld + src);
+                    for (int d = 0; d < D; ++d) x[v][d] = __ldg(a.state_in + (size_t)d * a.ld + src);
+                }
+            } else {   // parents are global ids: read them where they live (local HBM or a peer over NVLink)
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    unsigned int g = (full || base + v < a.n) ? (unsigned int)par[v] : (unsigned int)a.gid_offset;
+                    unsigned int r = peer_owner(a.peer, g);
+                    const Real* src = reinterpret_cast<const Real*>(a.peer.state[a.cur][r]) + (g - r * a.peer.n_loc);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) x[v][d] = src[(size_t)d * a.ld];
+                }
             }
         } else if (MODE != EXT_INIT) {
 #pragma unroll
@@ -154,7 +208,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
         }
         vec_store<Real>(a.lw + base, w);
 
-        if (gather && base + stride < a.n) {
+        if (gather && !sharded && base + stride < a.n) {
             const size_t nsrc = (size_t)anc_next.x;
 #pragma unroll
             for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state_in + (size_t)d * a.ld + nsrc));
@@ -208,6 +262,14 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             st->blocks_done = 0;
             st->resampled = 0;
             st->t = t + 1;
+            if (sharded) {   // post this shard's triple to every rank, then the flag
+                for (int h = 0; h < a.peer.world; ++h) {
+                    Mailbox* mb = a.peer.mail[h];
+                    mb->smax[a.peer.rank] = b.m; mb->ssum[a.peer.rank] = b.s; mb->ssum2[a.peer.rank] = b.s2;
+                }
+                __threadfence_system();
+                for (int h = 0; h < a.peer.world; ++h) *(volatile long long*)&a.peer.mail[h]->flag_stats[a.peer.rank] = t + 1;
+            }
         }
     }
 }
@@ -282,7 +344,51 @@ struct FixedArgs {
     long long rt;             // RNG tag of this resample (step whose weights are resampled); < 0: stats->t - 1
     int accumulate_lml;
     int dynamic;              // 1: skip unless stats->do_resample (ESS-triggered, device-resident loop)
+    PeerTable peer;           // world == 1: single GPU
+    long long epoch;          // step number the mailbox flags must have reached; < 0: stats->t
 };
+
+// global (max, W, prefix of lower-ranked shards) for the reduce / scan passes
+struct GlobalWeights {
+    float mx;
+    unsigned long long W, c_offset;
+};
+template <typename Real>
+__device__ __forceinline__ float fixed_global_max(const FixedArgs<Real>& a, bool publish_stats) {
+    // single GPU: the extend epilogue left the exact max in stats.  Sharded: wait for every shard's triple, take the max
+    // (exact, order-free); block 0 also folds the triples in rank order into stats for the host-side queries.
+    if (a.peer.world <= 1) return (float)a.stats->max;
+    const long long epoch = a.epoch < 0 ? a.stats->t : a.epoch;
+    Mailbox* mb = a.peer.mail[a.peer.rank];
+    peer_wait(a.peer, mb->flag_stats, epoch);
+    Lse3<double> acc = lse3_identity<double>();
+    for (int h = 0; h < a.peer.world; ++h) acc = lse3_combine(acc, Lse3<double>{*(volatile double*)&mb->smax[h], *(volatile double*)&mb->ssum[h], *(volatile double*)&mb->ssum2[h]});
+    if (publish_stats) {
+        DeviceStats* st = a.stats;
+        st->max = acc.m; st->sumexp = acc.s; st->sumexp2 = acc.s2;
+        st->ess = (acc.s2 > 0.) ? (acc.s * acc.s) / acc.s2 : 0.;
+        st->degenerate = (acc.m == -INFINITY) ? 1 : 0;
+    }
+    return (float)acc.m;
+}
+template <typename Real>
+__device__ __forceinline__ GlobalWeights fixed_global_weights(const FixedArgs<Real>& a) {
+    GlobalWeights g;
+    if (a.peer.world <= 1) { g.mx = (float)a.stats->max; g.W = a.stats->W; g.c_offset = 0; return g; }
+    const long long epoch = a.epoch < 0 ? a.stats->t : a.epoch;
+    Mailbox* mb = a.peer.mail[a.peer.rank];
+    peer_wait(a.peer, mb->flag_w, epoch);
+    double m = -INFINITY;
+    g.W = 0; g.c_offset = 0;
+    for (int h = 0; h < a.peer.world; ++h) {
+        unsigned long long w = *(volatile unsigned long long*)&mb->W[h];
+        if (h < a.peer.rank) g.c_offset += w;
+        g.W += w;
+        m = fmax(m, *(volatile double*)&mb->smax[h]);
+    }
+    g.mx = (float)m;
+    return g;
+}
 
 __device__ __forceinline__ unsigned long long resample_rand_word(uint64_t seed, long long rt, const DeviceStats* st) {
     if (rt < 0) rt = st->t - 1;
@@ -323,10 +429,13 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
     // the only block-wide barrier is the one in front of the last-block test
     if (a.dynamic && !a.stats->do_resample) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float mx = (float)a.stats->max;
     __shared__ unsigned long long ws[kScanThreads / 32];
     __shared__ unsigned long long carry_s;
     __shared__ bool is_last;
+    __shared__ float mx_s;
+    if (tid == 0) mx_s = fixed_global_max<Real>(a, blockIdx.x == 0);
+    __syncthreads();
+    const float mx = mx_s;
     {
         const unsigned int tile = blockIdx.x;
         unsigned long long sum = 0;
@@ -386,6 +495,12 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
     if (tid == 0) {
         DeviceStats* st = a.stats;
         st->W = carry_s; st->overflow_count = 0; st->blocks_done = 0;
+        if (a.peer.world > 1) {   // post this shard's integer weight to every rank
+            const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+            for (int h = 0; h < a.peer.world; ++h) a.peer.mail[h]->W[a.peer.rank] = carry_s;
+            __threadfence_system();
+            for (int h = 0; h < a.peer.world; ++h) *(volatile long long*)&a.peer.mail[h]->flag_w[a.peer.rank] = epoch;
+        }
     }
 }
 
@@ -431,6 +546,7 @@ struct __align__(16) ScanShared {
     unsigned long long tile_excl;
     unsigned long long rand_word;
     TileBase base;
+    GlobalWeights gw;
     __align__(16) unsigned int nloc[kScanTile];             // inclusive offspring counts, relative to the tile's first output slot
     __align__(16) unsigned short head[kScanTile];   // expansion buffer: (local parent + 1) at the first slot of each run
     unsigned int warp_max[kScanThreads / 32];
@@ -581,10 +697,13 @@ __device__ __forceinline__ void expand_chunk(const FixedArgs<Real>& a, ScanShare
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kScanTile / kScanThreads; ++k) {
+        for (int k = 0; k < kScanTile / kScanThreads; ++k) {   // slots of other shards: remote stores into the owner's array
             unsigned int o = k * kScanThreads + tid;
-            unsigned long long slot = slot0 + o;
-            if (o < valid && slot >= a.out_base && slot < a.out_base + a.n_out_local) a.anc[slot - a.out_base] = src0 + (int32_t)sh.head[o];
+            if (o < valid) {
+                unsigned int slot = (unsigned int)(slot0 + o);
+                unsigned int r = peer_owner(a.peer, slot);
+                a.peer.anc[r][slot - r * a.peer.n_loc] = src0 + (int32_t)sh.head[o];
+            }
         }
     }
 }
@@ -596,22 +715,27 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
     if (a.dynamic && !a.stats->do_resample) return;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x;
-    const unsigned long long W = st->W;
-    const float mx = (float)st->max;
+    if (tid == 0) {   // global weights (sharded: from the mailbox), then the exact slot base of this tile
+        GlobalWeights g = fixed_global_weights<Real>(a);
+        sh.gw = g;
+        if (g.W != 0ull) {
+            const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), g.W);
+            sh.base = tile_base_exact(g.c_offset + a.desc[tile], g.W, U, a.n_out, 1. / (double)g.W);
+        }
+        a.desc[tile] = 0ull;   // ready for the next reduce pass
+    }
+    clear_heads(sh);
+    __syncthreads();
+    const unsigned long long W = sh.gw.W;
+    const float mx = sh.gw.mx;
     if (W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors, flagged
         for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
         if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; }
         return;
     }
     const double inv_w = 1. / (double)W;
-    if (tid == 0) {   // exclusive prefix of the tile (from the reduce pass) -> exact slot base of the tile
-        const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
-        sh.base = tile_base_exact(a.c_offset + a.desc[tile], W, U, a.n_out, inv_w);
-        a.desc[tile] = 0ull;   // ready for the next reduce pass
-    }
-    clear_heads(sh);
     unsigned long long q[kScanRounds][4], excl[kScanRounds];
-    tile_local_scan<Real>(a, sh, tile, mx, q, excl);   // (contains the barrier that publishes sh.base and the cleared heads)
+    tile_local_scan<Real>(a, sh, tile, mx, q, excl);
     const TileBase base = sh.base;
     tile_fill_nloc<Real>(a, sh, base, W, inv_w, q, excl);
     __syncthreads();
@@ -623,6 +747,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
         st->ess_stale = st->ess;
         if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
         st->resampled = 1;
+        st->W = W;
     }
     if (total == 0u) return;
     if (total > kHeavyCap) {
@@ -643,19 +768,35 @@ __global__ void __launch_bounds__(kScanThreads) fixed_overflow_kernel(FixedArgs<
     DeviceStats* st = a.stats;
     if (a.dynamic && !st->do_resample) return;
     const unsigned int count = st->overflow_count;
-    if (count == 0u) return;
-    const unsigned long long W = st->W;
-    const float mx = (float)st->max;
-    const double inv_w = 1. / (double)W;
-    for (unsigned int k = 0; k < count; ++k) {
-        const OverflowEntry e = a.overflow[k];
-        unsigned long long q[kScanRounds][4], excl[kScanRounds];
+    if (count == 0u && a.peer.world <= 1) return;
+    if (count != 0u) {
+        if (threadIdx.x == 0) sh.gw = fixed_global_weights<Real>(a);
         __syncthreads();
-        tile_local_scan<Real>(a, sh, e.tile, mx, q, excl);
-        tile_fill_nloc<Real>(a, sh, TileBase{e.n_start, e.rem}, W, inv_w, q, excl);
+        const unsigned long long W = sh.gw.W;
+        const float mx = sh.gw.mx;
+        const double inv_w = 1. / (double)W;
+        for (unsigned int k = 0; k < count; ++k) {
+            const OverflowEntry e = a.overflow[k];
+            unsigned long long q[kScanRounds][4], excl[kScanRounds];
+            __syncthreads();
+            tile_local_scan<Real>(a, sh, e.tile, mx, q, excl);
+            tile_fill_nloc<Real>(a, sh, TileBase{e.n_start, e.rem}, W, inv_w, q, excl);
+            __syncthreads();
+            for (unsigned long long chunk_base = (unsigned long long)blockIdx.x * kScanTile; chunk_base < e.total; chunk_base += (unsigned long long)gridDim.x * kScanTile)
+                expand_chunk<Real>(a, sh, e.tile, e.n_start, (unsigned int)chunk_base, e.total, false);
+        }
+    }
+    if (a.peer.world > 1) {   // last block: every ancestor this shard owes anybody is written -> tell every rank
         __syncthreads();
-        for (unsigned long long chunk_base = (unsigned long long)blockIdx.x * kScanTile; chunk_base < e.total; chunk_base += (unsigned long long)gridDim.x * kScanTile)
-            expand_chunk<Real>(a, sh, e.tile, e.n_start, (unsigned int)chunk_base, e.total, false);
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) {
+                st->ticket = 0;
+                const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+                __threadfence_system();
+                for (int h = 0; h < a.peer.world; ++h) *(volatile long long*)&a.peer.mail[h]->flag_done[a.peer.rank] = epoch;
+            }
+        }
     }
 }
 

@@ -47,3 +47,16 @@ def logpdf(dist, x, params):
     out = C.c_double()
     check(lib.mpl_logpdf(dist.encode(), xx.ctypes.data_as(_lib.c_double_p), pp.ctypes.data_as(_lib.c_double_p), pp.size, C.byref(out)))
     return out.value
+
+
+def virtual_shards(model, n_global, world, obs, dtype="f32", seed=0):
+    """Shards emulated on one GPU (include/modppl_b200.h: mpl_test_virtual_shards) -> (state [D, N], log-weights [N], log-ML)."""
+    ys = np.ascontiguousarray(np.asarray(obs, dtype=np.float64))
+    ys = ys.reshape(ys.shape[0], -1)
+    D = model.state_dim
+    st = np.empty((D, n_global), dtype=np.float64)
+    lw = np.empty(n_global, dtype=np.float64)
+    lml = C.c_double()
+    check(lib.mpl_test_virtual_shards(model._h, n_global, world, 1 if dtype == "f64" else 0, seed, ys.ctypes.data_as(_lib.c_double_p), ys.shape[0], ys.shape[1],
+                                      st.ctypes.data_as(_lib.c_double_p), lw.ctypes.data_as(_lib.c_double_p), C.byref(lml)))
+    return st, lw, lml.value
