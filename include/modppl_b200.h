@@ -158,7 +158,7 @@ int mpl_ps_peer_error(mpl_ps*, int* out);   /* 1 if a kernel gave up waiting for
  * local).  init + resample, then steps with a resample after each except the last; outputs the final state
  * double[D * n_global] (SoA), log-weights double[n_global] and the log-ML estimate. */
 int mpl_test_virtual_shards(const mpl_model*, uint64_t n_global, int world, int dtype, uint64_t seed, const double* obs,
-                            size_t n_steps, size_t n_obs, double* state_out, double* lw_out, double* lml_out);
+                            size_t n_steps, size_t n_obs, double* state_out, double* lw_out, double* lml_out, double* loop_ms);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmodppl_b200.so")
+LIB_PATH = os.environ.get("MODPPL_B200_LIB") or os.path.join(_HERE, "lib", "libmodppl_b200.so")   # env override: A/B experiments only
 
 
 class MplError(RuntimeError):
@@ -86,7 +86,7 @@ SYMBOLS = {
     "mpl_ps_peer_attach": (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p),
     "mpl_ps_peer_detach": (C.c_int, C.c_void_p),
     "mpl_ps_peer_error": (C.c_int, C.c_void_p, C.POINTER(C.c_int)),
-    "mpl_test_virtual_shards": (C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, c_double_p, C.c_size_t, C.c_size_t, c_double_p, c_double_p, c_double_p),
+    "mpl_test_virtual_shards": (C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, c_double_p, C.c_size_t, C.c_size_t, c_double_p, c_double_p, c_double_p, c_double_p),
 }
 for _name, _s in SYMBOLS.items():
     _sig(_name, _s[0], *_s[1:])

@@ -6,6 +6,7 @@
 //   (4) parents that live in another shard      -> remote loads in the next extend's fused gather,
 // with step-numbered flags that the consuming kernels spin on locally.  The caller only has to all-gather one
 // MPL_PEER_BLOB_BYTES blob per rank once (bench.py does it with torch.distributed).
+#include <chrono>
 #include <cstring>
 #include <vector>
 #include "engine.h"
@@ -119,7 +120,7 @@ extern "C" int mpl_ps_peer_error(mpl_ps* ps, int* out) {
 // wait for one that has not been launched (B200_PROFILING.md: never co-schedule mutually waiting kernels on one GPU).
 // The kernels executed are exactly the multi-GPU ones (remote loads/stores become local ones).
 extern "C" int mpl_test_virtual_shards(const mpl_model* model, uint64_t n_global, int world, int dtype, uint64_t seed, const double* obs, size_t n_steps,
-                                       size_t n_obs, double* state_out, double* lw_out, double* lml_out) {
+                                       size_t n_obs, double* state_out, double* lw_out, double* lml_out, double* loop_ms) {
     // runs init, resample, then (n_steps - 1) x (step, resample) except that the last step is NOT followed by a
     // resample; returns the final state [D * n_global], log-weights [n_global] and the log-ML estimate.
     if (!model || !obs || n_steps < 1 || world < 1 || world > kMaxPeers || n_global % world) return fail(MPL_ERR_INVALID, "bad argument");
@@ -143,12 +144,14 @@ extern "C" int mpl_test_virtual_shards(const mpl_model* model, uint64_t n_global
             }
         }
     }
+    auto wall0 = std::chrono::steady_clock::now();
     for (size_t t = 0; t < n_steps && rc == MPL_OK; ++t) {
         for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = ps_phase_extend(sh[g], t == 0); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
         if (t + 1 == n_steps) break;
         for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = ps_phase_reduce(sh[g]); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
         for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = ps_phase_scan(sh[g]); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
     }
+    if (loop_ms) *loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     const int D = model->state_dim;
     std::vector<double> tmp;
     for (int g = 0; g < world && rc == MPL_OK; ++g) {

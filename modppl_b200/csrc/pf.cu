@@ -126,7 +126,10 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
         switch (mode) {
             case EXT_INIT: pf_extend_kernel<Model, Real, EXT_INIT><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
             case EXT_ACCUM: pf_extend_kernel<Model, Real, EXT_ACCUM><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
-            case EXT_GATHER: pf_extend_kernel<Model, Real, EXT_GATHER><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
+            case EXT_GATHER:
+                if (ps->world > 1) pf_extend_kernel<Model, Real, EXT_GATHER, true><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
+                else pf_extend_kernel<Model, Real, EXT_GATHER><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
+                break;
             default: pf_extend_kernel<Model, Real, EXT_DYNAMIC><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
         }
     }
@@ -491,6 +494,7 @@ extern "C" int mpl_ps_init_step(mpl_ps* ps, const double* obs, size_t n_obs) {
     Obs o;
     int rc = pack_obs(ps, obs, n_obs, o);
     if (rc) return rc;
+    if (ps->world > 1 && ps->initialised) return fail(MPL_ERR_UNSUPPORTED, "sharded particle system: init_step once per attach (mailbox epochs restart with t)");
     MPL_CUDA_OK(cudaSetDevice(ps->device));
     ps->t = 0;   // quirk Q4: init_step resets instead of pushing a second population
     ps->pending_gather = false;

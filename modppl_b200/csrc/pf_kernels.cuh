@@ -39,6 +39,10 @@ struct DeviceStats {
     int resampled;                 // 1: ancestors pending (next extend gathers, weights are zero)
     int do_resample;               // ESS trigger decision for the dynamic path
     int pad;
+    // sharded runs: block 0 of a kernel waits for the peers (system scope), publishes the global values into this
+    // struct and then raises the matching ready word; the kernel's other blocks only watch that local word
+    unsigned long long c_offset;   // integer weight of all lower-ranked shards
+    long long ready_stats, ready_w, ready_done;
 };
 
 struct OverflowEntry {
@@ -55,12 +59,19 @@ struct OverflowEntry {
 // "my ancestors are written" flag after the scan.
 constexpr int kMaxPeers = 8;
 struct Mailbox {
-    double smax[kMaxPeers], ssum[kMaxPeers], ssum2[kMaxPeers];
-    unsigned long long W[kMaxPeers];
-    long long flag_stats[kMaxPeers], flag_w[kMaxPeers], flag_done[kMaxPeers];
+    // self-validating words (the trick of NCCL's LL protocol): every 8-byte word carries 32 payload bits and the 32-bit
+    // step number, and an aligned 8-byte store is performed atomically -- so neither side needs a memory fence (a
+    // fence.sys costs ~4 us on B200 and there would be three on the critical path of every step)
+    unsigned long long stats_ll[kMaxPeers][6];   // (max, sum exp, sum exp^2) of shard h as six tagged halves
+    unsigned long long w_ll[kMaxPeers][2];       // integer weight total of shard h
+    long long flag_done[kMaxPeers];              // shard h has written every ancestor it owes for this step
     int error;
     int pad;
 };
+__device__ __forceinline__ void ll_write64(unsigned long long* dst2, unsigned long long value, unsigned int epoch) {
+    *(volatile unsigned long long*)(dst2 + 0) = (value & 0xffffffffull) | ((unsigned long long)epoch << 32);
+    *(volatile unsigned long long*)(dst2 + 1) = (value >> 32) | ((unsigned long long)epoch << 32);
+}
 struct PeerTable {
     int world, rank;
     unsigned int n_loc;   // particles per shard (equal shards)
@@ -71,17 +82,40 @@ struct PeerTable {
 };
 __device__ __forceinline__ unsigned int peer_owner(const PeerTable& p, unsigned int gid) { return p.shift >= 0 ? gid >> p.shift : gid / p.n_loc; }
 
-// one thread: wait until every rank's flag has reached `epoch` (bounded: ~2 s of spinning sets Mailbox::error)
-__device__ __forceinline__ void peer_wait(const PeerTable& p, const long long* flags, long long epoch) {
-    const volatile long long* f = flags;
-    const long long t0 = clock64();
-    for (int h = 0; h < p.world; ++h) {
-        while (f[h] < epoch) {
-            if (clock64() - t0 > 4000000000ll) { p.mail[p.rank]->error = 1; return; }
-            __nanosleep(100);
-        }
+// one thread: bounded spins (~20 s, then Mailbox::error is raised and every later wait returns at once)
+struct SpinGuard {
+    volatile int* err;
+    long long t0;
+    __device__ __forceinline__ SpinGuard(const PeerTable& p) {
+        err = &p.mail[p.rank]->error;
+#ifdef __CUDA_ARCH__
+        t0 = clock64();
+#endif
     }
-    __threadfence_system();
+    __device__ __forceinline__ bool give_up() {
+#ifdef __CUDA_ARCH__
+        if (*err) return true;
+        if (clock64() - t0 > 40000000000ll) { *err = 1; return true; }
+        __nanosleep(100);
+#endif
+        return false;
+    }
+};
+__device__ __forceinline__ unsigned long long ll_read64(const unsigned long long* src2, unsigned int epoch, SpinGuard& g) {
+    const volatile unsigned long long* p = src2;
+    unsigned long long lo, hi;
+    while ((unsigned int)((lo = p[0]) >> 32) != epoch) if (g.give_up()) return 0ull;
+    while ((unsigned int)((hi = p[1]) >> 32) != epoch) if (g.give_up()) return 0ull;
+    return (lo & 0xffffffffull) | (hi << 32);
+}
+__device__ __forceinline__ void peer_wait_done(const PeerTable& p, long long epoch) {
+    SpinGuard g(p);
+    const volatile long long* f = p.mail[p.rank]->flag_done;
+    for (int h = 0; h < p.world; ++h) while (f[h] < epoch) if (g.give_up()) return;
+    __threadfence();
+}
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 template <typename Real> struct VecOf;
@@ -120,7 +154,7 @@ struct ExtendArgs {
 
 constexpr int kExtendThreads = 256;
 
-template <class Model, typename Real, int MODE>
+template <class Model, typename Real, int MODE, bool SHARDED = false>
 __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs<Real> a, Model model) {
     constexpr int D = Model::D;
     constexpr int V = VecOf<Real>::N;
@@ -140,11 +174,8 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
         gather = a.stats->resampled != 0;
         accum = !gather;
     }
-    const bool sharded = a.peer.world > 1;
-    if (sharded && gather) {   // every shard must have finished writing ancestors (and reading the buffer we overwrite)
-        if (tid == 0) peer_wait(a.peer, a.peer.mail[a.peer.rank]->flag_done, t);
-        __syncthreads();
-    }
+    constexpr bool sharded = SHARDED;
+    if (sharded && gather) gate_done(a.peer, a.stats, t);   // ancestors written everywhere; old buffer no longer read
 
     Lse3<Acc> run = lse3_identity<Acc>();
     const size_t stride = (size_t)gridDim.x * kExtendThreads * V;
@@ -163,17 +194,26 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             par[0] = anc_next.x; par[1] = anc_next.y;
             if constexpr (V == 4) { par[2] = anc_next.z; par[3] = anc_next.w; }
             if (base + stride < a.n) anc_next = *reinterpret_cast<const AncVec*>(a.anc + base + stride);
-            if (!sharded) {
+            bool local = true;   // all parents in this shard (always, on one GPU; nearly always when sharded)
+            if (sharded) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    size_t src = (full || base + v < a.n) ? (size_t)par[v] : 0;
+                    par[v] = (full || base + v < a.n) ? par[v] : (int32_t)a.gid_offset;
+                    local = local && ((unsigned int)par[v] - (unsigned int)a.gid_offset < a.peer.n_loc);
+                }
+            }
+            if (local) {
+                const unsigned int off = sharded ? (unsigned int)a.gid_offset : 0u;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    size_t src = (sharded || full || base + v < a.n) ? (size_t)((unsigned int)par[v] - off) : 0;
 #pragma unroll
                     for (int d = 0; d < D; ++d) x[v][d] = __ldg(a.state_in + (size_t)d * a.ld + src);
                 }
-            } else {   // parents are global ids: read them where they live (local HBM or a peer over NVLink)
+            } else {   // parents are global ids: read them where they live (a peer's HBM over NVLink)
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    unsigned int g = (full || base + v < a.n) ? (unsigned int)par[v] : (unsigned int)a.gid_offset;
+                    unsigned int g = (unsigned int)par[v];
                     unsigned int r = peer_owner(a.peer, g);
                     const Real* src = reinterpret_cast<const Real*>(a.peer.state[a.cur][r]) + (g - r * a.peer.n_loc);
 #pragma unroll
@@ -208,8 +248,8 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
         }
         vec_store<Real>(a.lw + base, w);
 
-        if (gather && !sharded && base + stride < a.n) {
-            const size_t nsrc = (size_t)anc_next.x;
+        if (gather && base + stride < a.n && (unsigned int)anc_next.x - (unsigned int)a.gid_offset < (unsigned int)a.n) {
+            const size_t nsrc = (size_t)((unsigned int)anc_next.x - (unsigned int)a.gid_offset);
 #pragma unroll
             for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state_in + (size_t)d * a.ld + nsrc));
         }
@@ -262,13 +302,13 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             st->blocks_done = 0;
             st->resampled = 0;
             st->t = t + 1;
-            if (sharded) {   // post this shard's triple to every rank, then the flag
+            if (a.peer.world > 1) {   // post this shard's triple to every rank (remote stores, self-validating words)
                 for (int h = 0; h < a.peer.world; ++h) {
-                    Mailbox* mb = a.peer.mail[h];
-                    mb->smax[a.peer.rank] = b.m; mb->ssum[a.peer.rank] = b.s; mb->ssum2[a.peer.rank] = b.s2;
+                    unsigned long long* dst = a.peer.mail[h]->stats_ll[a.peer.rank];
+                    ll_write64(dst + 0, (unsigned long long)__double_as_longlong(b.m), (unsigned int)(t + 1));
+                    ll_write64(dst + 2, (unsigned long long)__double_as_longlong(b.s), (unsigned int)(t + 1));
+                    ll_write64(dst + 4, (unsigned long long)__double_as_longlong(b.s2), (unsigned int)(t + 1));
                 }
-                __threadfence_system();
-                for (int h = 0; h < a.peer.world; ++h) *(volatile long long*)&a.peer.mail[h]->flag_stats[a.peer.rank] = t + 1;
             }
         }
     }
@@ -348,46 +388,62 @@ struct FixedArgs {
     long long epoch;          // step number the mailbox flags must have reached; < 0: stats->t
 };
 
-// global (max, W, prefix of lower-ranked shards) for the reduce / scan passes
-struct GlobalWeights {
-    float mx;
-    unsigned long long W, c_offset;
-};
-template <typename Real>
-__device__ __forceinline__ float fixed_global_max(const FixedArgs<Real>& a, bool publish_stats) {
-    // single GPU: the extend epilogue left the exact max in stats.  Sharded: wait for every shard's triple, take the max
-    // (exact, order-free); block 0 also folds the triples in rank order into stats for the host-side queries.
-    if (a.peer.world <= 1) return (float)a.stats->max;
-    const long long epoch = a.epoch < 0 ? a.stats->t : a.epoch;
-    Mailbox* mb = a.peer.mail[a.peer.rank];
-    peer_wait(a.peer, mb->flag_stats, epoch);
-    Lse3<double> acc = lse3_identity<double>();
-    for (int h = 0; h < a.peer.world; ++h) acc = lse3_combine(acc, Lse3<double>{*(volatile double*)&mb->smax[h], *(volatile double*)&mb->ssum[h], *(volatile double*)&mb->ssum2[h]});
-    if (publish_stats) {
-        DeviceStats* st = a.stats;
-        st->max = acc.m; st->sumexp = acc.s; st->sumexp2 = acc.s2;
-        st->ess = (acc.s2 > 0.) ? (acc.s * acc.s) / acc.s2 : 0.;
-        st->degenerate = (acc.m == -INFINITY) ? 1 : 0;
-    }
-    return (float)acc.m;
+// ---- sharded gates: called by every thread of a block at the top of a kernel -----------------------------------------------
+__device__ __forceinline__ void local_ready_wait(const long long* word, long long epoch, const PeerTable& p) {
+    const volatile long long* w = word;
+    volatile int* err = &p.mail[p.rank]->error;
+    while (*w < epoch) { if (*err) break; __nanosleep(50); }
+    __threadfence();
 }
-template <typename Real>
-__device__ __forceinline__ GlobalWeights fixed_global_weights(const FixedArgs<Real>& a) {
-    GlobalWeights g;
-    if (a.peer.world <= 1) { g.mx = (float)a.stats->max; g.W = a.stats->W; g.c_offset = 0; return g; }
-    const long long epoch = a.epoch < 0 ? a.stats->t : a.epoch;
-    Mailbox* mb = a.peer.mail[a.peer.rank];
-    peer_wait(a.peer, mb->flag_w, epoch);
-    double m = -INFINITY;
-    g.W = 0; g.c_offset = 0;
-    for (int h = 0; h < a.peer.world; ++h) {
-        unsigned long long w = *(volatile unsigned long long*)&mb->W[h];
-        if (h < a.peer.rank) g.c_offset += w;
-        g.W += w;
-        m = fmax(m, *(volatile double*)&mb->smax[h]);
+__device__ __forceinline__ void local_ready_set(long long* word, long long epoch) {
+    __threadfence();
+    *(volatile long long*)word = epoch;
+}
+// every shard's (max, sum exp, sum exp^2) has arrived: fold them in rank order (deterministic) into stats
+__device__ __forceinline__ void gate_stats(const PeerTable& p, DeviceStats* st, long long epoch) {
+    if (p.world <= 1) return;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            Mailbox* mb = p.mail[p.rank];
+            SpinGuard g(p);
+            Lse3<double> acc = lse3_identity<double>();
+            for (int h = 0; h < p.world; ++h) {
+                double m = __longlong_as_double((long long)ll_read64(&mb->stats_ll[h][0], (unsigned int)epoch, g));
+                double s1 = __longlong_as_double((long long)ll_read64(&mb->stats_ll[h][2], (unsigned int)epoch, g));
+                double s2 = __longlong_as_double((long long)ll_read64(&mb->stats_ll[h][4], (unsigned int)epoch, g));
+                acc = lse3_combine(acc, Lse3<double>{m, s1, s2});
+            }
+            st->max = acc.m; st->sumexp = acc.s; st->sumexp2 = acc.s2;
+            st->ess = (acc.s2 > 0.) ? (acc.s * acc.s) / acc.s2 : 0.;
+            st->degenerate = (acc.m == -INFINITY) ? 1 : 0;
+            local_ready_set(&st->ready_stats, epoch);
+        } else local_ready_wait(&st->ready_stats, epoch, p);
     }
-    g.mx = (float)m;
-    return g;
+    __syncthreads();
+}
+// every shard's integer weight total has arrived: global W and this shard's prefix
+__device__ __forceinline__ void gate_weights(const PeerTable& p, DeviceStats* st, long long epoch) {
+    if (p.world <= 1) return;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            Mailbox* mb = p.mail[p.rank];
+            SpinGuard g(p);
+            unsigned long long W = 0, c = 0;
+            for (int h = 0; h < p.world; ++h) { unsigned long long w = ll_read64(&mb->w_ll[h][0], (unsigned int)epoch, g); if (h < p.rank) c += w; W += w; }
+            st->W = W; st->c_offset = c;
+            local_ready_set(&st->ready_w, epoch);
+        } else local_ready_wait(&st->ready_w, epoch, p);
+    }
+    __syncthreads();
+}
+// every shard has written all the ancestors it owes (and is done reading the state buffer about to be overwritten)
+__device__ __forceinline__ void gate_done(const PeerTable& p, DeviceStats* st, long long epoch) {
+    if (p.world <= 1) return;
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) { peer_wait_done(p, epoch); local_ready_set(&st->ready_done, epoch); }
+        else local_ready_wait(&st->ready_done, epoch, p);
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ unsigned long long resample_rand_word(uint64_t seed, long long rt, const DeviceStats* st) {
@@ -432,10 +488,8 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
     __shared__ unsigned long long ws[kScanThreads / 32];
     __shared__ unsigned long long carry_s;
     __shared__ bool is_last;
-    __shared__ float mx_s;
-    if (tid == 0) mx_s = fixed_global_max<Real>(a, blockIdx.x == 0);
-    __syncthreads();
-    const float mx = mx_s;
+    gate_stats(a.peer, a.stats, a.epoch < 0 ? a.stats->t : a.epoch);
+    const float mx = (float)a.stats->max;
     {
         const unsigned int tile = blockIdx.x;
         unsigned long long sum = 0;
@@ -494,12 +548,11 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
     }
     if (tid == 0) {
         DeviceStats* st = a.stats;
-        st->W = carry_s; st->overflow_count = 0; st->blocks_done = 0;
-        if (a.peer.world > 1) {   // post this shard's integer weight to every rank
+        st->overflow_count = 0; st->blocks_done = 0;
+        if (a.peer.world <= 1) { st->W = carry_s; st->c_offset = 0; }
+        else {   // post this shard's integer weight to every rank (the scan's gate sums them into st->W)
             const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-            for (int h = 0; h < a.peer.world; ++h) a.peer.mail[h]->W[a.peer.rank] = carry_s;
-            __threadfence_system();
-            for (int h = 0; h < a.peer.world; ++h) *(volatile long long*)&a.peer.mail[h]->flag_w[a.peer.rank] = epoch;
+            for (int h = 0; h < a.peer.world; ++h) ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], carry_s, (unsigned int)epoch);
         }
     }
 }
@@ -546,7 +599,6 @@ struct __align__(16) ScanShared {
     unsigned long long tile_excl;
     unsigned long long rand_word;
     TileBase base;
-    GlobalWeights gw;
     __align__(16) unsigned int nloc[kScanTile];             // inclusive offspring counts, relative to the tile's first output slot
     __align__(16) unsigned short head[kScanTile];   // expansion buffer: (local parent + 1) at the first slot of each run
     unsigned int warp_max[kScanThreads / 32];
@@ -715,19 +767,17 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
     if (a.dynamic && !a.stats->do_resample) return;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x;
-    if (tid == 0) {   // global weights (sharded: from the mailbox), then the exact slot base of this tile
-        GlobalWeights g = fixed_global_weights<Real>(a);
-        sh.gw = g;
-        if (g.W != 0ull) {
-            const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), g.W);
-            sh.base = tile_base_exact(g.c_offset + a.desc[tile], g.W, U, a.n_out, 1. / (double)g.W);
+    gate_weights(a.peer, st, a.epoch < 0 ? st->t : a.epoch);
+    const unsigned long long W = st->W;
+    const float mx = (float)st->max;
+    if (tid == 0) {   // exact slot base of this tile from its exclusive prefix (reduce pass) and the shard's offset
+        if (W != 0ull) {
+            const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
+            sh.base = tile_base_exact(st->c_offset + a.desc[tile], W, U, a.n_out, 1. / (double)W);
         }
         a.desc[tile] = 0ull;   // ready for the next reduce pass
     }
     clear_heads(sh);
-    __syncthreads();
-    const unsigned long long W = sh.gw.W;
-    const float mx = sh.gw.mx;
     if (W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors, flagged
         for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
         if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; }
@@ -735,7 +785,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
     }
     const double inv_w = 1. / (double)W;
     unsigned long long q[kScanRounds][4], excl[kScanRounds];
-    tile_local_scan<Real>(a, sh, tile, mx, q, excl);
+    tile_local_scan<Real>(a, sh, tile, mx, q, excl);   // (contains the barrier that publishes sh.base and the cleared heads)
     const TileBase base = sh.base;
     tile_fill_nloc<Real>(a, sh, base, W, inv_w, q, excl);
     __syncthreads();
@@ -747,7 +797,6 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
         st->ess_stale = st->ess;
         if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
         st->resampled = 1;
-        st->W = W;
     }
     if (total == 0u) return;
     if (total > kHeavyCap) {
@@ -770,10 +819,8 @@ __global__ void __launch_bounds__(kScanThreads) fixed_overflow_kernel(FixedArgs<
     const unsigned int count = st->overflow_count;
     if (count == 0u && a.peer.world <= 1) return;
     if (count != 0u) {
-        if (threadIdx.x == 0) sh.gw = fixed_global_weights<Real>(a);
-        __syncthreads();
-        const unsigned long long W = sh.gw.W;
-        const float mx = sh.gw.mx;
+        const unsigned long long W = st->W;
+        const float mx = (float)st->max;
         const double inv_w = 1. / (double)W;
         for (unsigned int k = 0; k < count; ++k) {
             const OverflowEntry e = a.overflow[k];
@@ -786,15 +833,25 @@ __global__ void __launch_bounds__(kScanThreads) fixed_overflow_kernel(FixedArgs<
                 expand_chunk<Real>(a, sh, e.tile, e.n_start, (unsigned int)chunk_base, e.total, false);
         }
     }
-    if (a.peer.world > 1) {   // last block: every ancestor this shard owes anybody is written -> tell every rank
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) {
-                st->ticket = 0;
-                const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    if (a.peer.world > 1) {   // every ancestor this shard owes anybody is written -> tell every rank
+        // no heavy tiles: the scan kernel (complete at this kernel's start) wrote everything, one thread signals.
+        // heavy tiles: blocks fence their own remote stores, the last one to finish signals.
+        bool signal = false;
+        if (count == 0u) signal = (blockIdx.x == 0 && threadIdx.x == 0);
+        else {
+            __syncthreads();
+            if (threadIdx.x == 0) {
                 __threadfence_system();
-                for (int h = 0; h < a.peer.world; ++h) *(volatile long long*)&a.peer.mail[h]->flag_done[a.peer.rank] = epoch;
+                if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) { st->ticket = 0; signal = true; }
+            }
+        }
+        if (signal) {
+            // count == 0: the remote stores all belong to the scan kernel, which completed (and was flushed) before this
+            // kernel started, so a plain store is ordered behind them; otherwise release after the blocks' own fences
+            const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+            for (int h = 0; h < a.peer.world; ++h) {
+                if (count == 0u) *(volatile long long*)&a.peer.mail[h]->flag_done[a.peer.rank] = epoch;
+                else st_release_sys(&a.peer.mail[h]->flag_done[a.peer.rank], epoch);
             }
         }
     }

@@ -56,7 +56,8 @@ def virtual_shards(model, n_global, world, obs, dtype="f32", seed=0):
     D = model.state_dim
     st = np.empty((D, n_global), dtype=np.float64)
     lw = np.empty(n_global, dtype=np.float64)
-    lml = C.c_double()
+    lml, ms = C.c_double(), C.c_double()
     check(lib.mpl_test_virtual_shards(model._h, n_global, world, 1 if dtype == "f64" else 0, seed, ys.ctypes.data_as(_lib.c_double_p), ys.shape[0], ys.shape[1],
-                                      st.ctypes.data_as(_lib.c_double_p), lw.ctypes.data_as(_lib.c_double_p), C.byref(lml)))
+                                      st.ctypes.data_as(_lib.c_double_p), lw.ctypes.data_as(_lib.c_double_p), C.byref(lml), C.byref(ms)))
+    virtual_shards.last_loop_ms = ms.value
     return st, lw, lml.value
