@@ -245,8 +245,8 @@ __device__ __forceinline__ float exp2_poly(float f) {
     p = __fmaf_rn(p, f, 1.0f);
     return p;
 }
-__device__ __forceinline__ uint64_t fixed_weight(float d, int kbits) {
-    // branch-free; d = lw - max <= 0.  NaN and anything below -100 (incl. -inf) come out as 0.
+__device__ __forceinline__ uint64_t fixed_weight(float d, int kbits, float* qf = nullptr) {
+    // branch-free; d = lw - max <= 0.  NaN and anything below -100 (incl. -inf) come out as 0.  *qf: the weight as a float.
     d = fmaxf(d, -100.0f);                                   // fmaxf(NaN, x) = x
     float y = __fmul_rn(d, 1.44269504088896341f);
     float t = __fadd_rn(y, 12582912.0f);                     // 1.5 * 2^23: rounds y to the nearest integer (ties to even)
@@ -255,7 +255,9 @@ __device__ __forceinline__ uint64_t fixed_weight(float d, int kbits) {
     float f = __fsub_rn(y, n);                               // exact, in [-0.5, 0.5]
     float p = exp2_poly(f);                                  // in [0.70, 1.42]
     float scale = __int_as_float((127 + kbits + ni) << 23);  // 2^(kbits + n): exponent >= 127 + 36 - 145 > 0, never denormal
-    return __float2ull_rn(__fmul_rn(p, scale));              // exact product, then round-to-nearest-even to an integer
+    float v = __fmul_rn(p, scale);                           // exact product
+    if (qf) *qf = v;
+    return __float2ull_rn(v);                                // round-to-nearest-even to an integer
 }
 inline int fixed_kbits(uint64_t n_total) {
     int lg = 0;

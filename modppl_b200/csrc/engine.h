@@ -53,7 +53,12 @@ struct mpl_ps {
     double* staging;   // ld*max(D,1) doubles for read/write conversions
     int grid_extend, grid_reduce;
     long long t;       // next kernel time index (host mirror)
-    bool initialised, pending_gather, stats_valid;
+    bool initialised, pending_gather;
+    bool stats_valid;   // stats->{max,sumexp,sumexp2,ess} describe the current log-weights (weight_reduce ran)
+    bool max_valid;     // stats->max_bits[(t-1)&1] holds their exact max (left by the last extend)
+    double* sq_partials;   // per-tile sums of squared weights (ESS in the integer resampler)
+    int* host_flags;       // pinned + mapped: [0] = a heavy tile was seen (launch the overflow pass from now on)
+    int* host_flags_dev;
     bool profile;
     std::map<std::string, mpl::KernelTimer> timers;
     uint64_t launch_count;

@@ -120,6 +120,7 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     a.peer = ps->peer;
     a.cur = ps->cur;
     if (mode == EXT_DYNAMIC) a.state_out = (Real*)ps->state[ps->cur ^ 1];
+    if (mode == EXT_INIT) MPL_CUDA_OK(cudaMemsetAsync(ps->stats->max_bits, 0, sizeof(ps->stats->max_bits), ps->stream));
     const int grid = ps->grid_extend;
     {
         ScopedLaunch sl(ps, mode == EXT_INIT ? "init" : "extend");
@@ -196,7 +197,7 @@ static int materialise(mpl_ps* ps) {
     MPL_CUDA_OK(cudaGetLastError());
     ps->cur ^= 1;
     ps->pending_gather = false;
-    ps->stats_valid = false;
+    ps->stats_valid = false; ps->max_valid = false;
     return MPL_OK;
 }
 
@@ -215,6 +216,10 @@ static FixedArgs<Real> fixed_args(mpl_ps* ps, bool dynamic, bool dev_t) {
     a.src_base = (int32_t)ps->gid_offset;   // ancestors are global ids (== local indices on a single GPU)
     a.peer = ps->peer;
     a.epoch = dev_t ? -1 : ps->t;
+    a.max_slot = (ps->world > 1 || ps->stats_valid) ? -1 : (int)((ps->t - 1) & 1);
+    a.overflow_follows = (ps->world > 1 || ps->host_flags[0] != 0) ? 1 : 0;
+    a.overflow_seen_host = ps->host_flags_dev;
+    a.sq_partials = ps->sq_partials;
     a.desc = ps->desc;
     a.overflow = ps->overflow;
     a.stats = ps->stats;
@@ -241,7 +246,7 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
             fixed_scan_kernel<Real><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
         }
         MPL_CUDA_OK(cudaGetLastError());
-        {
+        if (a.overflow_follows) {
             ScopedLaunch sl(ps, "fixed_overflow");
             fixed_overflow_kernel<Real><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a);
         }
@@ -300,8 +305,11 @@ static int do_resample(mpl_ps* ps, int scheme) {
     if (ps->world > 1 && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED) return fail(MPL_ERR_UNSUPPORTED, "sharded particle systems support MPL_RESAMPLE_SYSTEMATIC_FIXED only");
     int rc = materialise(ps);   // resample twice in a row: apply the first one
     if (rc) return rc;
-    rc = ensure_stats(ps);
-    if (rc) return rc;
+    const bool exact = scheme == MPL_RESAMPLE_MULTINOMIAL || scheme == MPL_RESAMPLE_SYSTEMATIC;
+    if (exact || !ps->max_valid) {   // the reference scheme needs log-sum-exp; the integer schemes only the max (left by the extend)
+        rc = ensure_stats(ps);
+        if (rc) return rc;
+    }
     switch (scheme) {
         case MPL_RESAMPLE_MULTINOMIAL:
         case MPL_RESAMPLE_SYSTEMATIC: rc = resample_exact(ps, scheme); break;
@@ -313,7 +321,7 @@ static int do_resample(mpl_ps* ps, int scheme) {
     }
     if (rc) return rc;
     ps->pending_gather = true;
-    ps->stats_valid = false;
+    ps->stats_valid = false; ps->max_valid = false;
     return MPL_OK;
 }
 
@@ -323,10 +331,10 @@ int ps_phase_extend(mpl_ps* ps, bool init) {
     if (init) {
         ps->t = 0; ps->pending_gather = false;
         rc = launch_extend(ps, EXT_INIT, dummy, true, false);
-        ps->t = 1; ps->initialised = true; ps->stats_valid = true;
+        ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
     } else {
         rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false);
-        ps->pending_gather = false; ps->t += 1; ps->stats_valid = true;
+        ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
     }
     return rc;
 }
@@ -343,14 +351,14 @@ int ps_phase_scan(mpl_ps* ps) {
     if (ps->dtype == MPL_F32) {
         auto a = fixed_args<float>(ps, false, false);
         { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan_kernel<float><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
-        { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow_kernel<float><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a); }
+        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow_kernel<float><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a); }
     } else {
         auto a = fixed_args<double>(ps, false, false);
         { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan_kernel<double><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
-        { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow_kernel<double><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a); }
+        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow_kernel<double><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a); }
     }
     MPL_CUDA_OK(cudaGetLastError());
-    ps->pending_gather = true; ps->stats_valid = false;
+    ps->pending_gather = true; ps->stats_valid = false; ps->max_valid = false;
     return MPL_OK;
 }
 
@@ -423,7 +431,8 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->ld = (num_particles + kScanTile - 1) / kScanTile * kScanTile;
     ps->seed = c.seed; ps->gid_offset = c.gid_offset; ps->n_global = c.n_global ? c.n_global : num_particles;
     ps->D = model->state_dim;
-    ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false;
+    ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
+    ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
     ps->probs = nullptr; ps->cums = nullptr; ps->icum = nullptr; ps->obs_dev = nullptr; ps->obs_steps = 0; ps->staging = nullptr;
@@ -445,6 +454,9 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ok = ok && cudaMallocHost(&ps->stats_host, sizeof(DeviceStats)) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->partials, kNumSMs * 8 * sizeof(Lse3<double>)) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->ipartials, kNumSMs * 8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->sq_partials, num_tiles * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ps->host_flags, 64, cudaHostAllocMapped) == cudaSuccess;
+    if (ok) { std::memset(ps->host_flags, 0, 64); ok = cudaHostGetDevicePointer(&ps->host_flags_dev, ps->host_flags, 0) == cudaSuccess; }
     if (ok) {
         // particle_filter.rs:44-57: zero log-weights, zero log-ML.  ESS of the all-zero stale buffer is 1/N (quirk Q1).
         DeviceStats init;
@@ -472,6 +484,7 @@ extern "C" void mpl_ps_destroy(mpl_ps* ps) {
     for (auto& kv : ps->timers) for (auto& pr : kv.second.pending) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaFree(ps->state[0]); cudaFree(ps->state[1]); cudaFree(ps->lw); cudaFree(ps->anc); cudaFree(ps->desc); cudaFree(ps->overflow);
     cudaFree(ps->stats); cudaFreeHost(ps->stats_host); cudaFree(ps->partials); cudaFree(ps->ipartials);
+    cudaFree(ps->sq_partials); if (ps->host_flags) cudaFreeHost(ps->host_flags);
     if (ps->world > 1 && !ps->peer_virtual) mpl_ps_peer_detach(ps);
     cudaFree(ps->mailbox);
     cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
@@ -500,7 +513,7 @@ extern "C" int mpl_ps_init_step(mpl_ps* ps, const double* obs, size_t n_obs) {
     ps->pending_gather = false;
     rc = launch_extend(ps, EXT_INIT, o, false, false);
     if (rc) return rc;
-    ps->t = 1; ps->initialised = true; ps->stats_valid = true;
+    ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
     return MPL_OK;
 }
 
@@ -514,7 +527,7 @@ extern "C" int mpl_ps_step(mpl_ps* ps, const double* obs, size_t n_obs) {
     rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, o, false, false);
     if (rc) return rc;
     ps->pending_gather = false;
-    ps->t += 1; ps->stats_valid = true;
+    ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
     return MPL_OK;
 }
 
@@ -608,7 +621,7 @@ extern "C" int mpl_ps_write(mpl_ps* ps, int what, const void* host_src, size_t b
         MPL_CUDA_OK(cudaMemcpyAsync(ps->staging, host_src, bytes, cudaMemcpyHostToDevice, ps->stream));
         if (ps->dtype == MPL_F32) from_f64_kernel<float><<<grid, 256, 0, ps->stream>>>(ps->staging, (float*)ps->lw, ps->n);
         else from_f64_kernel<double><<<grid, 256, 0, ps->stream>>>(ps->staging, (double*)ps->lw, ps->n);
-        ps->stats_valid = false;
+        ps->stats_valid = false; ps->max_valid = false;
     } else if (what == MPL_READ_STATE) {
         if (bytes != (size_t)ps->D * ps->n * sizeof(double)) return fail(MPL_ERR_INVALID, "state buffer must be double[D*N]");
         for (int d = 0; d < ps->D; ++d) {
@@ -665,10 +678,10 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
         if (tt == 0) {
             ps->t = 0; ps->pending_gather = false;
             rc = launch_extend(ps, EXT_INIT, dummy, true, false);
-            ps->t = 1; ps->initialised = true; ps->stats_valid = true;
+            ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
         } else {
             rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false);
-            ps->pending_gather = false; ps->t += 1; ps->stats_valid = true;
+            ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
         }
         if (rc == MPL_OK) rc = do_resample(ps, scheme);
     }

@@ -31,7 +31,7 @@ struct DeviceStats {
     unsigned long long W;          // total integer weight (fixed schemes)
     unsigned long long rand_word;  // systematic offset word of this resample
     long long t;                   // next kernel time index (device copy, for mpl_ps_run)
-    unsigned int max_ordered;      // atomicMax target for the exact global max (float path)
+    unsigned int max_ordered;      // (unused)
     unsigned int blocks_done;      // last-block-done counter of the extend epilogue
     unsigned int ticket;           // (unused)
     unsigned int overflow_count;
@@ -42,6 +42,7 @@ struct DeviceStats {
     // sharded runs: block 0 of a kernel waits for the peers (system scope), publishes the global values into this
     // struct and then raises the matching ready word; the kernel's other blocks only watch that local word
     unsigned long long c_offset;   // integer weight of all lower-ranked shards
+    unsigned long long max_bits[2];   // exact max of the log-weights written by the extend of step t, slot t & 1 (order-preserving bits)
     long long ready_stats, ready_w, ready_done;
 };
 
@@ -63,7 +64,7 @@ struct Mailbox {
     // step number, and an aligned 8-byte store is performed atomically -- so neither side needs a memory fence (a
     // fence.sys costs ~4 us on B200 and there would be three on the critical path of every step)
     unsigned long long stats_ll[kMaxPeers][6];   // (max, sum exp, sum exp^2) of shard h as six tagged halves
-    unsigned long long w_ll[kMaxPeers][2];       // integer weight total of shard h
+    unsigned long long w_ll[kMaxPeers][4];       // integer weight total of shard h, and its sum of squared weights
     long long flag_done[kMaxPeers];              // shard h has written every ancestor it owes for this step
     int error;
     int pad;
@@ -118,6 +119,15 @@ __device__ __forceinline__ void st_release_sys(long long* p, long long v) {
     asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long ordered_bits(double x) {
+    long long b = __double_as_longlong(x);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double from_ordered_bits(unsigned long long u) {
+    if (u == 0ull) return -INFINITY;   // slot never touched: no finite weight
+    return __longlong_as_double((long long)((u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u));
+}
+
 template <typename Real> struct VecOf;
 template <> struct VecOf<float> { typedef float4 type; static constexpr int N = 4; };
 template <> struct VecOf<double> { typedef double2 type; static constexpr int N = 2; };
@@ -158,7 +168,6 @@ template <class Model, typename Real, int MODE, bool SHARDED = false>
 __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs<Real> a, Model model) {
     constexpr int D = Model::D;
     constexpr int V = VecOf<Real>::N;
-    typedef Real Acc;
     const int tid = threadIdx.x;
 
     long long t = a.t;
@@ -177,7 +186,8 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
     constexpr bool sharded = SHARDED;
     if (sharded && gather) gate_done(a.peer, a.stats, t);   // ancestors written everywhere; old buffer no longer read
 
-    Lse3<Acc> run = lse3_identity<Acc>();
+    Real run_max = (Real)-INFINITY;
+    if (blockIdx.x == 0 && tid == 0) a.stats->max_bits[(t + 1) & 1] = 0ull;   // slot of the next step (its last reader finished before this launch)
     const size_t stride = (size_t)gridDim.x * kExtendThreads * V;
     typedef typename std::conditional<V == 4, int4, int2>::type AncVec;
     size_t base = ((size_t)blockIdx.x * kExtendThreads + tid) * V;
@@ -254,64 +264,43 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state_in + (size_t)d * a.ld + nsrc));
         }
 
-        // online (max, sum exp, sum exp^2)
-        Acc m = (Acc)-INFINITY;
+        // exact running max of the log-weights (NaN and padding lanes count as -inf, quirk Q9).  Sum statistics are not
+        // needed on this path: the integer resampler derives the log total weight and the ESS from its own sums, and
+        // ESS / log-ML queries run weight_reduce_kernel on demand.
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             bool ok = (full || base + v < a.n) && (w[v] == w[v]);
-            w[v] = ok ? w[v] : (Real)-INFINITY;
-            m = fmax(m, (Acc)w[v]);
-        }
-        if (m > (Acc)-INFINITY) {
-            Acc s1 = 0, s2 = 0;
-#pragma unroll
-            for (int v = 0; v < V; ++v) { Acc e = stat_exp((Acc)w[v] - m); s1 += e; s2 += e * e; }
-            run = lse3_combine(run, Lse3<Acc>{m, s1, s2});
+            run_max = fmax(run_max, ok ? w[v] : (Real)-INFINITY);
         }
     }
 
-    // block reduction -> partial -> last block finalises (deterministic order)
-    __shared__ Lse3<double> warp_part[kExtendThreads / 32];
+    __shared__ Real warp_max_s[kExtendThreads / 32];
     __shared__ bool is_last;
-    Lse3<Acc> wr = lse3_warp_reduce(run);
-    if ((tid & 31) == 0) warp_part[tid >> 5] = Lse3<double>{(double)wr.m, (double)wr.s, (double)wr.s2};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) run_max = fmax(run_max, __shfl_xor_sync(0xffffffffu, run_max, o));
+    if ((tid & 31) == 0) warp_max_s[tid >> 5] = run_max;
     __syncthreads();
     if (tid == 0) {
-        Lse3<double> b = warp_part[0];
-        for (int i = 1; i < kExtendThreads / 32; ++i) b = lse3_combine(b, warp_part[i]);
-        a.partials[blockIdx.x] = b;
-        __threadfence();
-        unsigned int done = atomicAdd(&a.stats->blocks_done, 1u);
-        is_last = (done == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        Lse3<double> acc = lse3_identity<double>();
-        for (unsigned int i = tid; i < gridDim.x; i += kExtendThreads) acc = lse3_combine(acc, a.partials[i]);
-        acc = lse3_warp_reduce(acc);
-        if ((tid & 31) == 0) warp_part[tid >> 5] = acc;
-        __syncthreads();
-        if (tid == 0) {
-            Lse3<double> b = warp_part[0];
-            for (int i = 1; i < kExtendThreads / 32; ++i) b = lse3_combine(b, warp_part[i]);
-            DeviceStats* st = a.stats;
-            st->max = b.m; st->sumexp = b.s; st->sumexp2 = b.s2;
-            st->ess = (b.s2 > 0.) ? (b.s * b.s) / b.s2 : 0.;
-            st->degenerate = (b.m == -INFINITY) ? 1 : 0;
-            st->blocks_done = 0;
-            st->resampled = 0;
-            st->t = t + 1;
-            if (a.peer.world > 1) {   // post this shard's triple to every rank (remote stores, self-validating words)
+        Real bm = warp_max_s[0];
+#pragma unroll
+        for (int i = 1; i < kExtendThreads / 32; ++i) bm = fmax(bm, warp_max_s[i]);
+        if (bm > (Real)-INFINITY) atomicMax(&a.stats->max_bits[t & 1], ordered_bits((double)bm));
+        is_last = false;
+        if (a.peer.world > 1) {   // sharded: the last block posts this shard's max to every rank
+            __threadfence();
+            is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
+            if (is_last) {
+                a.stats->blocks_done = 0;
+                __threadfence();
+                const double m = from_ordered_bits(*(volatile unsigned long long*)&a.stats->max_bits[t & 1]);
                 for (int h = 0; h < a.peer.world; ++h) {
                     unsigned long long* dst = a.peer.mail[h]->stats_ll[a.peer.rank];
-                    ll_write64(dst + 0, (unsigned long long)__double_as_longlong(b.m), (unsigned int)(t + 1));
-                    ll_write64(dst + 2, (unsigned long long)__double_as_longlong(b.s), (unsigned int)(t + 1));
-                    ll_write64(dst + 4, (unsigned long long)__double_as_longlong(b.s2), (unsigned int)(t + 1));
+                    ll_write64(dst + 0, (unsigned long long)__double_as_longlong(m), (unsigned int)(t + 1));
                 }
             }
         }
     }
+    (void)is_last;
 }
 
 // ================================================================================================
@@ -371,6 +360,7 @@ struct FixedArgs {
     int kbits;
     unsigned long long n_out; // global number of offspring (N_global)
     unsigned long long c_offset;   // integer weight of all lower-ranked shards
+    unsigned long long max_bits[2];   // exact max of the log-weights written by the extend of step t, slot t & 1 (order-preserving bits)
     unsigned long long out_base;   // global index of this shard's first output slot
     unsigned long long n_out_local;
     double log_n_global;
@@ -386,7 +376,15 @@ struct FixedArgs {
     int dynamic;              // 1: skip unless stats->do_resample (ESS-triggered, device-resident loop)
     PeerTable peer;           // world == 1: single GPU
     long long epoch;          // step number the mailbox flags must have reached; < 0: stats->t
+    int max_slot;             // >= 0: the max lives in stats->max_bits[max_slot] (left by the extend); < 0: in stats->max
+    int overflow_follows;     // 1: a fixed_overflow_kernel launch follows the scan (heavy tiles are queued for it)
+    int* overflow_seen_host;  // mapped host word, raised when any tile exceeds the heavy cap
+    double* sq_partials;      // per tile: sum of (q * 2^-k)^2, for ESS = W^2 / sum q^2
 };
+template <typename Real>
+__device__ __forceinline__ float fixed_max(const FixedArgs<Real>& a) {
+    return (float)(a.max_slot >= 0 ? from_ordered_bits(a.stats->max_bits[a.max_slot]) : a.stats->max);
+}
 
 // ---- sharded gates: called by every thread of a block at the top of a kernel -----------------------------------------------
 __device__ __forceinline__ void local_ready_wait(const long long* word, long long epoch, const PeerTable& p) {
@@ -399,23 +397,16 @@ __device__ __forceinline__ void local_ready_set(long long* word, long long epoch
     __threadfence();
     *(volatile long long*)word = epoch;
 }
-// every shard's (max, sum exp, sum exp^2) has arrived: fold them in rank order (deterministic) into stats
+// every shard's max has arrived: the global max is exact and order-free
 __device__ __forceinline__ void gate_stats(const PeerTable& p, DeviceStats* st, long long epoch) {
     if (p.world <= 1) return;
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
             Mailbox* mb = p.mail[p.rank];
             SpinGuard g(p);
-            Lse3<double> acc = lse3_identity<double>();
-            for (int h = 0; h < p.world; ++h) {
-                double m = __longlong_as_double((long long)ll_read64(&mb->stats_ll[h][0], (unsigned int)epoch, g));
-                double s1 = __longlong_as_double((long long)ll_read64(&mb->stats_ll[h][2], (unsigned int)epoch, g));
-                double s2 = __longlong_as_double((long long)ll_read64(&mb->stats_ll[h][4], (unsigned int)epoch, g));
-                acc = lse3_combine(acc, Lse3<double>{m, s1, s2});
-            }
-            st->max = acc.m; st->sumexp = acc.s; st->sumexp2 = acc.s2;
-            st->ess = (acc.s2 > 0.) ? (acc.s * acc.s) / acc.s2 : 0.;
-            st->degenerate = (acc.m == -INFINITY) ? 1 : 0;
+            double m = -INFINITY;
+            for (int h = 0; h < p.world; ++h) m = fmax(m, __longlong_as_double((long long)ll_read64(&mb->stats_ll[h][0], (unsigned int)epoch, g)));
+            st->max = m;
             local_ready_set(&st->ready_stats, epoch);
         } else local_ready_wait(&st->ready_stats, epoch, p);
     }
@@ -429,8 +420,16 @@ __device__ __forceinline__ void gate_weights(const PeerTable& p, DeviceStats* st
             Mailbox* mb = p.mail[p.rank];
             SpinGuard g(p);
             unsigned long long W = 0, c = 0;
-            for (int h = 0; h < p.world; ++h) { unsigned long long w = ll_read64(&mb->w_ll[h][0], (unsigned int)epoch, g); if (h < p.rank) c += w; W += w; }
+            double sq = 0.;
+            for (int h = 0; h < p.world; ++h) {
+                unsigned long long w = ll_read64(&mb->w_ll[h][0], (unsigned int)epoch, g);
+                sq += __longlong_as_double((long long)ll_read64(&mb->w_ll[h][2], (unsigned int)epoch, g));
+                if (h < p.rank) c += w;
+                W += w;
+            }
             st->W = W; st->c_offset = c;
+            st->sumexp2 = sq;
+            st->ess = sq > 0. ? ((double)W * (double)W) / sq : 0.;
             local_ready_set(&st->ready_w, epoch);
         } else local_ready_wait(&st->ready_w, epoch, p);
     }
@@ -455,7 +454,7 @@ __device__ __forceinline__ unsigned long long resample_rand_word(uint64_t seed, 
 
 // 4 consecutive log-weights -> 4 integer weights; out-of-range lanes give 0 (FULL: the whole tile is in range)
 template <typename Real, bool FULL>
-__device__ __forceinline__ void load_q4(const Real* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4]) {
+__device__ __forceinline__ void load_q4(const Real* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4], float* sq = nullptr) {
     float w[4];
     if constexpr (sizeof(Real) == 4) {
         float4 v = *reinterpret_cast<const float4*>(lw + idx);
@@ -466,8 +465,11 @@ __device__ __forceinline__ void load_q4(const Real* lw, size_t idx, size_t n, fl
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        unsigned long long v = fixed_weight(__fsub_rn(w[j], mx), kbits);
-        q[j] = (FULL || idx + j < n) ? v : 0ull;
+        float qf;
+        unsigned long long v = fixed_weight(__fsub_rn(w[j], mx), kbits, &qf);
+        const bool in = FULL || idx + j < n;
+        q[j] = in ? v : 0ull;
+        if (sq && in) *sq = fmaf(qf, qf, *sq);
     }
 }
 
@@ -486,19 +488,21 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
     if (a.dynamic && !a.stats->do_resample) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ unsigned long long ws[kScanThreads / 32];
+    __shared__ double wsq[kScanThreads / 32];
     __shared__ unsigned long long carry_s;
     __shared__ bool is_last;
     gate_stats(a.peer, a.stats, a.epoch < 0 ? a.stats->t : a.epoch);
-    const float mx = (float)a.stats->max;
+    const float mx = fixed_max<Real>(a);
     {
         const unsigned int tile = blockIdx.x;
         unsigned long long sum = 0;
+        float sqf = 0.f;   // sum of squared weights of this thread's 16 particles (for the ESS)
         const size_t tile_base = (size_t)tile * kScanTile;
         if (tile_base + kScanTile <= a.n) {
 #pragma unroll
             for (int r = 0; r < kScanRounds; ++r) {
                 unsigned long long q[4];
-                load_q4<Real, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q);
+                load_q4<Real, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q, &sqf);
                 sum += q[0] + q[1] + q[2] + q[3];
             }
         } else {
@@ -507,16 +511,24 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
                 size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
                 if (idx < a.n) {
                     unsigned long long q[4];
-                    load_q4<Real, false>(a.lw, idx, a.n, mx, a.kbits, q);
+                    load_q4<Real, false>(a.lw, idx, a.n, mx, a.kbits, q, &sqf);
                     sum += q[0] + q[1] + q[2] + q[3];
                 }
             }
         }
+        double sq = (double)sqf;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
         if (lane == 0 && sum) atomicAdd(&a.desc[tile], sum);
+        if (lane == 0) wsq[warp] = sq;
     }
     __syncthreads();
+    if (tid == 0) {   // fixed summation order: the ESS is reproducible
+        double b = 0.;
+#pragma unroll
+        for (int i = 0; i < kScanThreads / 32; ++i) b += wsq[i];
+        a.sq_partials[blockIdx.x] = b;
+    }
     if (tid == 0) {
         __threadfence();
         is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
@@ -546,13 +558,30 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
         if (tid == 0) carry_s += all;
         __syncthreads();
     }
+    // sum of squared weights over the tiles, in tile order
+    double sqt = 0.;
+    for (unsigned int i = tid; i < num_tiles; i += kScanThreads) sqt += a.sq_partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sqt += __shfl_xor_sync(0xffffffffu, sqt, o);
+    __syncthreads();
+    if (lane == 0) wsq[warp] = sqt;
+    __syncthreads();
     if (tid == 0) {
         DeviceStats* st = a.stats;
         st->overflow_count = 0; st->blocks_done = 0;
-        if (a.peer.world <= 1) { st->W = carry_s; st->c_offset = 0; }
-        else {   // post this shard's integer weight to every rank (the scan's gate sums them into st->W)
+        double sq = 0.;
+#pragma unroll
+        for (int i = 0; i < kScanThreads / 32; ++i) sq += wsq[i];
+        if (a.peer.world <= 1) {
+            st->W = carry_s; st->c_offset = 0;
+            st->sumexp2 = sq;
+            st->ess = sq > 0. ? ((double)carry_s * (double)carry_s) / sq : 0.;   // 1 / sum(w~^2), particle_filter.rs:98-100
+        } else {   // post this shard's integer weight (and sum of squares) to every rank; the scan's gate adds them up
             const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-            for (int h = 0; h < a.peer.world; ++h) ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], carry_s, (unsigned int)epoch);
+            for (int h = 0; h < a.peer.world; ++h) {
+                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], carry_s, (unsigned int)epoch);
+                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank] + 2, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
+            }
         }
     }
 }
@@ -769,7 +798,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
     const unsigned int tile = blockIdx.x;
     gate_weights(a.peer, st, a.epoch < 0 ? st->t : a.epoch);
     const unsigned long long W = st->W;
-    const float mx = (float)st->max;
+    const float mx = fixed_max<Real>(a);
     if (tid == 0) {   // exact slot base of this tile from its exclusive prefix (reduce pass) and the shard's offset
         if (W != 0ull) {
             const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
@@ -797,14 +826,20 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<R
         st->ess_stale = st->ess;
         if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
         st->resampled = 1;
+        st->degenerate = 0;
     }
     if (total == 0u) return;
-    if (total > kHeavyCap) {
-        if (tid == 0) {
-            unsigned int slot = atomicAdd(&st->overflow_count, 1u);
-            a.overflow[slot] = OverflowEntry{base.rem, base.n_start, tile, total};
+    if (total > kHeavyCap) {   // a few particles own a large share of the offspring
+        if (tid == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
+        if (a.overflow_follows) {   // queue the tile for the whole-grid pass
+            if (tid == 0) {
+                unsigned int slot = atomicAdd(&st->overflow_count, 1u);
+                a.overflow[slot] = OverflowEntry{base.rem, base.n_start, tile, total};
+            }
+            return;
         }
-        return;
+        // no overflow pass was launched for this step (none had been needed so far): this block does it alone, and the
+        // raised host word makes every later step launch the pass
     }
     for (unsigned int chunk_base = 0; chunk_base < total; chunk_base += kScanTile)
         expand_chunk<Real>(a, sh, tile, base.n_start, chunk_base, total, chunk_base == 0);
@@ -820,7 +855,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_overflow_kernel(FixedArgs<
     if (count == 0u && a.peer.world <= 1) return;
     if (count != 0u) {
         const unsigned long long W = st->W;
-        const float mx = (float)st->max;
+        const float mx = fixed_max<Real>(a);
         const double inv_w = 1. / (double)W;
         for (unsigned int k = 0; k < count; ++k) {
             const OverflowEntry e = a.overflow[k];
@@ -937,7 +972,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_cumsum_kernel(FixedArgs<Re
     __shared__ ScanShared sh;
     const int tid = threadIdx.x;
     const unsigned int tile = blockIdx.x;
-    const float mx = (float)a.stats->max;
+    const float mx = fixed_max<Real>(a);
     unsigned long long q[kScanRounds][4], excl[kScanRounds];
     tile_local_scan<Real>(a, sh, tile, mx, q, excl);
     const unsigned long long tile_excl = a.desc[tile];
