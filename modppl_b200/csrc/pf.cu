@@ -243,12 +243,12 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
     if (scheme == MPL_RESAMPLE_SYSTEMATIC_FIXED) {
         {
             ScopedLaunch sl(ps, "fixed_scan");
-            fixed_scan_kernel<Real><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
+            fixed_scan2_kernel<Real><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
         }
         MPL_CUDA_OK(cudaGetLastError());
         if (a.overflow_follows) {
             ScopedLaunch sl(ps, "fixed_overflow");
-            fixed_overflow_kernel<Real><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a);
+            fixed_overflow2_kernel<Real><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow);
         }
         MPL_CUDA_OK(cudaGetLastError());
     } else {
@@ -350,12 +350,12 @@ int ps_phase_scan(mpl_ps* ps) {
     const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
     if (ps->dtype == MPL_F32) {
         auto a = fixed_args<float>(ps, false, false);
-        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan_kernel<float><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
-        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow_kernel<float><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a); }
+        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan2_kernel<float><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow); }
+        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow2_kernel<float><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow); }
     } else {
         auto a = fixed_args<double>(ps, false, false);
-        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan_kernel<double><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
-        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow_kernel<double><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a); }
+        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan2_kernel<double><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow); }
+        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow2_kernel<double><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow); }
     }
     MPL_CUDA_OK(cudaGetLastError());
     ps->pending_gather = true; ps->stats_valid = false; ps->max_valid = false;
@@ -438,7 +438,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->probs = nullptr; ps->cums = nullptr; ps->icum = nullptr; ps->obs_dev = nullptr; ps->obs_steps = 0; ps->staging = nullptr;
     const size_t es = elem_size(ps);
     const size_t num_tiles = ps->ld / kScanTile;
-    ps->overflow_cap = ps->n_global / kHeavyCap + 4;
+    ps->overflow_cap = (ps->n_global / kWarpHeavyCap + 8) * 2;   // entries (OverflowEntry2 is the larger record)
     const int V = ps->dtype == MPL_F32 ? 4 : 2;
     ps->grid_extend = grid_for(ps->n, kExtendThreads * V, kNumSMs * 8);
     ps->grid_reduce = grid_for(ps->n, 256 * 4, kNumSMs * 8);
@@ -449,7 +449,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ok = ok && cudaMalloc(&ps->anc, ps->ld * sizeof(int32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->desc, num_tiles * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(ps->desc, 0, num_tiles * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMalloc(&ps->overflow, ps->overflow_cap * sizeof(OverflowEntry)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ps->overflow, ps->overflow_cap * sizeof(OverflowEntry2)) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->stats, sizeof(DeviceStats)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ps->stats_host, sizeof(DeviceStats)) == cudaSuccess;
     ok = ok && cudaMalloc(&ps->partials, kNumSMs * 8 * sizeof(Lse3<double>)) == cudaSuccess;

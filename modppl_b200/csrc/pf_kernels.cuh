@@ -1037,3 +1037,5 @@ static __global__ void __launch_bounds__(256) i32_to_i64_kernel(const int32_t* _
 }
 
 }  // namespace mpl
+
+#include "scan2.cuh"
