@@ -204,7 +204,7 @@ static int materialise(mpl_ps* ps) {
 template <typename Real>
 static FixedArgs<Real> fixed_args(mpl_ps* ps, bool dynamic, bool dev_t) {
     FixedArgs<Real> a;
-    a.lw = (const Real*)ps->lw;
+    a.lw = (Real*)ps->lw;
     a.n = ps->n;
     a.kbits = fixed_kbits(ps->n_global);
     a.n_out = ps->n_global;

@@ -355,7 +355,9 @@ __global__ void __launch_bounds__(256) weight_reduce_kernel(const Real* __restri
 
 template <typename Real>
 struct FixedArgs {
-    const Real* lw;
+    Real* lw;                 // in: log-weights.  The reduce pass overwrites them IN PLACE with the integer weights (exactly
+                              // representable in Real): after a resample the log-weights are zero by definition
+                              // (particle_filter.rs:114), and the scan then reads 4 bytes per particle without re-evaluating exp
     size_t n;                 // local particles
     int kbits;
     unsigned long long n_out; // global number of offspring (N_global)
@@ -452,9 +454,40 @@ __device__ __forceinline__ unsigned long long resample_rand_word(uint64_t seed, 
     return ((unsigned long long)x.x << 32) | x.y;
 }
 
-// 4 consecutive log-weights -> 4 integer weights; out-of-range lanes give 0 (FULL: the whole tile is in range)
+// 4 consecutive log-weights -> 4 integer weights; out-of-range lanes give 0 (FULL: the whole tile is in range).
+// WRITEBACK: store the integer weights over the log-weights (as Real; every q is an integer below 2^41 with at most 24
+// significant bits, hence exact in fp32).
+template <typename Real, bool FULL, bool WRITEBACK = false>
+__device__ __forceinline__ void load_q4(Real* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4], float* sq = nullptr) {
+    float w[4];
+    if constexpr (sizeof(Real) == 4) {
+        float4 v = *reinterpret_cast<const float4*>(lw + idx);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+        double2 a = *reinterpret_cast<const double2*>(lw + idx), b = *reinterpret_cast<const double2*>(lw + idx + 2);
+        w[0] = (float)a.x; w[1] = (float)a.y; w[2] = (float)b.x; w[3] = (float)b.y;
+    }
+    float qr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float qf;
+        unsigned long long v = fixed_weight(__fsub_rn(w[j], mx), kbits, &qf);
+        const bool in = FULL || idx + j < n;
+        q[j] = in ? v : 0ull;
+        qr[j] = in ? rintf(qf) : 0.f;
+        if (sq && in) *sq = fmaf(qf, qf, *sq);
+    }
+    if constexpr (WRITEBACK) {
+        if constexpr (sizeof(Real) == 4) *reinterpret_cast<float4*>(lw + idx) = make_float4(qr[0], qr[1], qr[2], qr[3]);
+        else {
+            *reinterpret_cast<double2*>(lw + idx) = make_double2((double)qr[0], (double)qr[1]);
+            *reinterpret_cast<double2*>(lw + idx + 2) = make_double2((double)qr[2], (double)qr[3]);
+        }
+    }
+}
+// 4 consecutive STORED integer weights (left by the reduce pass)
 template <typename Real, bool FULL>
-__device__ __forceinline__ void load_q4(const Real* lw, size_t idx, size_t n, float mx, int kbits, unsigned long long (&q)[4], float* sq = nullptr) {
+__device__ __forceinline__ void load_stored_q4(const Real* lw, size_t idx, size_t n, unsigned long long (&q)[4]) {
     float w[4];
     if constexpr (sizeof(Real) == 4) {
         float4 v = *reinterpret_cast<const float4*>(lw + idx);
@@ -464,13 +497,7 @@ __device__ __forceinline__ void load_q4(const Real* lw, size_t idx, size_t n, fl
         w[0] = (float)a.x; w[1] = (float)a.y; w[2] = (float)b.x; w[3] = (float)b.y;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float qf;
-        unsigned long long v = fixed_weight(__fsub_rn(w[j], mx), kbits, &qf);
-        const bool in = FULL || idx + j < n;
-        q[j] = in ? v : 0ull;
-        if (sq && in) *sq = fmaf(qf, qf, *sq);
-    }
+    for (int j = 0; j < 4; ++j) q[j] = (FULL || idx + j < n) ? __float2ull_rn(w[j]) : 0ull;
 }
 
 // R1: per-tile integer weight sums; the last block to finish turns them into exclusive tile prefixes (in place, in
@@ -502,7 +529,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
 #pragma unroll
             for (int r = 0; r < kScanRounds; ++r) {
                 unsigned long long q[4];
-                load_q4<Real, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q, &sqf);
+                load_q4<Real, true, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q, &sqf);
                 sum += q[0] + q[1] + q[2] + q[3];
             }
         } else {
@@ -511,7 +538,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
                 size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
                 if (idx < a.n) {
                     unsigned long long q[4];
-                    load_q4<Real, false>(a.lw, idx, a.n, mx, a.kbits, q, &sqf);
+                    load_q4<Real, false, true>(a.lw, idx, a.n, mx, a.kbits, q, &sqf);
                     sum += q[0] + q[1] + q[2] + q[3];
                 }
             }
@@ -646,14 +673,14 @@ __device__ __forceinline__ unsigned long long tile_local_scan(const FixedArgs<Re
     if (tile_base + kScanTile <= a.n) {
 #pragma unroll
         for (int r = 0; r < kScanRounds; ++r) {
-            load_q4<Real, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q[r]);
+            load_stored_q4<Real, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, q[r]);
             incl[r] = q[r][0] + q[r][1] + q[r][2] + q[r][3];
         }
     } else {
 #pragma unroll
         for (int r = 0; r < kScanRounds; ++r) {
             size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
-            if (idx < a.n) load_q4<Real, false>(a.lw, idx, a.n, mx, a.kbits, q[r]);
+            if (idx < a.n) load_stored_q4<Real, false>(a.lw, idx, a.n, q[r]);
             else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0ull; }
             incl[r] = q[r][0] + q[r][1] + q[r][2] + q[r][3];
         }

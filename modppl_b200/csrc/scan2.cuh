@@ -23,7 +23,7 @@ struct Scan2Shared {
     __align__(16) unsigned short head[kScanThreads / 32][kWarpChunk];
 };
 
-// Loads and quantises the lane's 16 particles of a warp tile; returns per-round lane sums' inclusive scan over lanes
+// Loads the lane's 16 stored integer weights (left in place of the log-weights by the reduce pass) of a warp tile; returns per-round lane sums' inclusive scan over lanes
 // (incl[r]), the lane's own round sums (own[r]) and the warp-wide round totals (tot[r]).
 template <typename Real>
 __device__ __forceinline__ void warp_tile_load_scan(const FixedArgs<Real>& a, size_t wt_base, float mx, unsigned long long (&q)[4][4],
@@ -31,12 +31,12 @@ __device__ __forceinline__ void warp_tile_load_scan(const FixedArgs<Real>& a, si
     const int lane = threadIdx.x & 31;
     if (wt_base + kWarpTile <= a.n) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) load_q4<Real, true>(a.lw, wt_base + (size_t)r * 128 + (size_t)lane * 4, a.n, mx, a.kbits, q[r]);
+        for (int r = 0; r < 4; ++r) load_stored_q4<Real, true>(a.lw, wt_base + (size_t)r * 128 + (size_t)lane * 4, a.n, q[r]);
     } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             size_t idx = wt_base + (size_t)r * 128 + (size_t)lane * 4;
-            if (idx < a.n) load_q4<Real, false>(a.lw, idx, a.n, mx, a.kbits, q[r]);
+            if (idx < a.n) load_stored_q4<Real, false>(a.lw, idx, a.n, q[r]);
             else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0ull; }
         }
     }
