@@ -4,6 +4,7 @@
 #include <cstring>
 #include <mutex>
 #include "engine.h"
+#include "cumsum_exact.cuh"
 
 namespace mpl {
 
@@ -282,7 +283,11 @@ static int resample_exact(mpl_ps* ps, int scheme) {
         else normalize_kernel<double><<<grid, 256, 0, ps->stream>>>((const double*)ps->lw, ps->n, ps->probs, ps->stats, std::log((double)ps->n_global), 1);
     }
     MPL_CUDA_OK(cudaGetLastError());
-    int rc = launch_cumsum_exact(ps, ps->probs, ps->n, ps->cums, ps->stream);
+    int rc;
+    {
+        ScopedLaunch sl(ps, "cumsum_exact");
+        rc = launch_cumsum_exact(ps, ps->probs, ps->n, ps->cums, ps->stream);
+    }
     if (rc) return rc;
     {
         ScopedLaunch sl(ps, "search");
@@ -294,9 +299,28 @@ static int resample_exact(mpl_ps* ps, int scheme) {
 }
 
 static int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream) {
-    if (ps) ps->launch_count++;
-    cumsum_seq_kernel<<<1, 256, 0, stream>>>(probs, n, out);
+    // categorical.rs:25-30: S_k = fl(S_{k-1} + p_k) in index order.  Short inputs: one thread adds in order.  Long inputs:
+    // the parallel exact emulation of cumsum_exact.cuh (same bits).
+    if (n < (size_t)4 * kCxTile) {
+        if (ps) ps->launch_count++;
+        cumsum_seq_kernel<<<1, 256, 0, stream>>>(probs, n, out);
+        MPL_CUDA_OK(cudaGetLastError());
+        return MPL_OK;
+    }
+    const unsigned int num_tiles = (unsigned int)((n + kCxTile - 1) / kCxTile);
+    CxTile* tiles = nullptr;
+    int* bad = nullptr;
+    MPL_CUDA_OK(cudaMallocAsync(&tiles, (size_t)num_tiles * sizeof(CxTile) + 64, stream));
+    bad = reinterpret_cast<int*>(reinterpret_cast<char*>(tiles) + (size_t)num_tiles * sizeof(CxTile));
+    MPL_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), stream));
+    cx_tilesum_kernel<<<num_tiles, kCxThreads, 0, stream>>>(probs, n, tiles, bad);
+    cx_classify_kernel<<<1, 1024, 0, stream>>>(tiles, num_tiles, bad);
+    cx_pairs_kernel<<<num_tiles, kCxThreads, 0, stream>>>(probs, n, tiles);
+    cx_walk_kernel<<<1, kCxThreads, 0, stream>>>(probs, n, tiles, num_tiles, out);
+    cx_fill_kernel<<<num_tiles, kCxThreads, 0, stream>>>(probs, n, tiles, out);
+    if (ps) ps->launch_count += 5;
     MPL_CUDA_OK(cudaGetLastError());
+    MPL_CUDA_OK(cudaFreeAsync(tiles, stream));
     return MPL_OK;
 }
 

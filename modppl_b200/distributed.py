@@ -118,6 +118,7 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
     ps.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
+    lml = ps.log_marginal_likelihood_estimate()     # same point of the run as the single-GPU arm: identical by construction
     # per-kernel CUDA-event times (includes time spent waiting for peers inside the kernels)
     ps.profile_enable(True)
     t_prof = t_first + K
@@ -127,7 +128,6 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
     ps.profile_enable(False)
     kernel_ms = {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}
     err = ps.peer_error()
-    lml = ps.log_marginal_likelihood_estimate()
     dist.barrier()
     if rank == 0:
         value = n_global * K / (ms * 1e-3)

@@ -355,3 +355,44 @@ def test_virtual_shards_degenerate_weights_cross_shards():
         if t + 1 < T:
             one.resample(m.SYSTEMATIC_FIXED)
     assert np.array_equal(st, one.traces) and np.array_equal(lw, one.log_weights)
+
+
+# ------------------------------------------------------------------------------------------------- exact PARALLEL running sum
+def cumsum_cases(n, rng):
+    yield "lognormal", np.exp(rng.normal(size=n) * 3)
+    yield "uniform", rng.random(n)
+    # exact ties: every element is an odd multiple of half the grid spacing the running sum will have => round-half-even
+    yield "forced_ties", rng.integers(1, 1 << 30, size=n).astype(np.float64) * 2.0**-54
+    w = rng.random(n) * 1e-12
+    w[n // 3] = 1.0
+    yield "one_dominant", w
+    w = rng.random(n)
+    w[: n // 2] = 0.0
+    yield "leading_zeros", w
+    yield "tiny_then_big", np.concatenate([np.full(n // 2, 1e-300), rng.random(n - n // 2)])
+    yield "subnormals", np.concatenate([np.full(n // 2, 5e-324), rng.random(n - n // 2) * 1e-310])
+    yield "powers_of_two", 2.0 ** rng.integers(-60, -10, size=n).astype(np.float64)
+
+
+@pytest.mark.parametrize("n", [8192, 8192 + 3, 100000, (1 << 22) + 17])
+def test_parallel_cumsum_equals_sequential_bit_for_bit(n):
+    # n >= 4 tiles takes the parallel emulation of sequential rounding (csrc/cumsum_exact.cuh); numpy's 1-D float64
+    # cumsum is the sequential loop of categorical.rs:25-30
+    rng = np.random.default_rng(n)
+    for name, w in cumsum_cases(n, rng):
+        for normalise in (True, False):
+            p = w / w.sum() if normalise and w.sum() > 0 else w
+            got = m.parity.cumsum_sequential(p)
+            ref = np.cumsum(p)
+            bad = np.nonzero(got != ref)[0]
+            assert bad.size == 0, (name, normalise, bad[:5], got[bad[:3]], ref[bad[:3]])
+
+
+def test_parallel_cumsum_bad_inputs_fall_back_to_sequential_semantics():
+    rng = np.random.default_rng(3)
+    p = rng.random(20000)
+    p[1234] = -0.5                      # not a probability vector: still the same sequential sum
+    assert np.array_equal(m.parity.cumsum_sequential(p), np.cumsum(p))
+    p[5000] = np.nan
+    got, ref = m.parity.cumsum_sequential(p), np.cumsum(p)
+    assert np.array_equal(got[:5000], ref[:5000]) and np.all(np.isnan(got[5000:]))
