@@ -99,6 +99,7 @@ int mpl_ps_sync(mpl_ps*);
  * the loop on the handle's stream. */
 int mpl_ps_upload_observations(mpl_ps*, const double* obs, size_t n_steps, size_t n_obs);
 int mpl_ps_run(mpl_ps*, size_t first_step, size_t n_steps, int scheme, double ess_threshold, float* elapsed_ms);
+int mpl_ps_num_resamples(mpl_ps*, uint64_t* out);   /* resamples performed so far (integer schemes) */
 
 /* per-kernel CUDA-event timing (bench.py's roofline leg).  names: "extend", "fixed_reduce", "fixed_scan", ... */
 int mpl_ps_profile_enable(mpl_ps*, int on);

@@ -64,6 +64,7 @@ SYMBOLS = {
     "mpl_ps_sync": (C.c_int, C.c_void_p),
     "mpl_ps_upload_observations": (C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_size_t),
     "mpl_ps_run": (C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_double, c_float_p),
+    "mpl_ps_num_resamples": (C.c_int, C.c_void_p, c_u64_p),
     "mpl_ps_profile_enable": (C.c_int, C.c_void_p, C.c_int),
     "mpl_ps_profile_get": (C.c_int, C.c_void_p, C.c_char_p, c_double_p, c_u64_p),
     "mpl_ps_launch_count": (C.c_int, C.c_void_p, c_u64_p),

@@ -42,7 +42,7 @@ struct mpl_ps {
     double* cums;     // ld
     unsigned long long* icum;   // ld (integer multinomial)
     unsigned long long* desc;   // scan tile descriptors
-    mpl::OverflowEntry* overflow;
+    void* overflow;   // OverflowEntry2 records (scan2.cuh)
     size_t overflow_cap;
     mpl::DeviceStats* stats;    // device
     mpl::DeviceStats* stats_host;   // pinned
@@ -59,6 +59,8 @@ struct mpl_ps {
     double* sq_partials;   // per-tile sums of squared weights (ESS in the integer resampler)
     int* host_flags;       // pinned + mapped: [0] = a heavy tile was seen (launch the overflow pass from now on)
     int* host_flags_dev;
+    double ess_threshold_abs;   // ESS-triggered device loop: threshold in particles
+    bool dynamic_state_known;
     bool profile;
     std::map<std::string, mpl::KernelTimer> timers;
     uint64_t launch_count;

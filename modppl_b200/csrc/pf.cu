@@ -132,7 +132,10 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
                 if (ps->world > 1) pf_extend_kernel<Model, Real, EXT_GATHER, true><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
                 else pf_extend_kernel<Model, Real, EXT_GATHER><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
                 break;
-            default: pf_extend_kernel<Model, Real, EXT_DYNAMIC><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
+            default:
+                if (ps->world > 1) pf_extend_kernel<Model, Real, EXT_DYNAMIC, true><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
+                else pf_extend_kernel<Model, Real, EXT_DYNAMIC><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
+                break;
         }
     }
     MPL_CUDA_OK(cudaGetLastError());
@@ -221,8 +224,9 @@ static FixedArgs<Real> fixed_args(mpl_ps* ps, bool dynamic, bool dev_t) {
     a.overflow_follows = (ps->world > 1 || ps->host_flags[0] != 0) ? 1 : 0;
     a.overflow_seen_host = ps->host_flags_dev;
     a.sq_partials = ps->sq_partials;
+    a.ess_threshold = ps->ess_threshold_abs;
     a.desc = ps->desc;
-    a.overflow = ps->overflow;
+    a.overflow_unused = nullptr;
     a.stats = ps->stats;
     a.partials = ps->ipartials;
     a.seed = ps->seed;
@@ -238,18 +242,21 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
     const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
     {
         ScopedLaunch sl(ps, "fixed_reduce");
-        fixed_reduce_kernel<Real><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
+        if (dynamic) fixed_reduce_kernel<Real, false><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
+        else fixed_reduce_kernel<Real, true><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (scheme == MPL_RESAMPLE_SYSTEMATIC_FIXED) {
         {
             ScopedLaunch sl(ps, "fixed_scan");
-            fixed_scan2_kernel<Real><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
+            if (dynamic) fixed_scan2_kernel<Real, false><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
+            else fixed_scan2_kernel<Real, true><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
         }
         MPL_CUDA_OK(cudaGetLastError());
         if (a.overflow_follows) {
             ScopedLaunch sl(ps, "fixed_overflow");
-            fixed_overflow2_kernel<Real><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow);
+            if (dynamic) fixed_overflow2_kernel<Real, false><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow);
+            else fixed_overflow2_kernel<Real, true><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow);
         }
         MPL_CUDA_OK(cudaGetLastError());
     } else {
@@ -365,8 +372,8 @@ int ps_phase_extend(mpl_ps* ps, bool init) {
 int ps_phase_reduce(mpl_ps* ps) {
     const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
     ScopedLaunch sl(ps, "fixed_reduce");
-    if (ps->dtype == MPL_F32) { auto a = fixed_args<float>(ps, false, false); fixed_reduce_kernel<float><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
-    else { auto a = fixed_args<double>(ps, false, false); fixed_reduce_kernel<double><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
+    if (ps->dtype == MPL_F32) { auto a = fixed_args<float>(ps, false, false); fixed_reduce_kernel<float, true><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
+    else { auto a = fixed_args<double>(ps, false, false); fixed_reduce_kernel<double, true><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles); }
     MPL_CUDA_OK(cudaGetLastError());
     return MPL_OK;
 }
@@ -374,12 +381,12 @@ int ps_phase_scan(mpl_ps* ps) {
     const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
     if (ps->dtype == MPL_F32) {
         auto a = fixed_args<float>(ps, false, false);
-        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan2_kernel<float><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow); }
-        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow2_kernel<float><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow); }
+        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan2_kernel<float, true><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow); }
+        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow2_kernel<float, true><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow); }
     } else {
         auto a = fixed_args<double>(ps, false, false);
-        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan2_kernel<double><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow); }
-        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow2_kernel<double><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow); }
+        { ScopedLaunch sl(ps, "fixed_scan"); fixed_scan2_kernel<double, true><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow); }
+        if (a.overflow_follows) { ScopedLaunch sl(ps, "fixed_overflow"); fixed_overflow2_kernel<double, true><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow); }
     }
     MPL_CUDA_OK(cudaGetLastError());
     ps->pending_gather = true; ps->stats_valid = false; ps->max_valid = false;
@@ -456,7 +463,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->seed = c.seed; ps->gid_offset = c.gid_offset; ps->n_global = c.n_global ? c.n_global : num_particles;
     ps->D = model->state_dim;
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
-    ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr;
+    ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
     ps->probs = nullptr; ps->cums = nullptr; ps->icum = nullptr; ps->obs_dev = nullptr; ps->obs_steps = 0; ps->staging = nullptr;
@@ -691,8 +698,11 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
     if (!ps->obs_dev) return fail(MPL_ERR_INVALID, "mpl_ps_upload_observations first");
     if (first_step + n_steps > ps->obs_steps) return fail(MPL_ERR_INVALID, "run exceeds the uploaded observations");
     if (first_step > 0 && (long long)first_step != ps->t) return fail(MPL_ERR_INVALID, "first_step must equal the filter's current time index");
-    if (ess_threshold > 0.) return fail(MPL_ERR_UNSUPPORTED, "ESS-triggered device loop: not in this build");
+    const bool dynamic = ess_threshold > 0.;
+    if (dynamic && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED) return fail(MPL_ERR_UNSUPPORTED, "ESS-triggered device loop: MPL_RESAMPLE_SYSTEMATIC_FIXED only");
+    if (dynamic && first_step > 0 && !ps->dynamic_state_known) return fail(MPL_ERR_INVALID, "ESS-triggered run must start at step 0 or continue a previous ESS-triggered run");
     MPL_CUDA_OK(cudaSetDevice(ps->device));
+    ps->ess_threshold_abs = dynamic ? ess_threshold * (double)ps->n_global : 0.;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (elapsed_ms) { MPL_CUDA_OK(cudaEventCreate(&e0)); MPL_CUDA_OK(cudaEventCreate(&e1)); MPL_CUDA_OK(cudaEventRecord(e0, ps->stream)); }
     Obs dummy; std::memset(&dummy, 0, sizeof dummy);
@@ -703,11 +713,18 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
             ps->t = 0; ps->pending_gather = false;
             rc = launch_extend(ps, EXT_INIT, dummy, true, false);
             ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
+        } else if (dynamic) {
+            // whether the previous step resampled is only known on the device: the extend reads stats->resampled_flag[t & 1]
+            rc = launch_extend(ps, EXT_DYNAMIC, dummy, true, false);
+            ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
         } else {
             rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false);
             ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
         }
-        if (rc == MPL_OK) rc = do_resample(ps, scheme);
+        if (rc != MPL_OK) break;
+        if (dynamic) {
+            rc = ps->dtype == MPL_F32 ? resample_fixed_t<float>(ps, scheme, true, false) : resample_fixed_t<double>(ps, scheme, true, false);
+        } else rc = do_resample(ps, scheme);
     }
     if (elapsed_ms) {
         cudaEventRecord(e1, ps->stream);
@@ -716,7 +733,21 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         if (e != cudaSuccess) return fail(MPL_ERR_CUDA, std::string("run: ") + cudaGetErrorString(e));
     }
+    if (rc == MPL_OK && dynamic) {   // learn from the device whether the last step resampled
+        if ((rc = fetch_stats(ps))) return rc;
+        ps->pending_gather = ps->stats_host->resampled_flag[ps->t & 1] != 0;
+        ps->stats_valid = false; ps->max_valid = !ps->pending_gather;
+        ps->dynamic_state_known = true;
+    }
     return rc;
+}
+
+extern "C" int mpl_ps_num_resamples(mpl_ps* ps, uint64_t* out) {
+    if (!ps || !out) return fail(MPL_ERR_INVALID, "null argument");
+    int rc = fetch_stats(ps);
+    if (rc) return rc;
+    *out = ps->stats_host->n_resamples;
+    return MPL_OK;
 }
 
 extern "C" int mpl_ps_profile_enable(mpl_ps* ps, int on) {

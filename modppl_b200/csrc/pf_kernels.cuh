@@ -42,15 +42,10 @@ struct DeviceStats {
     // sharded runs: block 0 of a kernel waits for the peers (system scope), publishes the global values into this
     // struct and then raises the matching ready word; the kernel's other blocks only watch that local word
     unsigned long long c_offset;   // integer weight of all lower-ranked shards
+    int resampled_flag[2];         // [t & 1]: the extend of step t must gather through the ancestors (set by the scan of step t-1)
+    unsigned long long n_resamples;   // resamples performed so far
     unsigned long long max_bits[2];   // exact max of the log-weights written by the extend of step t, slot t & 1 (order-preserving bits)
     long long ready_stats, ready_w, ready_done;
-};
-
-struct OverflowEntry {
-    unsigned long long rem;
-    unsigned long long n_start;
-    unsigned int tile;
-    unsigned int total;
 };
 
 // ---- multi-GPU: one process per GPU, peers reached through NVLink-mapped pointers (CUDA IPC) ----------------------------
@@ -180,7 +175,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
     bool gather = (MODE == EXT_GATHER);
     bool accum = (MODE == EXT_ACCUM);
     if (MODE == EXT_DYNAMIC) {
-        gather = a.stats->resampled != 0;
+        gather = a.stats->resampled_flag[t & 1] != 0;
         accum = !gather;
     }
     constexpr bool sharded = SHARDED;
@@ -362,6 +357,8 @@ struct FixedArgs {
     int kbits;
     unsigned long long n_out; // global number of offspring (N_global)
     unsigned long long c_offset;   // integer weight of all lower-ranked shards
+    int resampled_flag[2];         // [t & 1]: the extend of step t must gather through the ancestors (set by the scan of step t-1)
+    unsigned long long n_resamples;   // resamples performed so far
     unsigned long long max_bits[2];   // exact max of the log-weights written by the extend of step t, slot t & 1 (order-preserving bits)
     unsigned long long out_base;   // global index of this shard's first output slot
     unsigned long long n_out_local;
@@ -369,13 +366,14 @@ struct FixedArgs {
     int32_t* anc;             // local output slots [out_base, out_base + n_out_local)
     int32_t src_base;         // value written for local particle 0 (global id of it, or 0)
     unsigned long long* desc;
-    OverflowEntry* overflow;
+    void* overflow_unused;
     DeviceStats* stats;
     unsigned long long* partials;   // gridDim.x of the reduce kernel
     uint64_t seed;
     long long rt;             // RNG tag of this resample (step whose weights are resampled); < 0: stats->t - 1
     int accumulate_lml;
-    int dynamic;              // 1: skip unless stats->do_resample (ESS-triggered, device-resident loop)
+    int dynamic;              // 1: ESS-triggered (device-resident loop): the reduce pass decides, the scan skips unless stats->do_resample
+    double ess_threshold;     // dynamic: resample when ESS < ess_threshold (absolute, in particles)
     PeerTable peer;           // world == 1: single GPU
     long long epoch;          // step number the mailbox flags must have reached; < 0: stats->t
     int max_slot;             // >= 0: the max lives in stats->max_bits[max_slot] (left by the extend); < 0: in stats->max
@@ -415,7 +413,7 @@ __device__ __forceinline__ void gate_stats(const PeerTable& p, DeviceStats* st, 
     __syncthreads();
 }
 // every shard's integer weight total has arrived: global W and this shard's prefix
-__device__ __forceinline__ void gate_weights(const PeerTable& p, DeviceStats* st, long long epoch) {
+__device__ __forceinline__ void gate_weights(const PeerTable& p, DeviceStats* st, long long epoch, int dynamic = 0, double ess_threshold = 0.) {
     if (p.world <= 1) return;
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
@@ -432,6 +430,7 @@ __device__ __forceinline__ void gate_weights(const PeerTable& p, DeviceStats* st
             st->W = W; st->c_offset = c;
             st->sumexp2 = sq;
             st->ess = sq > 0. ? ((double)W * (double)W) / sq : 0.;
+            if (dynamic) st->do_resample = (st->ess < ess_threshold) ? 1 : 0;
             local_ready_set(&st->ready_w, epoch);
         } else local_ready_wait(&st->ready_w, epoch, p);
     }
@@ -508,11 +507,11 @@ constexpr int kScanRounds = 4;
 constexpr int kScanTile = kScanThreads * 4 * kScanRounds;   // 4096 particles per tile
 constexpr unsigned int kHeavyCap = 32u * kScanTile;        // tiles with more offspring than this go to the overflow pass
 
-template <typename Real>
+template <typename Real, bool WRITEBACK>
 __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Real> a, unsigned int num_tiles) {
     // one tile per block; warps add their partial sums straight into desc[tile] (zeroed by the previous scan pass), so
-    // the only block-wide barrier is the one in front of the last-block test
-    if (a.dynamic && !a.stats->do_resample) return;
+    // the only block-wide barrier is the one in front of the last-block test.  WRITEBACK = false (ESS-triggered runs): the
+    // log-weights must survive when the decision is "do not resample".
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ unsigned long long ws[kScanThreads / 32];
     __shared__ double wsq[kScanThreads / 32];
@@ -529,7 +528,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
 #pragma unroll
             for (int r = 0; r < kScanRounds; ++r) {
                 unsigned long long q[4];
-                load_q4<Real, true, true>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q, &sqf);
+                load_q4<Real, true, WRITEBACK>(a.lw, tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4, a.n, mx, a.kbits, q, &sqf);
                 sum += q[0] + q[1] + q[2] + q[3];
             }
         } else {
@@ -538,7 +537,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
                 size_t idx = tile_base + (size_t)r * (kScanThreads * 4) + (size_t)tid * 4;
                 if (idx < a.n) {
                     unsigned long long q[4];
-                    load_q4<Real, false, true>(a.lw, idx, a.n, mx, a.kbits, q, &sqf);
+                    load_q4<Real, false, WRITEBACK>(a.lw, idx, a.n, mx, a.kbits, q, &sqf);
                     sum += q[0] + q[1] + q[2] + q[3];
                 }
             }
@@ -603,6 +602,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
             st->W = carry_s; st->c_offset = 0;
             st->sumexp2 = sq;
             st->ess = sq > 0. ? ((double)carry_s * (double)carry_s) / sq : 0.;   // 1 / sum(w~^2), particle_filter.rs:98-100
+            if (a.dynamic) st->do_resample = (st->ess < a.ess_threshold) ? 1 : 0;
         } else {   // post this shard's integer weight (and sum of squares) to every rank; the scan's gate adds them up
             const long long epoch = a.epoch < 0 ? st->t : a.epoch;
             for (int h = 0; h < a.peer.world; ++h) {
@@ -655,11 +655,6 @@ struct __align__(16) ScanShared {
     unsigned long long tile_excl;
     unsigned long long rand_word;
     TileBase base;
-    __align__(16) unsigned int nloc[kScanTile];             // inclusive offspring counts, relative to the tile's first output slot
-    __align__(16) unsigned short head[kScanTile];   // expansion buffer: (local parent + 1) at the first slot of each run
-    unsigned int warp_max[kScanThreads / 32];
-    unsigned int carry;
-    unsigned int tile;
 };
 
 // Loads a tile, quantises, and leaves in excl[r] the tile-local exclusive prefix of this thread's round-r chunk.
@@ -714,209 +709,6 @@ __device__ __forceinline__ unsigned long long tile_local_scan(const FixedArgs<Re
     }
     aggregate = carry;
     return aggregate;
-}
-
-// nloc[e] = (#offspring of all particles up to and including element e) - n_start
-template <typename Real>
-__device__ __forceinline__ void tile_fill_nloc(const FixedArgs<Real>& a, ScanShared& sh, const TileBase& base, unsigned long long W, double inv_w,
-                                               const unsigned long long (&q)[kScanRounds][4], const unsigned long long (&excl)[kScanRounds]) {
-    const int tid = threadIdx.x;
-    const double rem_d = (double)base.rem, n_out_d = (double)a.n_out;
-#pragma unroll
-    for (int r = 0; r < kScanRounds; ++r) {
-        unsigned long long c = excl[r];
-        uint4 out;
-        unsigned int* o = reinterpret_cast<unsigned int*>(&out);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            c += q[r][j];
-            o[j] = local_count(c, base.rem, rem_d, W, n_out_d, a.n_out, inv_w);
-        }
-        *reinterpret_cast<uint4*>(&sh.nloc[r * (kScanThreads * 4) + tid * 4]) = out;
-    }
-}
-
-// Expands one chunk of kScanTile consecutive output slots of a tile: slots [chunk_base, chunk_base + kScanTile) of the
-// tile-local offspring range.  Every particle with >= 1 offspring drops (its local index + 1) at the first slot of its
-// run; an inclusive max-scan propagates it along the run (local indices increase with the slot); the result is
-// written with coalesced 4-byte stores.  All threads of the block must call this.
-__device__ __forceinline__ void clear_heads(ScanShared& sh) {
-    uint4* head4 = reinterpret_cast<uint4*>(sh.head);
-    head4[threadIdx.x * 2] = make_uint4(0, 0, 0, 0);
-    head4[threadIdx.x * 2 + 1] = make_uint4(0, 0, 0, 0);
-}
-// `cleared`: the caller already zeroed sh.head and a barrier has passed since (saves one barrier for the first chunk).
-// On return every thread may still be reading sh.head: the caller must put a barrier before the next clear.
-template <typename Real>
-__device__ __forceinline__ void expand_chunk(const FixedArgs<Real>& a, ScanShared& sh, unsigned int tile, unsigned long long n_start,
-                                             unsigned int chunk_base, unsigned int total, bool cleared) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint4* head4 = reinterpret_cast<uint4*>(sh.head);
-    if (!cleared) { __syncthreads(); clear_heads(sh); __syncthreads(); }
-    if (tid == 0) {   // parent of the chunk's first slot: first element e with nloc[e] > chunk_base
-        unsigned int lo = 0, hi = kScanTile - 1;
-        while (lo < hi) { unsigned int mid = (lo + hi) >> 1; if (sh.nloc[mid] > chunk_base) hi = mid; else lo = mid + 1; }
-        sh.carry = lo + 1;
-    }
-#pragma unroll
-    for (int r = 0; r < kScanRounds; ++r) {
-        const unsigned int e0 = r * (kScanThreads * 4) + tid * 4;
-        uint4 cur = *reinterpret_cast<const uint4*>(&sh.nloc[e0]);
-        unsigned int prev = (e0 == 0) ? 0u : sh.nloc[e0 - 1];
-        const unsigned int c[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            unsigned int rel = prev - chunk_base;   // wraps when prev < chunk_base
-            if (c[j] > prev && rel < (unsigned int)kScanTile) sh.head[rel] = (unsigned short)(e0 + j + 1);
-            prev = c[j];
-        }
-    }
-    __syncthreads();
-    // blocked max-scan: thread owns slots [16*tid, 16*tid + 16)
-    uint4 h0 = head4[tid * 2], h1 = head4[tid * 2 + 1];
-    unsigned int v[16] = {h0.x & 0xffffu, h0.x >> 16, h0.y & 0xffffu, h0.y >> 16, h0.z & 0xffffu, h0.z >> 16, h0.w & 0xffffu, h0.w >> 16,
-                          h1.x & 0xffffu, h1.x >> 16, h1.y & 0xffffu, h1.y >> 16, h1.z & 0xffffu, h1.z >> 16, h1.w & 0xffffu, h1.w >> 16};
-#pragma unroll
-    for (int i = 1; i < 16; ++i) v[i] = max(v[i], v[i - 1]);
-    unsigned int incl = v[15];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = max(incl, up); }
-    if (lane == 31) sh.warp_max[warp] = incl;
-    unsigned int before = __shfl_up_sync(0xffffffffu, incl, 1);
-    if (lane == 0) before = 0;
-    __syncthreads();
-    unsigned int pre = max(before, sh.carry);
-#pragma unroll
-    for (int w = 0; w < kScanThreads / 32; ++w) if (w < warp) pre = max(pre, sh.warp_max[w]);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = max(v[i], pre);
-    head4[tid * 2] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-    head4[tid * 2 + 1] = make_uint4(v[8] | (v[9] << 16), v[10] | (v[11] << 16), v[12] | (v[13] << 16), v[14] | (v[15] << 16));
-    __syncthreads();
-    const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile) - 1;
-    const unsigned long long slot0 = n_start + chunk_base;
-    const unsigned int valid = min((unsigned int)kScanTile, total - chunk_base);
-    if (slot0 >= a.out_base && slot0 + valid <= a.out_base + a.n_out_local) {   // whole chunk lands in this shard (always, on one GPU)
-        int32_t* dst = a.anc + (slot0 - a.out_base);
-#pragma unroll
-        for (int k = 0; k < kScanTile / kScanThreads; ++k) {
-            unsigned int o = k * kScanThreads + tid;
-            if (o < valid) dst[o] = src0 + (int32_t)sh.head[o];
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanTile / kScanThreads; ++k) {   // slots of other shards: remote stores into the owner's array
-            unsigned int o = k * kScanThreads + tid;
-            if (o < valid) {
-                unsigned int slot = (unsigned int)(slot0 + o);
-                unsigned int r = peer_owner(a.peer, slot);
-                a.peer.anc[r][slot - r * a.peer.n_loc] = src0 + (int32_t)sh.head[o];
-            }
-        }
-    }
-}
-
-template <typename Real>
-__global__ void __launch_bounds__(kScanThreads, 4) fixed_scan_kernel(FixedArgs<Real> a, unsigned int num_tiles) {
-    __shared__ ScanShared sh;
-    const int tid = threadIdx.x;
-    if (a.dynamic && !a.stats->do_resample) return;
-    DeviceStats* st = a.stats;
-    const unsigned int tile = blockIdx.x;
-    gate_weights(a.peer, st, a.epoch < 0 ? st->t : a.epoch);
-    const unsigned long long W = st->W;
-    const float mx = fixed_max<Real>(a);
-    if (tid == 0) {   // exact slot base of this tile from its exclusive prefix (reduce pass) and the shard's offset
-        if (W != 0ull) {
-            const unsigned long long U = __umul64hi(resample_rand_word(a.seed, a.rt, st), W);
-            sh.base = tile_base_exact(st->c_offset + a.desc[tile], W, U, a.n_out, 1. / (double)W);
-        }
-        a.desc[tile] = 0ull;   // ready for the next reduce pass
-    }
-    clear_heads(sh);
-    if (W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors, flagged
-        for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
-        if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; }
-        return;
-    }
-    const double inv_w = 1. / (double)W;
-    unsigned long long q[kScanRounds][4], excl[kScanRounds];
-    tile_local_scan<Real>(a, sh, tile, mx, q, excl);   // (contains the barrier that publishes sh.base and the cleared heads)
-    const TileBase base = sh.base;
-    tile_fill_nloc<Real>(a, sh, base, W, inv_w, q, excl);
-    __syncthreads();
-    const unsigned int total = sh.nloc[kScanTile - 1];
-
-    if (tile == 0 && tid == 0) {   // scalar bookkeeping of resample(): particle_filter.rs:104-105,114
-        double lse = (double)mx + log((double)W) - (double)a.kbits * 0.6931471805599453;
-        st->lse = lse;
-        st->ess_stale = st->ess;
-        if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
-        st->resampled = 1;
-        st->degenerate = 0;
-    }
-    if (total == 0u) return;
-    if (total > kHeavyCap) {   // a few particles own a large share of the offspring
-        if (tid == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
-        if (a.overflow_follows) {   // queue the tile for the whole-grid pass
-            if (tid == 0) {
-                unsigned int slot = atomicAdd(&st->overflow_count, 1u);
-                a.overflow[slot] = OverflowEntry{base.rem, base.n_start, tile, total};
-            }
-            return;
-        }
-        // no overflow pass was launched for this step (none had been needed so far): this block does it alone, and the
-        // raised host word makes every later step launch the pass
-    }
-    for (unsigned int chunk_base = 0; chunk_base < total; chunk_base += kScanTile)
-        expand_chunk<Real>(a, sh, tile, base.n_start, chunk_base, total, chunk_base == 0);
-}
-
-// heavy tiles (a few particles own a large share of the offspring): the whole grid expands each of them
-template <typename Real>
-__global__ void __launch_bounds__(kScanThreads) fixed_overflow_kernel(FixedArgs<Real> a) {
-    __shared__ ScanShared sh;
-    DeviceStats* st = a.stats;
-    if (a.dynamic && !st->do_resample) return;
-    const unsigned int count = st->overflow_count;
-    if (count == 0u && a.peer.world <= 1) return;
-    if (count != 0u) {
-        const unsigned long long W = st->W;
-        const float mx = fixed_max<Real>(a);
-        const double inv_w = 1. / (double)W;
-        for (unsigned int k = 0; k < count; ++k) {
-            const OverflowEntry e = a.overflow[k];
-            unsigned long long q[kScanRounds][4], excl[kScanRounds];
-            __syncthreads();
-            tile_local_scan<Real>(a, sh, e.tile, mx, q, excl);
-            tile_fill_nloc<Real>(a, sh, TileBase{e.n_start, e.rem}, W, inv_w, q, excl);
-            __syncthreads();
-            for (unsigned long long chunk_base = (unsigned long long)blockIdx.x * kScanTile; chunk_base < e.total; chunk_base += (unsigned long long)gridDim.x * kScanTile)
-                expand_chunk<Real>(a, sh, e.tile, e.n_start, (unsigned int)chunk_base, e.total, false);
-        }
-    }
-    if (a.peer.world > 1) {   // every ancestor this shard owes anybody is written -> tell every rank
-        // no heavy tiles: the scan kernel (complete at this kernel's start) wrote everything, one thread signals.
-        // heavy tiles: blocks fence their own remote stores, the last one to finish signals.
-        bool signal = false;
-        if (count == 0u) signal = (blockIdx.x == 0 && threadIdx.x == 0);
-        else {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence_system();
-                if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) { st->ticket = 0; signal = true; }
-            }
-        }
-        if (signal) {
-            // count == 0: the remote stores all belong to the scan kernel, which completed (and was flushed) before this
-            // kernel started, so a plain store is ordered behind them; otherwise release after the blocks' own fences
-            const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-            for (int h = 0; h < a.peer.world; ++h) {
-                if (count == 0u) *(volatile long long*)&a.peer.mail[h]->flag_done[a.peer.rank] = epoch;
-                else st_release_sys(&a.peer.mail[h]->flag_done[a.peer.rank], epoch);
-            }
-        }
-    }
 }
 
 // ================================================================================================

@@ -23,20 +23,24 @@ struct Scan2Shared {
     __align__(16) unsigned short head[kScanThreads / 32][kWarpChunk];
 };
 
-// Loads the lane's 16 stored integer weights (left in place of the log-weights by the reduce pass) of a warp tile; returns per-round lane sums' inclusive scan over lanes
+// Loads the lane's 16 integer weights of a warp tile (STORED: left in place of the log-weights by the reduce pass; else
+// re-quantised from the log-weights, for ESS-triggered runs where the log-weights must survive a skipped resample); returns per-round lane sums' inclusive scan over lanes
 // (incl[r]), the lane's own round sums (own[r]) and the warp-wide round totals (tot[r]).
-template <typename Real>
+template <typename Real, bool STORED>
 __device__ __forceinline__ void warp_tile_load_scan(const FixedArgs<Real>& a, size_t wt_base, float mx, unsigned long long (&q)[4][4],
                                                     unsigned long long (&incl)[4], unsigned long long (&own)[4], unsigned long long (&tot)[4]) {
     const int lane = threadIdx.x & 31;
     if (wt_base + kWarpTile <= a.n) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) load_stored_q4<Real, true>(a.lw, wt_base + (size_t)r * 128 + (size_t)lane * 4, a.n, q[r]);
+        for (int r = 0; r < 4; ++r) {
+            if constexpr (STORED) load_stored_q4<Real, true>(a.lw, wt_base + (size_t)r * 128 + (size_t)lane * 4, a.n, q[r]);
+            else load_q4<Real, true>(a.lw, wt_base + (size_t)r * 128 + (size_t)lane * 4, a.n, mx, a.kbits, q[r]);
+        }
     } else {
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             size_t idx = wt_base + (size_t)r * 128 + (size_t)lane * 4;
-            if (idx < a.n) load_stored_q4<Real, false>(a.lw, idx, a.n, q[r]);
+            if (idx < a.n) { if constexpr (STORED) load_stored_q4<Real, false>(a.lw, idx, a.n, q[r]); else load_q4<Real, false>(a.lw, idx, a.n, mx, a.kbits, q[r]); }
             else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0ull; }
         }
     }
@@ -136,19 +140,24 @@ __device__ __forceinline__ void warp_expand_chunk(const FixedArgs<Real>& a, unsi
     __syncwarp();
 }
 
-template <typename Real>
+template <typename Real, bool STORED>
 __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan2_kernel(FixedArgs<Real> a, unsigned int num_tiles, OverflowEntry2* overflow) {
     __shared__ Scan2Shared sh;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (a.dynamic && !a.stats->do_resample) return;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x;
-    gate_weights(a.peer, st, a.epoch < 0 ? st->t : a.epoch);
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    gate_weights(a.peer, st, epoch, a.dynamic, a.ess_threshold);
+    if (a.dynamic && !st->do_resample) {   // ESS above the threshold: keep the population, weights keep accumulating
+        if (tid == 0) a.desc[tile] = 0ull;
+        if (tile == 0 && tid == 0) st->resampled_flag[epoch & 1] = 0;
+        return;
+    }
     const unsigned long long W = st->W;
     const float mx = fixed_max<Real>(a);
     if (W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors, flagged
         for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
-        if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; }
+        if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1; }
         if (tid == 0) a.desc[tile] = 0ull;
         return;
     }
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan2_kernel(FixedArgs<
     }
     const size_t wt_base = (size_t)tile * kScanTile + (size_t)warp * kWarpTile;
     unsigned long long q[4][4], incl[4], own[4], tot[4];
-    warp_tile_load_scan<Real>(a, wt_base, mx, q, incl, own, tot);
+    warp_tile_load_scan<Real, STORED>(a, wt_base, mx, q, incl, own, tot);
     if (lane == 0) sh.warp_tot[warp] = tot[0] + tot[1] + tot[2] + tot[3];
     __syncthreads();   // the only block barrier: warp totals and the tile base
     unsigned long long wp = 0;
@@ -173,6 +182,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan2_kernel(FixedArgs<
         st->ess_stale = st->ess;
         if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
         st->resampled = 1;
+        st->resampled_flag[epoch & 1] = 1;
+        st->n_resamples += 1;
         st->degenerate = 0;
     }
     unsigned int n[4][4];
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan2_kernel(FixedArgs<
 }
 
 // heavy warp tiles: every warp of the grid recomputes the tile's counts (512 particles) and expands its share of chunks
-template <typename Real>
+template <typename Real, bool STORED>
 __global__ void __launch_bounds__(kScanThreads) fixed_overflow2_kernel(FixedArgs<Real> a, const OverflowEntry2* overflow) {
     __shared__ Scan2Shared sh;
     DeviceStats* st = a.stats;
@@ -216,7 +227,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_overflow2_kernel(FixedArgs
             const OverflowEntry2 e = overflow[k];
             const size_t wt_base = (size_t)e.tile * kScanTile + (size_t)e.warp * kWarpTile;
             unsigned long long q[4][4], incl[4], own[4], tot[4];
-            warp_tile_load_scan<Real>(a, wt_base, mx, q, incl, own, tot);
+            warp_tile_load_scan<Real, STORED>(a, wt_base, mx, q, incl, own, tot);
             unsigned int n[4][4];
             warp_tile_counts(e.wp, q, incl, own, tot, TileBase{e.n_start, e.rem}, W, inv_w, a.n_out, n);
             const int32_t src0 = a.src_base + (int32_t)(e.tile * (unsigned int)kScanTile + e.warp * kWarpTile) - 1;

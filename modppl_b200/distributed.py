@@ -101,6 +101,7 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
     sampler = B.ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+        time.sleep(0.5)      # nvidia-smi needs a moment to enumerate 8 GPUs
     l0 = ps.launch_count()
     dist.barrier(); torch.cuda.synchronize()
     ms = ps.run(1 + W, K, scheme)

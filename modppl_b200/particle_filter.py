@@ -89,6 +89,11 @@ class ParticleSystem:
         check(lib.mpl_ps_run(self._h, first_step, n_steps, scheme, ess_threshold, C.byref(ms) if timed else None))
         return ms.value
 
+    def num_resamples(self):
+        n = C.c_uint64()
+        check(lib.mpl_ps_num_resamples(self._h, C.byref(n)))
+        return n.value
+
     def sync(self):
         check(lib.mpl_ps_sync(self._h))
 

@@ -396,3 +396,42 @@ def test_parallel_cumsum_bad_inputs_fall_back_to_sequential_semantics():
     p[5000] = np.nan
     got, ref = m.parity.cumsum_sequential(p), np.cumsum(p)
     assert np.array_equal(got[:5000], ref[:5000]) and np.all(np.isnan(got[5000:]))
+
+
+# ------------------------------------------------------------------------------------------------- ESS-triggered device loop (config 5)
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_ess_triggered_device_loop_matches_call_per_step(dtype):
+    # stochastic-volatility model, systematic resampling when the fresh ESS drops below N/2: the device-resident loop
+    # (decision taken on the GPU, nothing copied to the host) against the same policy driven from the host
+    T, n = 60, 1 << 15
+    rng = np.random.default_rng(5)
+    x, ys = -1.0, []
+    for t in range(T):
+        x = -1.024 + 0.9702 * (x + 1.024) + 0.178 * rng.normal()
+        ys.append([math.exp(x / 2) * rng.normal()])
+    ys = np.array(ys)
+    dev = m.ParticleSystem(m.stochastic_volatility(), n, seed=9, dtype=dtype)
+    dev.upload_observations(ys)
+    dev.run(0, T, m.SYSTEMATIC_FIXED, ess_threshold=0.5)
+    host = m.ParticleSystem(m.stochastic_volatility(), n, seed=9, dtype=dtype)
+    host.init_step(ys[0])
+    n_res = 0
+    for t in range(T):
+        if t > 0:
+            host.step(ys[t])
+        if host.effective_sample_size(False) < 0.5 * n:
+            host.resample(m.SYSTEMATIC_FIXED); n_res += 1
+    assert 0 < n_res < T                                     # the trigger fires sometimes, not always
+    assert dev.num_resamples() == n_res
+    a, b = dev.log_marginal_likelihood_estimate(), host.log_marginal_likelihood_estimate()
+    assert abs(a - b) <= 1e-6 * abs(b)
+    assert np.array_equal(dev.traces, host.traces)
+    # and the oracle with the same policy (fresh ESS, quirk Q1 aside) agrees on the log-ML to Monte-Carlo-free precision
+    ref = O.OraclePS("sv", [-1.024, 0.9702, 0.178], n, dtype=dtype, seed=9)
+    ref.init_step(ys[0])
+    for t in range(T):
+        if t > 0:
+            ref.step(ys[t])
+        if ref.effective_sample_size(False) < 0.5 * n:
+            ref.resample(2)
+    assert abs(a - ref.log_marginal_likelihood_estimate()) <= (1e-3 if dtype == "f32" else 1e-6) * abs(a)
