@@ -1,6 +1,8 @@
 // pf.cu -- ParticleSystem host driver + C ABI (reference modppl/src/inference/particle_filter.rs:8-121).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include "engine.h"

@@ -133,6 +133,11 @@ template <> __device__ __forceinline__ void vec_load<double>(const double* p, do
 template <typename Real> __device__ __forceinline__ void vec_store(Real* p, const Real (&v)[VecOf<Real>::N]);
 template <> __device__ __forceinline__ void vec_store<float>(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 template <> __device__ __forceinline__ void vec_store<double>(double* p, const double (&v)[2]) { *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]); }
+// streaming variants (ld/st.global.cs: evict-first).  The state is touched once per step and must not displace the arrays
+// that one kernel of the step hands to the next through the 126 MB L2: log-weights -> integer weights -> ancestors.
+template <typename Real> __device__ __forceinline__ void vec_store_stream(Real* p, const Real (&v)[VecOf<Real>::N]);
+template <> __device__ __forceinline__ void vec_store_stream<float>(float* p, const float (&v)[4]) { __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3])); }
+template <> __device__ __forceinline__ void vec_store_stream<double>(double* p, const double (&v)[2]) { __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1])); }
 
 // ================================================================================================
 // K1/K2/K6/K3: extend
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
     typedef typename std::conditional<V == 4, int4, int2>::type AncVec;
     size_t base = ((size_t)blockIdx.x * kExtendThreads + tid) * V;
     AncVec anc_next = AncVec();
-    if (gather && base < a.n) anc_next = *reinterpret_cast<const AncVec*>(a.anc + base);
+    if (gather && base < a.n) anc_next = __ldcs(reinterpret_cast<const AncVec*>(a.anc + base));
     for (; base < a.n; base += stride) {
         Real x[V][D];
         Real w[V];
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             // pull the parents' cache lines towards L2 so the dependent gather of the next iteration starts warm
             par[0] = anc_next.x; par[1] = anc_next.y;
             if constexpr (V == 4) { par[2] = anc_next.z; par[3] = anc_next.w; }
-            if (base + stride < a.n) anc_next = *reinterpret_cast<const AncVec*>(a.anc + base + stride);
+            if (base + stride < a.n) anc_next = __ldcs(reinterpret_cast<const AncVec*>(a.anc + base + stride));   // last use of these ancestors
             bool local = true;   // all parents in this shard (always, on one GPU; nearly always when sharded)
             if (sharded) {
 #pragma unroll
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             Real tmp[V];
 #pragma unroll
             for (int v = 0; v < V; ++v) tmp[v] = x[v][d];
-            vec_store<Real>(a.state_out + (size_t)d * a.ld + base, tmp);
+            vec_store_stream<Real>(a.state_out + (size_t)d * a.ld + base, tmp);
         }
         vec_store<Real>(a.lw + base, w);
 
@@ -489,7 +494,7 @@ template <typename Real, bool FULL>
 __device__ __forceinline__ void load_stored_q4(const Real* lw, size_t idx, size_t n, unsigned long long (&q)[4]) {
     float w[4];
     if constexpr (sizeof(Real) == 4) {
-        float4 v = *reinterpret_cast<const float4*>(lw + idx);
+        float4 v = __ldcs(reinterpret_cast<const float4*>(lw + idx));   // last use
         w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
     } else {
         double2 a = *reinterpret_cast<const double2*>(lw + idx), b = *reinterpret_cast<const double2*>(lw + idx + 2);
