@@ -155,6 +155,7 @@ int mpl_ps_peer_export(mpl_ps*, void* blob /* MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_attach(mpl_ps*, int rank, int world, const void* blobs /* world * MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_detach(mpl_ps*);
 int mpl_ps_peer_error(mpl_ps*, int* out);   /* 1 if a kernel gave up waiting for a peer (bounded spin) */
+int mpl_ps_trace(mpl_ps*, long long* out16);   /* device time stamps (ns) of the last sharded step's phases; diagnostics */
 /* Test hook: `world` shards emulated on ONE GPU run the multi-GPU kernels phase by phase (remote loads/stores become
  * local).  init + resample, then steps with a resample after each except the last; outputs the final state
  * double[D * n_global] (SoA), log-weights double[n_global] and the log-ML estimate. */

@@ -87,6 +87,7 @@ SYMBOLS = {
     "mpl_ps_peer_attach": (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p),
     "mpl_ps_peer_detach": (C.c_int, C.c_void_p),
     "mpl_ps_peer_error": (C.c_int, C.c_void_p, C.POINTER(C.c_int)),
+    "mpl_ps_trace": (C.c_int, C.c_void_p, C.POINTER(C.c_longlong)),
     "mpl_test_virtual_shards": (C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, c_double_p, C.c_size_t, C.c_size_t, c_double_p, c_double_p, c_double_p, c_double_p),
 }
 for _name, _s in SYMBOLS.items():

@@ -23,6 +23,11 @@ int fail(int code, const std::string& msg);
     } while (0)
 
 constexpr int kNumSMs = 148;   // B200
+
+// Programmatic dependent launch: the next kernel of the step is launched while this one drains and its blocks wait here
+// until this grid has completed and its memory is visible.  Hides ~4 us of kernel-boundary latency per launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 constexpr double kPi = 3.14159265358979323846;
 
 // ------------------------------------------------------------------------------------------------

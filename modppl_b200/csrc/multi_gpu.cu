@@ -7,6 +7,7 @@
 // with step-numbered flags that the consuming kernels spin on locally.  The caller only has to all-gather one
 // MPL_PEER_BLOB_BYTES blob per rank once (bench.py does it with torch.distributed).
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "engine.h"
@@ -100,6 +101,17 @@ extern "C" int mpl_ps_peer_detach(mpl_ps* ps) {
                 if (ps->ipc_opened[k][h]) { cudaIpcCloseMemHandle(ps->ipc_opened[k][h]); ps->ipc_opened[k][h] = nullptr; }
     std::memset(&ps->peer, 0, sizeof ps->peer);
     ps->peer.world = 1; ps->world = 1; ps->rank = 0;
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_trace(mpl_ps* ps, long long* out16) {
+    // %globaltimer stamps (ns) of the last step: [0] extend gate entered, [1] passed, [2] extend's last block done,
+    // [3] reduce gate entered, [4] passed, [5] reduce's last block done, [6] scan gate entered, [7] passed, [8] done flag sent
+    if (!ps || !out16) return fail(MPL_ERR_INVALID, "null argument");
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    DeviceStats h;
+    MPL_CUDA_OK(cudaMemcpy(&h, ps->stats, sizeof h, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; ++i) out16[i] = h.trace[i];
     return MPL_OK;
 }
 

@@ -69,6 +69,20 @@ template <typename Real> Hmm<Real> make_hmm(const mpl_model& m) {
     return f;
 }
 
+// ---- launches with programmatic stream serialisation (the kernels call pdl_wait() first thing) -------------------
+static bool g_use_pdl = getenv("MPL_NO_PDL") == nullptr;
+template <typename... KArgs, typename... Args>
+static cudaError_t pdl_launch(void (*kernel)(KArgs...), unsigned int grid, unsigned int block, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- launch bookkeeping ----------------------------------------------------------------------------------
 struct ScopedLaunch {
     mpl_ps* ps; const char* name; cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -128,15 +142,15 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     {
         ScopedLaunch sl(ps, mode == EXT_INIT ? "init" : "extend");
         switch (mode) {
-            case EXT_INIT: pf_extend_kernel<Model, Real, EXT_INIT><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
-            case EXT_ACCUM: pf_extend_kernel<Model, Real, EXT_ACCUM><<<grid, kExtendThreads, 0, ps->stream>>>(a, model); break;
+            case EXT_INIT: pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false>, grid, kExtendThreads, ps->stream, a, model); break;
+            case EXT_ACCUM: pdl_launch(pf_extend_kernel<Model, Real, EXT_ACCUM, false>, grid, kExtendThreads, ps->stream, a, model); break;
             case EXT_GATHER:
-                if (ps->world > 1) pf_extend_kernel<Model, Real, EXT_GATHER, true><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
-                else pf_extend_kernel<Model, Real, EXT_GATHER><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
+                if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, true>, grid, kExtendThreads, ps->stream, a, model);
+                else pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, false>, grid, kExtendThreads, ps->stream, a, model);
                 break;
             default:
-                if (ps->world > 1) pf_extend_kernel<Model, Real, EXT_DYNAMIC, true><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
-                else pf_extend_kernel<Model, Real, EXT_DYNAMIC><<<grid, kExtendThreads, 0, ps->stream>>>(a, model);
+                if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, true>, grid, kExtendThreads, ps->stream, a, model);
+                else pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, false>, grid, kExtendThreads, ps->stream, a, model);
                 break;
         }
     }
@@ -244,21 +258,21 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
     const size_t num_tiles = (ps->n + kScanTile - 1) / kScanTile;
     {
         ScopedLaunch sl(ps, "fixed_reduce");
-        if (dynamic) fixed_reduce_kernel<Real, false><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
-        else fixed_reduce_kernel<Real, true><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles);
+        if (dynamic) pdl_launch(fixed_reduce_kernel<Real, false>, (unsigned int)num_tiles, kScanThreads, ps->stream, a, (unsigned int)num_tiles);
+        else pdl_launch(fixed_reduce_kernel<Real, true>, (unsigned int)num_tiles, kScanThreads, ps->stream, a, (unsigned int)num_tiles);
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (scheme == MPL_RESAMPLE_SYSTEMATIC_FIXED) {
         {
             ScopedLaunch sl(ps, "fixed_scan");
-            if (dynamic) fixed_scan2_kernel<Real, false><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
-            else fixed_scan2_kernel<Real, true><<<(unsigned int)num_tiles, kScanThreads, 0, ps->stream>>>(a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
+            if (dynamic) pdl_launch(fixed_scan2_kernel<Real, false>, (unsigned int)num_tiles, kScanThreads, ps->stream, a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
+            else pdl_launch(fixed_scan2_kernel<Real, true>, (unsigned int)num_tiles, kScanThreads, ps->stream, a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
         }
         MPL_CUDA_OK(cudaGetLastError());
         if (a.overflow_follows) {
             ScopedLaunch sl(ps, "fixed_overflow");
-            if (dynamic) fixed_overflow2_kernel<Real, false><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow);
-            else fixed_overflow2_kernel<Real, true><<<kNumSMs * 2, kScanThreads, 0, ps->stream>>>(a, (const OverflowEntry2*)ps->overflow);
+            if (dynamic) pdl_launch(fixed_overflow2_kernel<Real, false>, kNumSMs * 2, kScanThreads, ps->stream, a, (const OverflowEntry2*)ps->overflow);
+            else pdl_launch(fixed_overflow2_kernel<Real, true>, kNumSMs * 2, kScanThreads, ps->stream, a, (const OverflowEntry2*)ps->overflow);
         }
         MPL_CUDA_OK(cudaGetLastError());
     } else {

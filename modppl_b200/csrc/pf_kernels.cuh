@@ -46,7 +46,9 @@ struct DeviceStats {
     unsigned long long n_resamples;   // resamples performed so far
     unsigned long long max_bits[2];   // exact max of the log-weights written by the extend of step t, slot t & 1 (order-preserving bits)
     long long ready_stats, ready_w, ready_done;
+    long long trace[16];           // %globaltimer stamps of the last step's phases (sharded runs; mpl_ps_trace)
 };
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // ---- multi-GPU: one process per GPU, peers reached through NVLink-mapped pointers (CUDA IPC) ----------------------------
 // Every rank owns a Mailbox; rank g writes column g of every peer's mailbox (remote stores), then a flag carrying the
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
     constexpr int D = Model::D;
     constexpr int V = VecOf<Real>::N;
     const int tid = threadIdx.x;
+    pdl_wait();
 
     long long t = a.t;
     if (t < 0) t = a.stats->t;
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
         }
     }
 
+    pdl_trigger();
     __shared__ Real warp_max_s[kExtendThreads / 32];
     __shared__ bool is_last;
 #pragma unroll
@@ -291,6 +295,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
             if (is_last) {
                 a.stats->blocks_done = 0;
+                a.stats->trace[2] = global_ns();
                 __threadfence();
                 const double m = from_ordered_bits(*(volatile unsigned long long*)&a.stats->max_bits[t & 1]);
                 for (int h = 0; h < a.peer.world; ++h) {
@@ -407,11 +412,13 @@ __device__ __forceinline__ void gate_stats(const PeerTable& p, DeviceStats* st, 
     if (p.world <= 1) return;
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
+            st->trace[3] = global_ns();
             Mailbox* mb = p.mail[p.rank];
             SpinGuard g(p);
             double m = -INFINITY;
             for (int h = 0; h < p.world; ++h) m = fmax(m, __longlong_as_double((long long)ll_read64(&mb->stats_ll[h][0], (unsigned int)epoch, g)));
             st->max = m;
+            st->trace[4] = global_ns();
             local_ready_set(&st->ready_stats, epoch);
         } else local_ready_wait(&st->ready_stats, epoch, p);
     }
@@ -422,6 +429,7 @@ __device__ __forceinline__ void gate_weights(const PeerTable& p, DeviceStats* st
     if (p.world <= 1) return;
     if (threadIdx.x == 0) {
         if (blockIdx.x == 0) {
+            st->trace[6] = global_ns();
             Mailbox* mb = p.mail[p.rank];
             SpinGuard g(p);
             unsigned long long W = 0, c = 0;
@@ -436,6 +444,7 @@ __device__ __forceinline__ void gate_weights(const PeerTable& p, DeviceStats* st
             st->sumexp2 = sq;
             st->ess = sq > 0. ? ((double)W * (double)W) / sq : 0.;
             if (dynamic) st->do_resample = (st->ess < ess_threshold) ? 1 : 0;
+            st->trace[7] = global_ns();
             local_ready_set(&st->ready_w, epoch);
         } else local_ready_wait(&st->ready_w, epoch, p);
     }
@@ -445,7 +454,7 @@ __device__ __forceinline__ void gate_weights(const PeerTable& p, DeviceStats* st
 __device__ __forceinline__ void gate_done(const PeerTable& p, DeviceStats* st, long long epoch) {
     if (p.world <= 1) return;
     if (threadIdx.x == 0) {
-        if (blockIdx.x == 0) { peer_wait_done(p, epoch); local_ready_set(&st->ready_done, epoch); }
+        if (blockIdx.x == 0) { st->trace[0] = global_ns(); peer_wait_done(p, epoch); st->trace[1] = global_ns(); local_ready_set(&st->ready_done, epoch); }
         else local_ready_wait(&st->ready_done, epoch, p);
     }
     __syncthreads();
@@ -522,6 +531,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
     __shared__ double wsq[kScanThreads / 32];
     __shared__ unsigned long long carry_s;
     __shared__ bool is_last;
+    pdl_wait();
     gate_stats(a.peer, a.stats, a.epoch < 0 ? a.stats->t : a.epoch);
     const float mx = fixed_max<Real>(a);
     {
@@ -553,6 +563,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
         if (lane == 0 && sum) atomicAdd(&a.desc[tile], sum);
         if (lane == 0) wsq[warp] = sq;
     }
+    pdl_trigger();
     __syncthreads();
     if (tid == 0) {   // fixed summation order: the ESS is reproducible
         double b = 0.;
@@ -609,6 +620,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
             st->ess = sq > 0. ? ((double)carry_s * (double)carry_s) / sq : 0.;   // 1 / sum(w~^2), particle_filter.rs:98-100
             if (a.dynamic) st->do_resample = (st->ess < a.ess_threshold) ? 1 : 0;
         } else {   // post this shard's integer weight (and sum of squares) to every rank; the scan's gate adds them up
+            st->trace[5] = global_ns();
             const long long epoch = a.epoch < 0 ? st->t : a.epoch;
             for (int h = 0; h < a.peer.world; ++h) {
                 ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], carry_s, (unsigned int)epoch);

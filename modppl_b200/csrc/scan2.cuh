@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan2_kernel(FixedArgs<
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x;
+    pdl_wait();
     const long long epoch = a.epoch < 0 ? st->t : a.epoch;
     gate_weights(a.peer, st, epoch, a.dynamic, a.ess_threshold);
     if (a.dynamic && !st->do_resample) {   // ESS above the threshold: keep the population, weights keep accumulating
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) fixed_scan2_kernel(FixedArgs<
     warp_tile_load_scan<Real, STORED>(a, wt_base, mx, q, incl, own, tot);
     if (lane == 0) sh.warp_tot[warp] = tot[0] + tot[1] + tot[2] + tot[3];
     __syncthreads();   // the only block barrier: warp totals and the tile base
+    pdl_trigger();
     unsigned long long wp = 0;
 #pragma unroll
     for (int w = 0; w < kScanThreads / 32; ++w) if (w < warp) wp += sh.warp_tot[w];
@@ -214,6 +216,8 @@ template <typename Real, bool STORED>
 __global__ void __launch_bounds__(kScanThreads) fixed_overflow2_kernel(FixedArgs<Real> a, const OverflowEntry2* overflow) {
     __shared__ Scan2Shared sh;
     DeviceStats* st = a.stats;
+    pdl_wait();
+    pdl_trigger();
     if (a.dynamic && !st->do_resample) return;
     const unsigned int count = st->overflow_count;
     if (count == 0u && a.peer.world <= 1) return;
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_overflow2_kernel(FixedArgs
             }
         }
         if (signal) {
+            st->trace[8] = global_ns();
             const long long epoch = a.epoch < 0 ? st->t : a.epoch;
             for (int h = 0; h < a.peer.world; ++h) {
                 if (count == 0u) *(volatile long long*)&a.peer.mail[h]->flag_done[a.peer.rank] = epoch;

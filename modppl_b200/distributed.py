@@ -66,6 +66,11 @@ class ShardedParticleSystem(ParticleSystem):
             joined = C.create_string_buffer(b"".join(blobs), PEER_BLOB_BYTES * world)
             check(lib.mpl_ps_peer_attach(self._h, rank, world, joined))
 
+    def trace(self):
+        buf = (C.c_longlong * 16)()
+        check(lib.mpl_ps_trace(self._h, buf))
+        return list(buf)
+
     def peer_error(self):
         e = C.c_int()
         check(lib.mpl_ps_peer_error(self._h, C.byref(e)))
@@ -109,6 +114,11 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
     dist.barrier(); torch.cuda.synchronize()
     ms = max_over_ranks(ms)
     launches = ps.launch_count() - l0
+    tr = ps.trace()     # last step of the timed run, this rank's clock (ns)
+    phases = {"extend_gate_wait": tr[1] - tr[0], "extend_body": tr[2] - tr[1], "to_reduce_gate": tr[3] - tr[2], "reduce_gate_wait": tr[4] - tr[3],
+              "reduce_body": tr[5] - tr[4], "to_scan_gate": tr[6] - tr[5], "scan_gate_wait": tr[7] - tr[6], "scan_to_signal": tr[8] - tr[7]}
+    all_phases = [None] * world
+    dist.all_gather_object(all_phases, phases)
     # e2e: one host round trip per step on every rank
     t_first = 1 + W + K
     dist.barrier(); torch.cuda.synchronize()
@@ -144,6 +154,7 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
             "gpu_launches": int(launches) * world, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": step_gbs, "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "traffic": None,
                          "peak_source": peak_src + f" x {world} GPUs", "kernel_ms_rank0": kernel_ms},
+            "phase_ns_per_rank": all_phases,
         }
         print(json.dumps(line))
     ps.close()
