@@ -16,6 +16,13 @@ class MplError(RuntimeError):
         self.code = code
 
 
+if not os.path.exists(LIB_PATH) and not os.environ.get("MODPPL_B200_LIB"):
+    # a fresh checkout: compile the CUDA library in-tree (nvcc cross-compiles sm_100a without a GPU)
+    import subprocess
+    try:
+        subprocess.check_call(["make", "-C", os.path.dirname(_HERE), "modppl_b200/lib/libmodppl_b200.so"], stdout=subprocess.DEVNULL)
+    except Exception as e:  # noqa: BLE001
+        raise ImportError(f"could not build {LIB_PATH}: {e}.  modppl_b200 has no CPU fallback.") from e
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `make` (or `python -c 'import __graft_entry__ as g; g.build()'`). "

@@ -579,6 +579,31 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // sharded: the shard total first -- every rank is waiting for it -- then the prefix scan overlaps the NVLink latency
+    if (a.peer.world > 1) {
+        unsigned long long tot = 0;
+        double sqt0 = 0.;
+        for (unsigned int i = tid; i < num_tiles; i += kScanThreads) { tot += a.desc[i]; sqt0 += a.sq_partials[i]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, o); sqt0 += __shfl_xor_sync(0xffffffffu, sqt0, o); }
+        __syncthreads();
+        if (lane == 0) { ws[warp] = tot; wsq[warp] = sqt0; }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long b = 0;
+            double sq = 0.;
+#pragma unroll
+            for (int i = 0; i < kScanThreads / 32; ++i) { b += ws[i]; sq += wsq[i]; }
+            DeviceStats* st = a.stats;
+            const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+            st->trace[5] = global_ns();
+            for (int h = 0; h < a.peer.world; ++h) {
+                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], b, (unsigned int)epoch);
+                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank] + 2, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
+            }
+        }
+        __syncthreads();
+    }
     // exclusive scan of the tile sums, 4 consecutive tiles per thread per pass
     for (unsigned int base = 0; base < num_tiles; base += kScanThreads * 4) {
         unsigned long long v[4], tot = 0;
@@ -619,14 +644,7 @@ __global__ void __launch_bounds__(kScanThreads) fixed_reduce_kernel(FixedArgs<Re
             st->sumexp2 = sq;
             st->ess = sq > 0. ? ((double)carry_s * (double)carry_s) / sq : 0.;   // 1 / sum(w~^2), particle_filter.rs:98-100
             if (a.dynamic) st->do_resample = (st->ess < a.ess_threshold) ? 1 : 0;
-        } else {   // post this shard's integer weight (and sum of squares) to every rank; the scan's gate adds them up
-            st->trace[5] = global_ns();
-            const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-            for (int h = 0; h < a.peer.world; ++h) {
-                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], carry_s, (unsigned int)epoch);
-                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank] + 2, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
-            }
-        }
+        }   // (sharded: already posted above)
     }
 }
 
