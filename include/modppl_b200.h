@@ -91,6 +91,11 @@ int mpl_ps_log_marginal_likelihood_estimate(mpl_ps*, double* out);              
 int mpl_ps_read(mpl_ps*, int what, void* host_dst, size_t bytes);                                   /* `pub traces` :13     */
 int mpl_ps_write(mpl_ps*, int what, const void* host_src, size_t bytes);                            /* parity hook: inject state / log-weights */
 int mpl_ps_num_particles(const mpl_ps*, uint64_t* out);
+/* Trajectories: the reference keeps every trace's whole history (`retv: Vec<State>`, dynunfold.rs:91-92) and clones it on
+ * each resample.  Here an optional log of per-step states and ancestors (max_steps x (D+1) x N elements, so for small N)
+ * is back-traced on demand: out[k][t][d] = state at step t of the lineage of particle ids[k]. */
+int mpl_ps_history_enable(mpl_ps*, uint64_t max_steps);
+int mpl_ps_trajectories(mpl_ps*, const int64_t* ids, uint64_t n_ids, double* out, size_t bytes, uint64_t* n_steps);
 int mpl_ps_sync(mpl_ps*);
 
 /* Device-resident filter loop: `n_steps` x (step; [ESS test]; resample) with all observations already in HBM.

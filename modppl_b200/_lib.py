@@ -68,6 +68,8 @@ SYMBOLS = {
     "mpl_ps_read": (C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t),
     "mpl_ps_write": (C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t),
     "mpl_ps_num_particles": (C.c_int, C.c_void_p, c_u64_p),
+    "mpl_ps_history_enable": (C.c_int, C.c_void_p, C.c_uint64),
+    "mpl_ps_trajectories": (C.c_int, C.c_void_p, c_i64_p, C.c_uint64, c_double_p, C.c_size_t, c_u64_p),
     "mpl_ps_sync": (C.c_int, C.c_void_p),
     "mpl_ps_upload_observations": (C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_size_t),
     "mpl_ps_run": (C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_double, c_float_p),

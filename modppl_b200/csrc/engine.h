@@ -59,6 +59,12 @@ struct mpl_ps {
     double* sq_partials;   // per-tile sums of squared weights (ESS in the integer resampler)
     int* host_flags;       // pinned + mapped: [0] = a heavy tile was seen (launch the overflow pass from now on)
     int* host_flags_dev;
+    // trajectory reconstruction (reference keeps traces[i].retv as a Vec<State>, dynunfold.rs:91-92): optional log of the
+    // per-step states and ancestors, back-traced on demand
+    void* hist_state;            // [hist_cap][D][ld] Real
+    int32_t* hist_anc;           // [hist_cap][ld]
+    size_t hist_cap;
+    std::vector<int> hist_resampled;   // [t]: a resample followed step t
     double ess_threshold_abs;   // ESS-triggered device loop: threshold in particles
     bool dynamic_state_known;
     bool profile;

@@ -156,6 +156,15 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (mode == EXT_GATHER || mode == EXT_DYNAMIC) ps->cur ^= 1;
+    if (ps->hist_cap) {   // trajectory log: the state this step produced (kernel time index ps->t, not yet incremented by the caller)
+        const size_t tt = (size_t)ps->t;
+        if (tt < ps->hist_cap) {
+            const size_t bytes = (size_t)ps->D * ps->ld * sizeof(Real);
+            MPL_CUDA_OK(cudaMemcpyAsync((char*)ps->hist_state + tt * bytes, ps->state[ps->cur], bytes, cudaMemcpyDeviceToDevice, ps->stream));
+            if (ps->hist_resampled.size() <= tt) ps->hist_resampled.resize(tt + 1, 0);
+            ps->hist_resampled[tt] = 0;
+        }
+    }
     return MPL_OK;
 }
 
@@ -369,6 +378,12 @@ static int do_resample(mpl_ps* ps, int scheme) {
     if (rc) return rc;
     ps->pending_gather = true;
     ps->stats_valid = false; ps->max_valid = false;
+    if (ps->hist_cap && ps->t >= 1 && (size_t)(ps->t - 1) < ps->hist_cap) {   // ancestors chosen after step t-1
+        const size_t tt = (size_t)(ps->t - 1);
+        MPL_CUDA_OK(cudaMemcpyAsync(ps->hist_anc + tt * ps->ld, ps->anc, ps->ld * sizeof(int32_t), cudaMemcpyDeviceToDevice, ps->stream));
+        if (ps->hist_resampled.size() <= tt) ps->hist_resampled.resize(tt + 1, 0);
+        ps->hist_resampled[tt] = 1;
+    }
     return MPL_OK;
 }
 
@@ -479,6 +494,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->seed = c.seed; ps->gid_offset = c.gid_offset; ps->n_global = c.n_global ? c.n_global : num_particles;
     ps->D = model->state_dim;
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
+    ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
@@ -532,6 +548,7 @@ extern "C" void mpl_ps_destroy(mpl_ps* ps) {
     cudaFree(ps->state[0]); cudaFree(ps->state[1]); cudaFree(ps->lw); cudaFree(ps->anc); cudaFree(ps->desc); cudaFree(ps->overflow);
     cudaFree(ps->stats); cudaFreeHost(ps->stats_host); cudaFree(ps->partials); cudaFree(ps->ipartials);
     cudaFree(ps->sq_partials); if (ps->host_flags) cudaFreeHost(ps->host_flags);
+    cudaFree(ps->hist_state); cudaFree(ps->hist_anc);
     if (ps->world > 1 && !ps->peer_virtual) mpl_ps_peer_detach(ps);
     cudaFree(ps->mailbox);
     cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
@@ -680,6 +697,52 @@ extern "C" int mpl_ps_write(mpl_ps* ps, int what, const void* host_src, size_t b
     } else return fail(MPL_ERR_INVALID, "unknown write selector");
     MPL_CUDA_OK(cudaGetLastError());
     MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_history_enable(mpl_ps* ps, uint64_t max_steps) {
+    if (!ps || max_steps == 0) return fail(MPL_ERR_INVALID, "bad argument");
+    if (ps->world > 1) return fail(MPL_ERR_UNSUPPORTED, "trajectory log: single GPU only");
+    if (ps->initialised) return fail(MPL_ERR_INVALID, "enable the trajectory log before init_step");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    cudaFree(ps->hist_state); cudaFree(ps->hist_anc); ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
+    const size_t es = elem_size(ps);
+    cudaError_t e = cudaMalloc(&ps->hist_state, (size_t)max_steps * ps->D * ps->ld * es);
+    if (e == cudaSuccess) e = cudaMalloc(&ps->hist_anc, (size_t)max_steps * ps->ld * sizeof(int32_t));
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(ps->hist_state); ps->hist_state = nullptr; return fail(MPL_ERR_CUDA, "trajectory log does not fit in device memory (it is max_steps x (D+1) x N)"); }
+    ps->hist_cap = (size_t)max_steps;
+    ps->hist_resampled.clear();
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_trajectories(mpl_ps* ps, const int64_t* ids, uint64_t n_ids, double* out, size_t bytes, uint64_t* n_steps) {
+    // out[k][t][d]: the state at step t of the lineage of particle ids[k] (`traces[ids[k]].retv`, dynunfold.rs:91)
+    if (!ps || !ids || !out) return fail(MPL_ERR_INVALID, "null argument");
+    if (!ps->hist_cap) return fail(MPL_ERR_INVALID, "trajectory log not enabled");
+    if (ps->dynamic_state_known) return fail(MPL_ERR_UNSUPPORTED, "trajectory log: not with the ESS-triggered device loop");
+    const size_t T = (size_t)ps->t;
+    if (T == 0 || T > ps->hist_cap) return fail(MPL_ERR_INVALID, "no logged steps, or more steps than the log holds");
+    if (bytes != n_ids * T * ps->D * sizeof(double)) return fail(MPL_ERR_INVALID, "trajectory buffer must be double[n_ids * T * D]");
+    for (uint64_t k = 0; k < n_ids; ++k) if (ids[k] < 0 || (uint64_t)ids[k] >= ps->n) return fail(MPL_ERR_INVALID, "particle id out of range");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    long long* dids = nullptr; int* dres = nullptr; double* dout = nullptr;
+    std::vector<int> res(ps->hist_resampled);
+    res.resize(T, 0);
+    MPL_CUDA_OK(cudaMalloc(&dids, n_ids * 8));
+    MPL_CUDA_OK(cudaMalloc(&dres, T * sizeof(int)));
+    MPL_CUDA_OK(cudaMalloc(&dout, bytes));
+    MPL_CUDA_OK(cudaMemcpyAsync(dids, ids, n_ids * 8, cudaMemcpyHostToDevice, ps->stream));
+    MPL_CUDA_OK(cudaMemcpyAsync(dres, res.data(), T * sizeof(int), cudaMemcpyHostToDevice, ps->stream));
+    const int after = (ps->pending_gather && res[T - 1]) ? 1 : 0;
+    const int grid = grid_for(n_ids, 128, kNumSMs * 8);
+    if (ps->dtype == MPL_F32) backtrace_kernel<float><<<grid, 128, 0, ps->stream>>>((const float*)ps->hist_state, ps->hist_anc, dres, ps->ld, ps->D, (int)T, after, dids, n_ids, dout);
+    else backtrace_kernel<double><<<grid, 128, 0, ps->stream>>>((const double*)ps->hist_state, ps->hist_anc, dres, ps->ld, ps->D, (int)T, after, dids, n_ids, dout);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ps->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ps->stream);
+    cudaFree(dids); cudaFree(dres); cudaFree(dout);
+    if (e != cudaSuccess) return fail(MPL_ERR_CUDA, cudaGetErrorString(e));
+    if (n_steps) *n_steps = T;
     return MPL_OK;
 }
 

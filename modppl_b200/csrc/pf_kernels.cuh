@@ -873,6 +873,21 @@ __global__ void __launch_bounds__(256) gather_kernel(const Real* __restrict__ in
     }
 }
 
+// trajectories by back-tracing the ancestor log: one thread per requested particle, newest step first
+template <typename Real>
+__global__ void __launch_bounds__(128) backtrace_kernel(const Real* __restrict__ hist_state, const int32_t* __restrict__ hist_anc, const int* __restrict__ resampled,
+                                                        size_t ld, int D, int T, int start_after_resample, const long long* __restrict__ ids, size_t n_ids,
+                                                        double* __restrict__ out /* [n_ids][T][D] */) {
+    for (size_t k = (size_t)blockIdx.x * 128 + threadIdx.x; k < n_ids; k += (size_t)gridDim.x * 128) {
+        size_t cur = (size_t)ids[k];
+        if (start_after_resample) cur = (size_t)hist_anc[(size_t)(T - 1) * ld + cur];   // ids name post-resample particles
+        for (int t = T - 1; t >= 0; --t) {
+            for (int d = 0; d < D; ++d) out[(k * T + t) * D + d] = (double)hist_state[((size_t)t * D + d) * ld + cur];
+            if (t > 0 && resampled[t - 1]) cur = (size_t)hist_anc[(size_t)(t - 1) * ld + cur];
+        }
+    }
+}
+
 template <typename Real>
 __global__ void __launch_bounds__(256) fill_kernel(Real* p, size_t n, Real v) {
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) p[i] = v;

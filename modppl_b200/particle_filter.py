@@ -30,10 +30,12 @@ class ParticleSystem:
     def init_step(self, constraints):                      # :60-70
         a, p, n = _obs(constraints)
         check(lib.mpl_ps_init_step(self._h, p, n))
+        self._steps_done = 1
 
     def step(self, constraints):                           # :73-95
         a, p, n = _obs(constraints)
         check(lib.mpl_ps_step(self._h, p, n))
+        self._steps_done = getattr(self, "_steps_done", 0) + 1
         return self
 
     def effective_sample_size(self, stale_like_reference=True):   # :98-100 (quirk Q1: the reference value is stale)
@@ -87,7 +89,22 @@ class ParticleSystem:
     def run(self, first_step, n_steps, scheme=SYSTEMATIC_FIXED, ess_threshold=0.0, timed=True):
         ms = C.c_float(0.0)
         check(lib.mpl_ps_run(self._h, first_step, n_steps, scheme, ess_threshold, C.byref(ms) if timed else None))
+        self._steps_done = first_step + n_steps
         return ms.value
+
+    def enable_history(self, max_steps):
+        """Log per-step states and ancestors so that `trajectories` can rebuild `traces[i].retv` (dynunfold.rs:91-92)."""
+        check(lib.mpl_ps_history_enable(self._h, int(max_steps)))
+        self._hist_cap = int(max_steps)
+
+    def trajectories(self, ids):
+        """-> array [len(ids), T, D]: the lineage of each particle, oldest step first."""
+        ids = np.ascontiguousarray(np.asarray(ids, dtype=np.int64).ravel())
+        T = C.c_uint64()
+        steps = self._steps_done        # logged steps == init_step + step calls so far
+        out = np.empty((ids.size, steps, self.state_dim), dtype=np.float64)
+        check(lib.mpl_ps_trajectories(self._h, ids.ctypes.data_as(_lib.c_i64_p), ids.size, out.ctypes.data_as(_lib.c_double_p), out.nbytes, C.byref(T)))
+        return out
 
     def num_resamples(self):
         n = C.c_uint64()

@@ -435,3 +435,42 @@ def test_ess_triggered_device_loop_matches_call_per_step(dtype):
         if ref.effective_sample_size(False) < 0.5 * n:
             ref.resample(2)
     assert abs(a - ref.log_marginal_likelihood_estimate()) <= (1e-3 if dtype == "f32" else 1e-6) * abs(a)
+
+
+# ------------------------------------------------------------------------------------------------- trajectories (next-tier row f.2)
+@pytest.mark.parametrize("scheme,dtype", [(0, "f64"), (2, "f32")])
+def test_trajectories_match_backtraced_oracle(scheme, dtype):
+    # the reference keeps traces[i].retv = Vec<State> and clones it on every resample (particle_filter.rs:109-113,
+    # dynunfold.rs:91-92); the engine logs states + ancestors and back-traces.  Oracle: record per-step states and parents
+    # and back-trace in numpy.
+    n, T = 2000, 12
+    ys = lgssm_data(T)
+    f = m.ParticleSystem(m.lgssm4(), n, seed=4, dtype=dtype)
+    f.enable_history(T)
+    r = O.OraclePS("lgssm4", [0.1, 0.5, 1.0], n, dtype=dtype, seed=4)
+    states, parents = [], []
+    for t in range(T):
+        if t == 0:
+            f.init_step(ys[0]); r.init_step(ys[0])
+        else:
+            f.step(ys[t]); r.step(ys[t])
+        # keep both on identical inputs so that round-off cannot flip an ancestor
+        f.write_state(r.traces); f.write_log_weights(r.log_weights)
+        states.append(r.traces.copy())
+        if t % 3 != 2:                      # some steps are not followed by a resample
+            f.resample(scheme); r.resample(scheme)
+            parents.append(r.parents.copy())
+        else:
+            parents.append(None)
+    ids = np.array([0, 1, 7, n // 2, n - 1])
+    got = f.trajectories(ids)
+    assert got.shape == (5, T, 4)
+    for k, i in enumerate(ids):
+        cur = i
+        if parents[T - 1] is not None:      # ids name post-resample particles when a resample is pending
+            cur = parents[T - 1][cur]
+        for t in range(T - 1, -1, -1):
+            # (the log holds the device's own step results: equal to the oracle's up to round-off; the LINEAGE is exact)
+            assert np.allclose(got[k, t], states[t][:, cur], rtol=1e-9 if dtype == "f64" else 1e-4, atol=1e-9 if dtype == "f64" else 1e-4), (k, t)
+            if t > 0 and parents[t - 1] is not None:
+                cur = parents[t - 1][cur]
