@@ -73,10 +73,12 @@ __host__ __device__ __forceinline__ float u01_oc32(uint32_t x) { return (float)(
 // logf/sincospif): -2 ln(u1) from MUFU.LG2 with a 3-term series where u1 is within 2^-6 of 1 (there MUFU.LG2's
 // absolute error would dominate the tiny result), sqrt.approx, MUFU.SIN/COS on an argument folded into [-pi, pi).
 // Absolute error of a normal deviate ~1e-6, far inside the 1e-4 fp32 parity tolerance.
-__device__ __forceinline__ float neg2log_fast(float u1) {
-    float l = __log2f(u1) * -1.3862943611198906f;                    // -2 ln2 lg2(u1)
-    float v = 1.0f - u1;                                              // exact
-    float s = v * fmaf(v, fmaf(v, 0.66666667f, 1.0f), 2.0f);         // -2 ln(1 - v) = 2v + v^2 + (2/3) v^3 + O(v^4)
+// k1, k2: the top 24 bits of two Philox words.  u1 = (k1 + 1) 2^-24 in (0, 1], u2 = k2 2^-24 in [0, 1); the 2^-24 scalings
+// are folded into the constants of the following FFMAs (lg2(u1) = lg2(k1 + 1) - 24 exactly).
+__device__ __forceinline__ float neg2log_fast_k(float kf /* k1 + 1 as float, exact */) {
+    float l = fmaf(__log2f(kf), -1.3862943611198906f, 33.27106466687737f);   // -2 ln2 (lg2(kf) - 24)
+    float v = fmaf(kf, -0x1.0p-24f, 1.0f);                                     // 1 - u1, exact
+    float s = v * fmaf(v, fmaf(v, 0.66666667f, 1.0f), 2.0f);                  // -2 ln(1 - v) = 2v + v^2 + (2/3) v^3 + O(v^4)
     return (v < 0.015625f) ? s : l;
 }
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -84,10 +86,19 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ void box_muller(float u1, float u2, float& z0, float& z1) {
-    float r = -sqrt_approx(neg2log_fast(u1));
-    float a = fmaf(u2, 6.283185307179586f, -3.141592653589793f);    // 2 pi u2 - pi in [-pi, pi)
+__device__ __forceinline__ void box_muller_bits(uint32_t x1, uint32_t x2, float& z0, float& z1) {
+    float r = -sqrt_approx(neg2log_fast_k((float)((x1 >> 8) + 1u)));
+    float a = fmaf((float)(x2 >> 8), 3.7450703e-07f /* 2 pi 2^-24 */, -3.141592653589793f);   // 2 pi u2 - pi in [-pi, pi)
     z0 = r * __cosf(a);                                               // cos(2 pi u2) = -cos(a)
+    z1 = r * __sinf(a);
+}
+__device__ __forceinline__ void box_muller(float u1, float u2, float& z0, float& z1) {   // (generic entry; the hot path uses the _bits form)
+    float l = __log2f(u1) * -1.3862943611198906f;
+    float v = 1.0f - u1;
+    float s = v * fmaf(v, fmaf(v, 0.66666667f, 1.0f), 2.0f);
+    float r = -sqrt_approx((v < 0.015625f) ? s : l);
+    float a = fmaf(u2, 6.283185307179586f, -3.141592653589793f);
+    z0 = r * __cosf(a);
     z1 = r * __sinf(a);
 }
 __device__ __forceinline__ void box_muller(double u1, double u2, double& z0, double& z1) {
@@ -106,11 +117,11 @@ __device__ __forceinline__ void draw_normals(const Stream& s, uint32_t first_blk
     for (int i = 0; i < COUNT; i += 4) {
         uint4 x = s.block(first_blk + i / 4);
         float a, b;
-        box_muller(u01_oc32(x.x), u01_co32(x.y), a, b);
+        box_muller_bits(x.x, x.y, a, b);
         z[i] = a;
         if (i + 1 < COUNT) z[i + 1] = b;
         if (i + 2 < COUNT) {
-            box_muller(u01_oc32(x.z), u01_co32(x.w), a, b);
+            box_muller_bits(x.z, x.w, a, b);
             z[i + 2] = a;
             if (i + 3 < COUNT) z[i + 3] = b;
         }

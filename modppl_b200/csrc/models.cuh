@@ -20,7 +20,7 @@ template <typename Real>
 struct Lgssm4 {
     static constexpr int D = 4;
     static constexpr int NOBS = 2;
-    Real q, r, x0, ln_r, inv_r;
+    Real q, r, x0, ln_r, inv_r, lw_const;   // lw_const = ln 2pi + 2 ln r
     __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
         Real z[4];
         draw_normals<4>(s, 0, z);
@@ -33,13 +33,10 @@ struct Lgssm4 {
             x[2] = x[2] + z[2] * q;
             x[3] = x[3] + z[3] * q;
         }
-        Real lw = 0;
-#pragma unroll
-        for (int d = 0; d < 2; ++d) {
-            Real zz = ((Real)obs.v[d] - x[d]) * inv_r;                  // z = (x - mu) / std with 1/std hoisted
-            lw += -(zz * zz + (Real)1.8378770664093453) / 2 - ln_r;   // normal.rs:13-17
-        }
-        return lw;
+        // two independent `normal` observations (normal.rs:13-17), summed in closed form:
+        //   sum_d -(z_d^2 + ln 2pi)/2 - ln r  =  -(z_0^2 + z_1^2)/2 - (ln 2pi + 2 ln r)
+        const Real z0 = ((Real)obs.v[0] - x[0]) * inv_r, z1 = ((Real)obs.v[1] - x[1]) * inv_r;   // 1/std hoisted
+        return (Real)-0.5 * (z0 * z0 + z1 * z1) - lw_const;
     }
 };
 

@@ -34,6 +34,7 @@ template <typename Real> Lgssm4<Real> make_lgssm4(const mpl_model& m) {
     f.x0 = (Real)(p.size() > 2 ? p[2] : 1.0);
     f.ln_r = (Real)std::log((double)f.r);
     f.inv_r = (Real)1 / f.r;
+    f.lw_const = (Real)(1.8378770664093453 + 2. * std::log((double)f.r));
     return f;
 }
 template <typename Real> Spiral<Real> make_spiral(const mpl_model& m) {

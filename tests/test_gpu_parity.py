@@ -474,3 +474,18 @@ def test_trajectories_match_backtraced_oracle(scheme, dtype):
             assert np.allclose(got[k, t], states[t][:, cur], rtol=1e-9 if dtype == "f64" else 1e-4, atol=1e-9 if dtype == "f64" else 1e-4), (k, t)
             if t > 0 and parents[t - 1] is not None:
                 cur = parents[t - 1][cur]
+
+
+def test_virtual_shards_ragged_shard_size():
+    # shard sizes that are not multiples of the 4096-particle tile (ragged last tile in every shard, ancestors and slot
+    # ranges straddling shard boundaries mid-tile)
+    n, world, T = 8 * 5003, 8, 5
+    ys = lgssm_data(T)
+    st, lw, lml = m.parity.virtual_shards(m.lgssm4(), n, world, ys, dtype="f32", seed=23)
+    one = m.ParticleSystem(m.lgssm4(), n, seed=23, dtype="f32")
+    one.init_step(ys[0]); one.resample(m.SYSTEMATIC_FIXED)
+    for t in range(1, T):
+        one.step(ys[t])
+        if t + 1 < T:
+            one.resample(m.SYSTEMATIC_FIXED)
+    assert np.array_equal(st, one.traces) and np.array_equal(lw, one.log_weights)
