@@ -135,7 +135,7 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     T = 1 + W + K + K + 8
     ys = observations(T)
-    scheme = m.SYSTEMATIC_FIXED if args.scheme == "systematic" else m.MULTINOMIAL_FIXED
+    scheme = {"systematic": m.SYSTEMATIC_FIXED, "multinomial": m.MULTINOMIAL_FIXED, "nested": m.SYSTEMATIC_NESTED}[args.scheme]
     if world > 1:
         from modppl_b200 import distributed as D
         return D.bench_multi(args, ys, scheme, rank, world, local_rank)
@@ -168,7 +168,7 @@ def run_ours(args):
     steps_prof = min(K, T - ps2_first)
     for k in range(steps_prof):
         ps.step(ys[ps2_first + k]); ps.resample(scheme, sync=False)
-    prof = {k: ps.profile_get(k) for k in ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "fixed_cumsum", "fixed_search")}
+    prof = {k: ps.profile_get(k) for k in ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "fixed_cumsum", "fixed_search", "nested_quantise", "nested_chunk", "nested_scan")}
     ps.profile_enable(False)
     peak, peak_src = measured_peak()
     ext_ms = prof["extend"][0] / max(1, prof["extend"][1])
@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scheme", default="systematic", choices=["systematic", "multinomial"])
+    ap.add_argument("--scheme", default="systematic", choices=["systematic", "multinomial", "nested"])
     ap.add_argument("--log2-particles", type=int, default=LOG2_PARTICLES)
     args = ap.parse_args()
     if args.warmup < 3:

@@ -61,6 +61,8 @@ struct mpl_ps {
     int* host_flags_dev;
     // trajectory reconstruction (reference keeps traces[i].retv as a Vec<State>, dynunfold.rs:91-92): optional log of the
     // per-step states and ancestors, back-traced on demand
+    int* rec_e; unsigned long long* rec_S; float* rec_sq;   // chunk records of the nested scheme (ld / 128 entries), lazily allocated
+    bool prequantised;           // the last extend already left integer weights + chunk records (fused epilogue)
     void* hist_state;            // [hist_cap][D][ld] Real
     int32_t* hist_anc;           // [hist_cap][ld]
     size_t hist_cap;

@@ -121,7 +121,7 @@ static int grid_for(size_t work_items, int per_block, int max_blocks) {
 
 // ---- extend dispatch ----------------------------------------------------------------------------------------
 template <class Model, typename Real>
-static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& obs, bool from_dev_obs, bool dev_t) {
+static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& obs, bool from_dev_obs, bool dev_t, bool nested = false) {
     ExtendArgs<Real> a;
     a.state_in = (const Real*)ps->state[ps->cur];
     a.state_out = (Real*)ps->state[mode == EXT_INIT || mode == EXT_ACCUM ? ps->cur : ps->cur ^ 1];
@@ -137,11 +137,24 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     a.partials = ps->partials;
     a.peer = ps->peer;
     a.cur = ps->cur;
+    a.rec = ChunkRecords{ps->rec_e, ps->rec_S, ps->rec_sq};
+    a.kbits = fixed_kbits(ps->n_global);
     if (mode == EXT_DYNAMIC) a.state_out = (Real*)ps->state[ps->cur ^ 1];
     if (mode == EXT_INIT) MPL_CUDA_OK(cudaMemsetAsync(ps->stats->max_bits, 0, sizeof(ps->stats->max_bits), ps->stream));
     const int grid = ps->grid_extend;
     {
         ScopedLaunch sl(ps, mode == EXT_INIT ? "init" : "extend");
+        if constexpr (sizeof(Real) == 4) {
+            if (nested && (mode == EXT_INIT || mode == EXT_GATHER)) {   // fused per-chunk quantisation (nested scheme, device-resident loop)
+                if (mode == EXT_INIT) pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false, true>, grid, kExtendThreads, ps->stream, a, model);
+                else if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, true, true>, grid, kExtendThreads, ps->stream, a, model);
+                else pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, false, true>, grid, kExtendThreads, ps->stream, a, model);
+                MPL_CUDA_OK(cudaGetLastError());
+                if (mode == EXT_GATHER) ps->cur ^= 1;
+                ps->prequantised = true;
+                goto extend_done;
+            }
+        }
         switch (mode) {
             case EXT_INIT: pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false>, grid, kExtendThreads, ps->stream, a, model); break;
             case EXT_ACCUM: pdl_launch(pf_extend_kernel<Model, Real, EXT_ACCUM, false>, grid, kExtendThreads, ps->stream, a, model); break;
@@ -157,6 +170,8 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (mode == EXT_GATHER || mode == EXT_DYNAMIC) ps->cur ^= 1;
+    ps->prequantised = false;
+extend_done:
     if (ps->hist_cap) {   // trajectory log: the state this step produced (kernel time index ps->t, not yet incremented by the caller)
         const size_t tt = (size_t)ps->t;
         if (tt < ps->hist_cap) {
@@ -169,14 +184,14 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     return MPL_OK;
 }
 
-static int launch_extend(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs, bool dev_t) {
+static int launch_extend(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs, bool dev_t, bool nested = false) {
     const mpl_model& m = ps->model;
     if (ps->dtype == MPL_F32) {
         switch (m.kind) {
-            case M_LGSSM4: return launch_extend_t<Lgssm4<float>, float>(ps, make_lgssm4<float>(m), mode, obs, from_dev_obs, dev_t);
-            case M_SPIRAL: return launch_extend_t<Spiral<float>, float>(ps, make_spiral<float>(m), mode, obs, from_dev_obs, dev_t);
-            case M_SV: return launch_extend_t<StochVol<float>, float>(ps, make_sv<float>(m), mode, obs, from_dev_obs, dev_t);
-            case M_HMM: return launch_extend_t<Hmm<float>, float>(ps, make_hmm<float>(m), mode, obs, from_dev_obs, dev_t);
+            case M_LGSSM4: return launch_extend_t<Lgssm4<float>, float>(ps, make_lgssm4<float>(m), mode, obs, from_dev_obs, dev_t, nested);
+            case M_SPIRAL: return launch_extend_t<Spiral<float>, float>(ps, make_spiral<float>(m), mode, obs, from_dev_obs, dev_t, nested);
+            case M_SV: return launch_extend_t<StochVol<float>, float>(ps, make_sv<float>(m), mode, obs, from_dev_obs, dev_t, nested);
+            case M_HMM: return launch_extend_t<Hmm<float>, float>(ps, make_hmm<float>(m), mode, obs, from_dev_obs, dev_t, nested);
         }
     } else {
         switch (m.kind) {
@@ -304,6 +319,45 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
 
 static int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream);
 
+static int ensure_chunk_records(mpl_ps* ps) {
+    if (ps->rec_e) return MPL_OK;
+    const size_t nch = ps->ld / kChunk;
+    MPL_CUDA_OK(cudaMalloc(&ps->rec_e, nch * sizeof(int)));
+    MPL_CUDA_OK(cudaMalloc(&ps->rec_S, nch * sizeof(unsigned long long)));
+    MPL_CUDA_OK(cudaMalloc(&ps->rec_sq, nch * sizeof(float)));
+    return MPL_OK;
+}
+
+template <typename Real>
+static int resample_nested_t(mpl_ps* ps) {
+    int rc = ensure_chunk_records(ps);
+    if (rc) return rc;
+    if (ps->world > 1 && (ps->n % kChunk)) return fail(MPL_ERR_UNSUPPORTED, "nested scheme, sharded: shard size must be a multiple of 128");
+    FixedArgs<Real> a = fixed_args<Real>(ps, false, false);
+    ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
+    const unsigned int num_tiles = (unsigned int)((ps->n + kScanTile - 1) / kScanTile);
+    const unsigned int num_chunks = (unsigned int)((ps->n + kChunk - 1) / kChunk);
+    if (!ps->prequantised) {
+        ScopedLaunch sl(ps, "nested_quantise");
+        pdl_launch(nested_quantise_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec);
+    }
+    {
+        ScopedLaunch sl(ps, "nested_chunk");
+        pdl_launch(nested_chunk_kernel<Real>, (num_tiles + 7) / 8, kScanThreads, ps->stream, a, rec, num_tiles, num_chunks);
+    }
+    {
+        ScopedLaunch sl(ps, "nested_scan");
+        pdl_launch(nested_scan_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec, num_tiles, num_chunks, (OverflowEntry2*)ps->overflow);
+    }
+    if (ps->world > 1) {   // the "ancestors written" flag for the peers rides on the (empty) overflow pass
+        ScopedLaunch sl(ps, "fixed_overflow");
+        pdl_launch(fixed_overflow2_kernel<Real, true>, kNumSMs * 2, kScanThreads, ps->stream, a, (const OverflowEntry2*)ps->overflow);
+    }
+    MPL_CUDA_OK(cudaGetLastError());
+    ps->prequantised = false;
+    return MPL_OK;
+}
+
 static int resample_exact(mpl_ps* ps, int scheme) {
     if (!ps->probs) {
         MPL_CUDA_OK(cudaMalloc(&ps->probs, ps->ld * sizeof(double)));
@@ -359,7 +413,7 @@ static int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double
 
 static int do_resample(mpl_ps* ps, int scheme) {
     if (!ps->initialised) return fail(MPL_ERR_INVALID, "resample before init_step");
-    if (ps->world > 1 && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED) return fail(MPL_ERR_UNSUPPORTED, "sharded particle systems support MPL_RESAMPLE_SYSTEMATIC_FIXED only");
+    if (ps->world > 1 && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED && scheme != MPL_RESAMPLE_SYSTEMATIC_NESTED) return fail(MPL_ERR_UNSUPPORTED, "sharded particle systems support the integer systematic schemes only");
     int rc = materialise(ps);   // resample twice in a row: apply the first one
     if (rc) return rc;
     const bool exact = scheme == MPL_RESAMPLE_MULTINOMIAL || scheme == MPL_RESAMPLE_SYSTEMATIC;
@@ -373,6 +427,9 @@ static int do_resample(mpl_ps* ps, int scheme) {
         case MPL_RESAMPLE_SYSTEMATIC_FIXED:
         case MPL_RESAMPLE_MULTINOMIAL_FIXED:
             rc = ps->dtype == MPL_F32 ? resample_fixed_t<float>(ps, scheme, false, false) : resample_fixed_t<double>(ps, scheme, false, false);
+            break;
+        case MPL_RESAMPLE_SYSTEMATIC_NESTED:
+            rc = ps->dtype == MPL_F32 ? resample_nested_t<float>(ps) : resample_nested_t<double>(ps);
             break;
         default: return fail(MPL_ERR_INVALID, "unknown resampling scheme");
     }
@@ -496,6 +553,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->D = model->state_dim;
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
     ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
+    ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = false;
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
@@ -550,6 +608,7 @@ extern "C" void mpl_ps_destroy(mpl_ps* ps) {
     cudaFree(ps->stats); cudaFreeHost(ps->stats_host); cudaFree(ps->partials); cudaFree(ps->ipartials);
     cudaFree(ps->sq_partials); if (ps->host_flags) cudaFreeHost(ps->host_flags);
     cudaFree(ps->hist_state); cudaFree(ps->hist_anc);
+    cudaFree(ps->rec_e); cudaFree(ps->rec_S); cudaFree(ps->rec_sq);
     if (ps->world > 1 && !ps->peer_virtual) mpl_ps_peer_detach(ps);
     cudaFree(ps->mailbox);
     cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
@@ -706,7 +765,8 @@ extern "C" int mpl_ps_history_enable(mpl_ps* ps, uint64_t max_steps) {
     if (ps->world > 1) return fail(MPL_ERR_UNSUPPORTED, "trajectory log: single GPU only");
     if (ps->initialised) return fail(MPL_ERR_INVALID, "enable the trajectory log before init_step");
     MPL_CUDA_OK(cudaSetDevice(ps->device));
-    cudaFree(ps->hist_state); cudaFree(ps->hist_anc); ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
+    cudaFree(ps->hist_state); cudaFree(ps->hist_anc);
+    cudaFree(ps->rec_e); cudaFree(ps->rec_S); cudaFree(ps->rec_sq); ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
     const size_t es = elem_size(ps);
     cudaError_t e = cudaMalloc(&ps->hist_state, (size_t)max_steps * ps->D * ps->ld * es);
     if (e == cudaSuccess) e = cudaMalloc(&ps->hist_anc, (size_t)max_steps * ps->ld * sizeof(int32_t));
@@ -779,10 +839,13 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
     if (first_step + n_steps > ps->obs_steps) return fail(MPL_ERR_INVALID, "run exceeds the uploaded observations");
     if (first_step > 0 && (long long)first_step != ps->t) return fail(MPL_ERR_INVALID, "first_step must equal the filter's current time index");
     const bool dynamic = ess_threshold > 0.;
+    int rc0 = MPL_OK;
     if (dynamic && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED) return fail(MPL_ERR_UNSUPPORTED, "ESS-triggered device loop: MPL_RESAMPLE_SYSTEMATIC_FIXED only");
     if (dynamic && first_step > 0 && !ps->dynamic_state_known) return fail(MPL_ERR_INVALID, "ESS-triggered run must start at step 0 or continue a previous ESS-triggered run");
     MPL_CUDA_OK(cudaSetDevice(ps->device));
     ps->ess_threshold_abs = dynamic ? ess_threshold * (double)ps->n_global : 0.;
+    const bool fuse_nested = !dynamic && scheme == MPL_RESAMPLE_SYSTEMATIC_NESTED && ps->dtype == MPL_F32 && !(ps->world > 1 && (ps->n % kChunk));
+    if (fuse_nested && (rc0 = ensure_chunk_records(ps))) return rc0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (elapsed_ms) { MPL_CUDA_OK(cudaEventCreate(&e0)); MPL_CUDA_OK(cudaEventCreate(&e1)); MPL_CUDA_OK(cudaEventRecord(e0, ps->stream)); }
     Obs dummy; std::memset(&dummy, 0, sizeof dummy);
@@ -791,14 +854,14 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
         size_t tt = first_step + k;
         if (tt == 0) {
             ps->t = 0; ps->pending_gather = false;
-            rc = launch_extend(ps, EXT_INIT, dummy, true, false);
+            rc = launch_extend(ps, EXT_INIT, dummy, true, false, fuse_nested);
             ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
         } else if (dynamic) {
             // whether the previous step resampled is only known on the device: the extend reads stats->resampled_flag[t & 1]
             rc = launch_extend(ps, EXT_DYNAMIC, dummy, true, false);
             ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
         } else {
-            rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false);
+            rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false, fuse_nested);
             ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
         }
         if (rc != MPL_OK) break;
@@ -926,7 +989,7 @@ extern "C" int mpl_logsumexp_stats(const void* lw, uint64_t n, int dtype, double
 extern "C" int mpl_fixed_resample(const float* lw, uint64_t n, int scheme, uint64_t rand_word_or_seed, uint32_t t, int32_t* anc, double* lse, uint64_t* total_weight) {
     // integer-weight resampling of injected f32 log-weights through a scratch particle system (D = 1)
     if (!lw || !anc || n == 0) return fail(MPL_ERR_INVALID, "bad argument");
-    if (scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED && scheme != MPL_RESAMPLE_MULTINOMIAL_FIXED) return fail(MPL_ERR_INVALID, "scheme must be a *_FIXED scheme");
+    if (scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED && scheme != MPL_RESAMPLE_MULTINOMIAL_FIXED && scheme != MPL_RESAMPLE_SYSTEMATIC_NESTED) return fail(MPL_ERR_INVALID, "scheme must be an integer-weight scheme");
     int rc = require_device();
     if (rc) return rc;
     double svp[3] = {0., 0.5, 1.};

@@ -16,6 +16,7 @@
 #include <type_traits>
 #include "common.cuh"
 #include "models.cuh"
+#include "nested_quant.cuh"
 
 namespace mpl {
 
@@ -162,11 +163,16 @@ struct ExtendArgs {
     Lse3<double>* partials;  // gridDim.x
     PeerTable peer;          // world == 1: single GPU
     int cur;                 // which state buffer is the input (index into peer.state)
+    ChunkRecords rec;        // NESTED: chunk records written by the fused quantisation epilogue
+    int kbits;
 };
 
 constexpr int kExtendThreads = 256;
 
-template <class Model, typename Real, int MODE, bool SHARDED = false>
+// NESTED (fp32 only): every warp iteration covers one aligned 128-particle chunk, whose log-weights are quantised on the
+// spot against the chunk's own maximum (nested.cuh) -- the integer weights replace the log-weights in HBM and the
+// reduce pass over the particles disappears.
+template <class Model, typename Real, int MODE, bool SHARDED = false, bool NESTED = false>
 __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs<Real> a, Model model) {
     constexpr int D = Model::D;
     constexpr int V = VecOf<Real>::N;
@@ -195,8 +201,8 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
     typedef typename std::conditional<V == 4, int4, int2>::type AncVec;
     size_t base = ((size_t)blockIdx.x * kExtendThreads + tid) * V;
     AncVec anc_next = AncVec();
-    if (gather && base < a.n) anc_next = __ldcs(reinterpret_cast<const AncVec*>(a.anc + base));
-    for (; base < a.n; base += stride) {
+    if (gather && base < a.ld) anc_next = __ldcs(reinterpret_cast<const AncVec*>(a.anc + base));
+    for (; base - (size_t)(tid & 31) * V < a.n; base += stride) {   // warp-uniform trip count (arrays are padded to ld)
         Real x[V][D];
         Real w[V];
         int32_t par[V];
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             // pull the parents' cache lines towards L2 so the dependent gather of the next iteration starts warm
             par[0] = anc_next.x; par[1] = anc_next.y;
             if constexpr (V == 4) { par[2] = anc_next.z; par[3] = anc_next.w; }
-            if (base + stride < a.n) anc_next = __ldcs(reinterpret_cast<const AncVec*>(a.anc + base + stride));   // last use of these ancestors
+            if (base + stride < a.ld) anc_next = __ldcs(reinterpret_cast<const AncVec*>(a.anc + base + stride));   // last use of these ancestors
             bool local = true;   // all parents in this shard (always, on one GPU; nearly always when sharded)
             if (sharded) {
 #pragma unroll
@@ -259,7 +265,21 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             for (int v = 0; v < V; ++v) tmp[v] = x[v][d];
             vec_store_stream<Real>(a.state_out + (size_t)d * a.ld + base, tmp);
         }
-        vec_store<Real>(a.lw + base, w);
+        if constexpr (NESTED) {
+            float wm[4], qv[4], sqc;
+#pragma unroll
+            for (int v = 0; v < V; ++v) wm[v] = (full || base + v < a.n) ? (float)w[v] : -INFINITY;
+            int e_c;
+            unsigned long long S_c;
+            warp_quantise_chunk(wm, a.kbits, qv, e_c, S_c, sqc);
+            Real qr[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) qr[v] = (Real)qv[v];
+            vec_store<Real>(a.lw + base, qr);
+            if ((tid & 31) == 0) { const size_t chunk = base / kChunk; a.rec.e[chunk] = e_c; a.rec.S[chunk] = S_c; a.rec.sq[chunk] = sqc; }
+        } else {
+            vec_store<Real>(a.lw + base, w);
+        }
 
         if (gather && base + stride < a.n && (unsigned int)anc_next.x - (unsigned int)a.gid_offset < (unsigned int)a.n) {
             const size_t nsrc = (size_t)((unsigned int)anc_next.x - (unsigned int)a.gid_offset);
@@ -908,3 +928,4 @@ static __global__ void __launch_bounds__(256) i32_to_i64_kernel(const int32_t* _
 }  // namespace mpl
 
 #include "scan2.cuh"
+#include "nested.cuh"

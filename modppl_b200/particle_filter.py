@@ -5,7 +5,7 @@ from . import _lib
 from ._lib import lib, check, check_handle, PfConfig
 
 F32, F64 = 0, 1
-MULTINOMIAL, SYSTEMATIC, SYSTEMATIC_FIXED, MULTINOMIAL_FIXED = 0, 1, 2, 3
+MULTINOMIAL, SYSTEMATIC, SYSTEMATIC_FIXED, MULTINOMIAL_FIXED, SYSTEMATIC_NESTED = 0, 1, 2, 3, 4
 _DTYPES = {"f32": F32, "f64": F64, F32: F32, F64: F64}
 
 

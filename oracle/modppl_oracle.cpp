@@ -353,6 +353,75 @@ extern "C" uint64_t mo_fixed_systematic(const float* lw, size_t n, uint64_t u64r
     return st.W;
 }
 
+namespace {
+inline uint64_t splitmix64_mix(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// #{ j in [0, n_out) : j*W + U < C*n_out }
+inline uint64_t slots_below(uint64_t C, uint64_t W, uint64_t U, uint64_t n_out) {
+    u128 lhs = (u128)C * n_out;
+    if (lhs <= (u128)U) return 0;
+    return (uint64_t)((lhs - U - 1) / W) + 1;
+}
+}  // namespace
+
+extern "C" uint64_t mo_nested_systematic(const float* lw, size_t n, uint64_t u64rand, int32_t* anc, double* lse_out) {
+    const size_t CH = 128;
+    const int kbits = mo_fixed_kbits(n);
+    const size_t nch = (n + CH - 1) / CH;
+    std::vector<uint64_t> q(n, 0), S(nch, 0);
+    std::vector<int> e(nch, 0);
+    std::vector<char> empty(nch, 1);
+    float M = -std::numeric_limits<float>::infinity();
+    for (size_t c = 0; c < nch; ++c) {
+        float Y = -std::numeric_limits<float>::infinity();
+        for (size_t i = c * CH; i < std::min(n, (c + 1) * CH); ++i) {
+            if (lw[i] == lw[i]) { float y = lw[i] * 1.44269504088896341f; if (y > Y) Y = y; if (lw[i] > M) M = lw[i]; }
+        }
+        if (!(Y > -std::numeric_limits<float>::infinity())) continue;
+        empty[c] = 0;
+        e[c] = (int)std::ceil(Y);
+        for (size_t i = c * CH; i < std::min(n, (c + 1) * CH); ++i) {
+            float y = lw[i] * 1.44269504088896341f;
+            float z = y - (float)e[c];
+            if (!(z > -126.0f)) z = -126.0f;              // also NaN, -inf
+            float nn = std::rint(z);
+            float f = z - nn;
+            float p = mo_exp2_poly(f);
+            float v = p * std::ldexp(1.0f, kbits + (int)nn);
+            q[i] = (uint64_t)std::llrint(v);
+            S[c] += q[i];
+        }
+    }
+    if (!(M > -std::numeric_limits<float>::infinity())) { if (lse_out) *lse_out = kNegInf; return 0; }
+    const int E = (int)std::ceil(M * 1.44269504088896341f);
+    std::vector<uint64_t> G(nch, 0);
+    uint64_t W = 0;
+    for (size_t c = 0; c < nch; ++c) { if (!empty[c] && E - e[c] < 64) G[c] = S[c] >> (E - e[c]); W += G[c]; }
+    if (lse_out) *lse_out = W ? (double)E * 0.6931471805599453 + std::log((double)W) - (double)kbits * 0.6931471805599453 : kNegInf;
+    if (W == 0) return 0;
+    const uint64_t U = mulhi64(u64rand, W);
+    uint64_t Gam = 0;
+    for (size_t c = 0; c < nch; ++c) {
+        const uint64_t a = slots_below(Gam, W, U, n);
+        Gam += G[c];
+        const uint64_t nc = slots_below(Gam, W, U, n) - a;
+        if (nc == 0) continue;
+        const uint64_t rc = splitmix64_mix(u64rand + (uint64_t)(c + 1) * 0x9E3779B97F4A7C15ull);
+        const uint64_t Uc = mulhi64(rc, S[c]);
+        uint64_t C = 0, prev = 0;
+        for (size_t i = c * CH; i < std::min(n, (c + 1) * CH); ++i) {
+            C += q[i];
+            const uint64_t cnt = slots_below(C, S[c], Uc, nc);
+            for (uint64_t l = prev; l < cnt; ++l) anc[a + l] = (int32_t)i;
+            prev = cnt;
+        }
+    }
+    return W;
+}
+
 extern "C" uint64_t mo_fixed_multinomial(const float* lw, size_t n, uint64_t seed, uint32_t t, int32_t* anc, double* lse_out) {
     std::vector<uint64_t> q;
     FixedStats st = fixed_quantize(lw, n, n, q);
@@ -591,10 +660,12 @@ template <typename Real> struct PS : mo_ps {
             std::vector<float> lwf(log_weights.begin(), log_weights.end());
             std::vector<int32_t> anc(num_particles);
             double lse; uint64_t W;
-            if (scheme == MO_RESAMPLE_SYSTEMATIC_FIXED) {
+            if (scheme == MO_RESAMPLE_SYSTEMATIC_FIXED || scheme == MO_RESAMPLE_SYSTEMATIC_NESTED) {
                 Stream s(seed, 0, rt, P_RESAMPLE_OFFSET);
                 uint32_t x[4]; s.block(0, x);
-                W = mo_fixed_systematic(lwf.data(), num_particles, ((uint64_t)x[0] << 32) | x[1], anc.data(), &lse);
+                const uint64_t word = ((uint64_t)x[0] << 32) | x[1];
+                W = scheme == MO_RESAMPLE_SYSTEMATIC_FIXED ? mo_fixed_systematic(lwf.data(), num_particles, word, anc.data(), &lse)
+                                                           : mo_nested_systematic(lwf.data(), num_particles, word, anc.data(), &lse);
             } else {
                 W = mo_fixed_multinomial(lwf.data(), num_particles, seed, rt, anc.data(), &lse);
             }

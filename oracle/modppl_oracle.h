@@ -59,6 +59,9 @@ int mo_fixed_kbits(uint64_t n_total);
 /* lw: float log-weights.  Returns total W; writes ancestors (systematic, offset word `u64rand`). */
 uint64_t mo_fixed_systematic(const float* lw, size_t n, uint64_t u64rand, int32_t* anc, double* lse_out);
 uint64_t mo_fixed_multinomial(const float* lw, size_t n, uint64_t seed, uint32_t t, int32_t* anc, double* lse_out);
+/* nested systematic on integer weights: weights quantised against the max of their own 128-particle chunk (power-of-two
+ * reference), chunks resampled systematically by their totals, particles systematically inside each chunk. */
+uint64_t mo_nested_systematic(const float* lw, size_t n, uint64_t u64rand, int32_t* anc, double* lse_out);
 
 /* ---- particle filter (inference/particle_filter.rs) -------------------------- */
 typedef struct mo_ps mo_ps;
@@ -68,6 +71,7 @@ typedef struct mo_ps mo_ps;
 #define MO_RESAMPLE_SYSTEMATIC 1         /* same cumsum convention, positions (u+i)/N */
 #define MO_RESAMPLE_SYSTEMATIC_FIXED 2   /* integer weights */
 #define MO_RESAMPLE_MULTINOMIAL_FIXED 3
+#define MO_RESAMPLE_SYSTEMATIC_NESTED 4
 mo_ps* mo_ps_new(const char* model, const double* params, size_t n_params, uint64_t num_particles,
                  int dtype, uint64_t seed, uint64_t gid_offset, uint64_t n_global);
 void mo_ps_free(mo_ps*);

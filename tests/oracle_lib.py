@@ -53,6 +53,7 @@ _f("mo_fixed_weight", C.c_uint64, C.c_float, C.c_int)
 _f("mo_fixed_kbits", C.c_int, C.c_uint64)
 _f("mo_fixed_systematic", C.c_uint64, fp, C.c_size_t, C.c_uint64, i32p, dp)
 _f("mo_fixed_multinomial", C.c_uint64, fp, C.c_size_t, C.c_uint64, C.c_uint32, i32p, dp)
+_f("mo_nested_systematic", C.c_uint64, fp, C.c_size_t, C.c_uint64, i32p, dp)
 _f("mo_ps_new", C.c_void_p, C.c_char_p, dp, C.c_size_t, C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64)
 _f("mo_ps_free", None, C.c_void_p)
 _f("mo_ps_init_step", C.c_int, C.c_void_p, dp, C.c_size_t)
@@ -158,6 +159,14 @@ def fixed_systematic(lw, rand_word):
     anc = np.empty(a.size, dtype=np.int32)
     lse = C.c_double()
     W = L.mo_fixed_systematic(a.ctypes.data_as(fp), a.size, rand_word, anc.ctypes.data_as(i32p), C.byref(lse))
+    return anc, lse.value, W
+
+
+def nested_systematic(lw, rand_word):
+    a = np.ascontiguousarray(lw, dtype=np.float32)
+    anc = np.empty(a.size, dtype=np.int32)
+    lse = C.c_double()
+    W = L.mo_nested_systematic(a.ctypes.data_as(fp), a.size, rand_word, anc.ctypes.data_as(i32p), C.byref(lse))
     return anc, lse.value, W
 
 

@@ -489,3 +489,81 @@ def test_virtual_shards_ragged_shard_size():
         if t + 1 < T:
             one.resample(m.SYSTEMATIC_FIXED)
     assert np.array_equal(st, one.traces) and np.array_equal(lw, one.log_weights)
+
+
+# ------------------------------------------------------------------------------------------------- nested systematic (scheme 4)
+@pytest.mark.parametrize("n", [1, 3, 127, 128, 129, 1000, 4096, 4097, 100000, (1 << 20) + 5])
+def test_nested_systematic_bit_exact(n):
+    rng = np.random.default_rng(50 + n)
+    cases = {
+        "normal": rng.normal(size=n) * 2,
+        "flat": np.zeros(n),
+        "peaked": np.where(np.arange(n) == n // 2, 0.0, -60.0),
+        "half_dead": np.where(rng.random(n) < 0.5, -np.inf, rng.normal(size=n)),
+        "heavy_tail": -np.abs(rng.standard_cauchy(size=n)) * 5,
+        "dead_chunks": np.where((np.arange(n) // 128) % 3 == 0, -np.inf, rng.normal(size=n) - 200.0),   # whole chunks without mass, large offset
+        "wide_range": rng.normal(size=n) * 30,                                                           # chunk maxima differ by many binades
+    }
+    for name, lw in cases.items():
+        lw = lw.astype(np.float32)
+        if not np.isfinite(lw).any():
+            lw[0] = 0.0
+        anc, lse, W = m.parity.fixed_resample(lw, scheme=4, seed=77, t=5)
+        ref_anc, ref_lse, ref_W = O.nested_systematic(lw, O.resample_offset_word(77, 5))
+        assert W == ref_W, name
+        assert np.array_equal(anc, ref_anc), (name, np.nonzero(anc != ref_anc)[0][:5])
+        assert abs(lse - ref_lse) <= 1e-12 * max(1.0, abs(ref_lse))
+
+
+def test_nested_systematic_full_size_properties():
+    n = 1 << 24
+    rng = np.random.default_rng(8)
+    lw = (rng.normal(size=n) * 1.5 - 40.0).astype(np.float32)
+    anc, lse, W = m.parity.fixed_resample(lw, scheme=4, seed=3, t=9)
+    assert np.all(np.diff(anc) >= 0) and anc[0] >= 0 and anc[-1] < n
+    w = np.exp(lw.astype(np.float64) - float(lw.max()))
+    counts = np.bincount(anc, minlength=n)
+    assert counts.sum() == n
+    assert np.all(np.abs(counts - n * w / w.sum()) < 2.0 + 1e-3)          # two systematic levels: within 2 of N w_i
+    assert abs(lse - (float(lw.max()) + math.log(w.sum()))) < 2e-5
+    lw2 = np.full(n, -80.0, dtype=np.float32)
+    lw2[12345678] = 0.0
+    anc2, _, _ = m.parity.fixed_resample(lw2, scheme=4, seed=3, t=9)
+    assert np.all(anc2 == 12345678)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_nested_inside_particle_system(dtype):
+    n = 3000
+    params, gen = MODELS["lgssm4"]
+    ys = gen(4)
+    ps = m.ParticleSystem(m.lgssm4(*params), n, seed=8, dtype=dtype)
+    ref = O.OraclePS("lgssm4", params, n, dtype=dtype, seed=8)
+    ps.init_step(ys[0]); ref.init_step(ys[0])
+    for t in range(1, 4):
+        ps.write_state(ref.traces); ps.write_log_weights(ref.log_weights)
+        lse, ref_lse = ps.resample(m.SYSTEMATIC_NESTED), ref.resample(4)
+        assert abs(lse - ref_lse) <= 2e-6 * max(1.0, abs(ref_lse))
+        assert np.array_equal(ps.parents, ref.parents)
+        assert np.array_equal(ps.traces, ref.traces)
+        ps.step(ys[t]); ref.step(ys[t])
+    assert abs(ps.log_marginal_likelihood_estimate() - ref.log_marginal_likelihood_estimate()) <= 1e-4
+
+
+def test_nested_fused_epilogue_equals_standalone_quantisation():
+    # device-resident loop (extend kernel quantises each 128-particle chunk in its epilogue) == call-per-step API
+    # (stand-alone quantisation kernel): same ancestors, same states, same log-ML, bit for bit
+    T, n = 12, (1 << 16) + 384
+    ys = lgssm_data(T)
+    a = m.ParticleSystem(m.lgssm4(), n, seed=3, dtype="f32")
+    a.upload_observations(ys)
+    a.run(0, T, m.SYSTEMATIC_NESTED)
+    b = m.ParticleSystem(m.lgssm4(), n, seed=3, dtype="f32")
+    b.init_step(ys[0]); b.resample(m.SYSTEMATIC_NESTED)
+    for y in ys[1:]:
+        b.step(y); b.resample(m.SYSTEMATIC_NESTED)
+    assert a.log_marginal_likelihood_estimate() == b.log_marginal_likelihood_estimate()
+    assert np.array_equal(a.parents, b.parents)
+    assert np.array_equal(a.traces, b.traces)
+    truth = O.kalman_lml_lgssm4(0.1, 0.5, 1.0, ys)
+    assert abs(a.log_marginal_likelihood_estimate() - truth) < 1.0
