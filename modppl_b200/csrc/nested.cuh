@@ -16,6 +16,20 @@
 namespace mpl {
 
 constexpr int kChunksPerTile = kScanTile / kChunk;   // 32
+constexpr int kTilesPerChunkBlock = 32;              // tiles summarised by one block of the chunk pass (one warp scan)
+
+// level-1 prefixes: the exclusive prefix of a tile's chunk masses is blk[tile / 32] + tile_pre[tile]
+struct NestedPrefixes {
+    unsigned long long* tile_pre;   // exclusive prefix of the tile inside its 32-tile block
+    unsigned long long* blk;        // block totals, turned into exclusive prefixes by the last block of the chunk pass
+    double* blk_sq;                 // per-block sums of squared weights at the global scale (ESS)
+};
+
+// warp-wide sum of per-lane values below 2^48: two integer redux instructions instead of ten 32-bit shuffles
+__device__ __forceinline__ unsigned long long warp_sum_u48(unsigned long long v) {
+    const unsigned int lo = (unsigned int)v & 0xFFFFFFu, hi = (unsigned int)(v >> 24);
+    return ((unsigned long long)__reduce_add_sync(0xffffffffu, hi) << 24) + (unsigned long long)__reduce_add_sync(0xffffffffu, lo);
+}
 
 // ---- stand-alone quantisation pass (call-per-step API; the device-resident loop fuses this into the extend kernel) -----
 template <typename Real>
@@ -51,69 +65,76 @@ __device__ __forceinline__ unsigned long long nested_chunk_mass(int e_c, unsigne
     return s < 64 ? (S_c >> s) : 0ull;
 }
 
-// ---- chunk pass: per-tile sums of the chunk masses at the global scale, then (last block) exclusive tile prefixes + W ----
-// one warp per tile (32 chunks, one per lane)
+// ---- chunk pass: chunk masses at the global scale -> tile sums -> (per block) tile prefixes + block total; the last block
+// turns the block totals into prefixes and publishes W.  One warp per 4 tiles (32 chunks of a tile <-> the 32 lanes).
 template <typename Real>
-__global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Real> a, ChunkRecords rec, unsigned int num_tiles, unsigned int num_chunks) {
+__global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
+                                                                    unsigned int num_chunks) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ unsigned long long ts[kTilesPerChunkBlock];
+    __shared__ double tsq[kTilesPerChunkBlock];
     __shared__ unsigned long long ws[kScanThreads / 32];
     __shared__ double wsq[kScanThreads / 32];
     __shared__ unsigned long long carry_s;
     __shared__ bool is_last;
     pdl_wait();
+    pdl_trigger();   // the expansion kernel may become resident now: it loads its weights while this grid runs
+    constexpr int kTilesPerWarp = kTilesPerChunkBlock / (kScanThreads / 32);
+    const unsigned int tile0 = blockIdx.x * kTilesPerChunkBlock + warp * kTilesPerWarp;
+    int e[kTilesPerWarp];
+    unsigned long long S[kTilesPerWarp];
+    float sqf[kTilesPerWarp];
+#pragma unroll
+    for (int i = 0; i < kTilesPerWarp; ++i) {
+        const unsigned int c = (tile0 + i) * kChunksPerTile + lane;
+        const bool valid = c < num_chunks;
+        e[i] = valid ? rec.e[c] : kChunkEmpty;
+        S[i] = valid ? rec.S[c] : 0ull;
+        sqf[i] = valid ? rec.sq[c] : 0.f;
+    }
     gate_stats(a.peer, a.stats, a.epoch < 0 ? a.stats->t : a.epoch);
     const int E = nested_global_exp(fixed_max<Real>(a));
-    const unsigned int tile = blockIdx.x * (kScanThreads / 32) + warp;
-    if (tile < num_tiles) {
-        const unsigned int c = tile * kChunksPerTile + lane;
-        unsigned long long g = 0;
-        double sq = 0.;
-        if (c < num_chunks) {
-            const int e_c = rec.e[c];
-            g = nested_chunk_mass(e_c, rec.S[c], E);
-            if (e_c != kChunkEmpty && E - e_c < 500) sq = (double)rec.sq[c] * exp2(-2. * (double)(E - e_c));
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { g += __shfl_xor_sync(0xffffffffu, g, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
-        if (lane == 0) { a.desc[tile] = g; a.sq_partials[tile] = sq; }
+    for (int i = 0; i < kTilesPerWarp; ++i) {
+        unsigned long long g = nested_chunk_mass(e[i], S[i], E);
+        double sq = 0.;
+        if (e[i] != kChunkEmpty && E - e[i] < 500) sq = (double)sqf[i] * exp2(-2. * (double)(E - e[i]));
+        g = warp_sum_u48(g);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) { ts[warp * kTilesPerWarp + i] = g; tsq[warp * kTilesPerWarp + i] = sq; }
     }
-    pdl_trigger();
     __syncthreads();
-    if (tid == 0) {
-        __threadfence();
-        is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
-        carry_s = 0ull;
+    if (warp == 0) {
+        const unsigned long long v = ts[lane];
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        double sq = tsq[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const unsigned int tile = blockIdx.x * kTilesPerChunkBlock + lane;
+        if (tile < num_tiles) nb.tile_pre[tile] = incl - v;
+        if (lane == 31) {
+            nb.blk[blockIdx.x] = incl; nb.blk_sq[blockIdx.x] = sq;
+            __threadfence();
+            is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
+            carry_s = 0ull;
+        }
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (a.peer.world > 1) {   // the shard total first (every rank is waiting for it), then the prefix scan
-        unsigned long long tot = 0;
-        double sq0 = 0.;
-        for (unsigned int i = tid; i < num_tiles; i += kScanThreads) { tot += a.desc[i]; sq0 += a.sq_partials[i]; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, o); sq0 += __shfl_xor_sync(0xffffffffu, sq0, o); }
-        __syncthreads();
-        if (lane == 0) { ws[warp] = tot; wsq[warp] = sq0; }
-        __syncthreads();
-        if (tid == 0) {
-            unsigned long long b = 0;
-            double sq = 0.;
-            for (int i = 0; i < kScanThreads / 32; ++i) { b += ws[i]; sq += wsq[i]; }
-            const long long epoch = a.epoch < 0 ? a.stats->t : a.epoch;
-            a.stats->trace[5] = global_ns();
-            for (int h = 0; h < a.peer.world; ++h) {
-                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], b, (unsigned int)epoch);
-                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank] + 2, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
-            }
-        }
-        __syncthreads();
-    }
-    for (unsigned int base = 0; base < num_tiles; base += kScanThreads * 4) {   // exclusive scan of the tile sums, in place
+    const unsigned int nblk = gridDim.x;
+    double sqt = 0.;
+    for (unsigned int base = 0; base < nblk; base += kScanThreads * 4) {   // exclusive scan of the block totals, in place
         unsigned long long v[4], tot = 0;
         const unsigned int first = base + tid * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v[i] = (first + i < num_tiles) ? a.desc[first + i] : 0ull; tot += v[i]; }
+        for (int i = 0; i < 4; ++i) {
+            v[i] = (first + i < nblk) ? __ldcg(nb.blk + first + i) : 0ull; tot += v[i];
+            if (first + i < nblk) sqt += __ldcg(nb.blk_sq + first + i);
+        }
         unsigned long long incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
@@ -124,16 +145,13 @@ __global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Re
 #pragma unroll
         for (int w = 0; w < kScanThreads / 32; ++w) { unsigned long long x = ws[w]; if (w < warp) pre += x; all += x; }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { if (first + i < num_tiles) a.desc[first + i] = pre; pre += v[i]; }
+        for (int i = 0; i < 4; ++i) { if (first + i < nblk) nb.blk[first + i] = pre; pre += v[i]; }
         __syncthreads();
         if (tid == 0) carry_s += all;
         __syncthreads();
     }
-    double sqt = 0.;
-    for (unsigned int i = tid; i < num_tiles; i += kScanThreads) sqt += a.sq_partials[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sqt += __shfl_xor_sync(0xffffffffu, sqt, o);
-    __syncthreads();
     if (lane == 0) wsq[warp] = sqt;
     __syncthreads();
     if (tid == 0) {
@@ -141,53 +159,85 @@ __global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Re
         st->overflow_count = 0; st->blocks_done = 0;
         double sq = 0.;
         for (int i = 0; i < kScanThreads / 32; ++i) sq += wsq[i];
+        const unsigned long long tot = carry_s;
         if (a.peer.world <= 1) {
-            st->W = carry_s; st->c_offset = 0;
+            st->W = tot; st->c_offset = 0;
             st->sumexp2 = sq;
-            st->ess = sq > 0. ? ((double)carry_s * (double)carry_s) / sq : 0.;
+            st->ess = sq > 0. ? ((double)tot * (double)tot) / sq : 0.;
+        } else {   // the shard's total mass and squared sum go to every rank (the expansion kernel's gate adds them up)
+            const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+            st->trace[5] = global_ns();
+            for (int h = 0; h < a.peer.world; ++h) {
+                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], tot, (unsigned int)epoch);
+                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank] + 2, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
+            }
         }
     }
 }
 
-// ---- expansion: one block per tile, one warp per 4 chunks --------------------------------------------------------------------
+// ---- expansion: one block per tile, one warp per 4 chunks; no block barrier ---------------------------------------------------
 template <typename Real>
-__global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, unsigned int num_tiles, unsigned int num_chunks,
-                                                                      OverflowEntry2* overflow) {
-    __shared__ Scan2Shared sh;
+__global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
+                                                                      unsigned int num_chunks) {
+    __shared__ __align__(16) unsigned short head[kScanThreads / 32][kWarpChunk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x;
+    // The integer weights and chunk records come from the kernel BEFORE the chunk pass, and this grid is only released once
+    // every block of the chunk pass is past its own dependency wait -- so they are complete and visible already: load them
+    // (and do the warp-local scans) before waiting for the chunk pass' prefixes.
+    const size_t wt_base = (size_t)tile * kScanTile + (size_t)warp * kWarpTile;
+    // integer weights stay in their float form (exact: at most 24 significant bits) to keep registers free
+    float qf[4][4];
+    unsigned long long excl[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const size_t idx = wt_base + (size_t)r * kChunk + (size_t)lane * 4;
+        if (idx < a.n) {   // (chunks are quantised whole: entries past n inside the last chunk hold 0)
+            if constexpr (sizeof(Real) == 4) {
+                float4 v = __ldcs(reinterpret_cast<const float4*>(a.lw + idx));   // last use
+                qf[r][0] = v.x; qf[r][1] = v.y; qf[r][2] = v.z; qf[r][3] = v.w;
+            } else {
+                double2 u = *reinterpret_cast<const double2*>(a.lw + idx), v = *reinterpret_cast<const double2*>(a.lw + idx + 2);
+                qf[r][0] = (float)u.x; qf[r][1] = (float)u.y; qf[r][2] = (float)v.x; qf[r][3] = (float)v.y;
+            }
+        } else { qf[r][0] = qf[r][1] = qf[r][2] = qf[r][3] = 0.f; }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {   // exclusive prefix of the lane's 4 particles inside chunk r
+        const unsigned long long own = __float2ull_rz(qf[r][0]) + __float2ull_rz(qf[r][1]) + __float2ull_rz(qf[r][2]) + __float2ull_rz(qf[r][3]);
+        unsigned long long inc = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+        excl[r] = inc - own;
+    }
+    const unsigned int c_l = tile * kChunksPerTile + lane;   // level 1: lane l <-> chunk l of the tile
+    unsigned long long S_l = 0;
+    int e_l = kChunkEmpty;
+    if (c_l < num_chunks) { S_l = rec.S[c_l]; e_l = rec.e[c_l]; }
     pdl_wait();
     const long long epoch = a.epoch < 0 ? st->t : a.epoch;
     gate_weights(a.peer, st, epoch, 0, 0.);
     const unsigned long long W = st->W;
-    const float mx = fixed_max<Real>(a);
     if (W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors, flagged
         for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
         if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1; }
-        if (tid == 0) a.desc[tile] = 0ull;
         return;
     }
-    const int E = nested_global_exp(mx);
+    const int E = nested_global_exp(fixed_max<Real>(a));
     const double inv_w = 1. / (double)W;
     const unsigned long long word = resample_rand_word(a.seed, a.rt, st);
     // every warp derives the tile's exact slot base itself
     const unsigned long long U = __umul64hi(word, W);
-    const TileBase base = tile_base_exact(st->c_offset + a.desc[tile], W, U, a.n_out, inv_w);
-    __syncthreads();                      // every warp has read the tile prefix ...
-    if (tid == 0) a.desc[tile] = 0ull;    // ... so it can be cleared for a later single-level reduce pass (which accumulates)
-    // level 1: masses of the tile's 32 chunks (lane l <-> chunk l), exclusive prefix, slot offsets of the chunk boundaries
-    const unsigned int c_l = tile * kChunksPerTile + lane;
-    unsigned long long g = 0, S_l = 0;
-    if (c_l < num_chunks) { S_l = rec.S[c_l]; g = nested_chunk_mass(rec.e[c_l], S_l, E); }
-    unsigned long long gi = g;
+    const TileBase base = tile_base_exact(st->c_offset + nb.blk[tile / kTilesPerChunkBlock] + nb.tile_pre[tile], W, U, a.n_out, inv_w);
+    // masses of the tile's 32 chunks, inclusive prefix, slot offsets of the chunk boundaries
+    unsigned long long gi = nested_chunk_mass(e_l, S_l, E);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, gi, o); if (lane >= o) gi += up; }
     const double rem_d = (double)base.rem, n_out_d = (double)a.n_out;
     const unsigned int slot_end_l = local_count(gi, base.rem, rem_d, W, n_out_d, a.n_out, inv_w);        // slots of the tile up to and including chunk l
     unsigned int slot_beg_l = __shfl_up_sync(0xffffffffu, slot_end_l, 1);
     if (lane == 0) slot_beg_l = 0;
-    __syncwarp();
     if (tile == 0 && tid == 0) {   // scalar bookkeeping of resample(): particle_filter.rs:104-105,114
         double lse = (double)E * 0.6931471805599453 + log((double)W) - (double)a.kbits * 0.6931471805599453;
         st->lse = lse;
@@ -200,9 +250,6 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
     }
     pdl_trigger();
     // this warp's 4 chunks: 4*warp .. 4*warp + 3  (round r of the lane's 16 particles == chunk 4*warp + r)
-    const size_t wt_base = (size_t)tile * kScanTile + (size_t)warp * kWarpTile;
-    unsigned long long q[4][4], incl[4], own[4], tot[4];
-    warp_tile_load_scan<Real, true>(a, wt_base, mx, q, incl, own, tot);
     unsigned int n[4][4];
     const unsigned int ws = __shfl_sync(0xffffffffu, slot_beg_l, 4 * warp);
 #pragma unroll
@@ -220,24 +267,21 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
         const unsigned long long U_c = __umul64hi(splitmix64_mix(word + (chunk_gid + 1ull) * 0x9E3779B97F4A7C15ull), S_c);
         const unsigned long long rem_c = S_c - U_c - 1ull;
         const double inv_s = 1. / (double)S_c, rem_cd = (double)rem_c, n_cd = (double)n_c;
-        unsigned long long C = incl[r] - own[r];
+        unsigned long long C = excl[r];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            C += q[r][j];
+            C += __float2ull_rz(qf[r][j]);
             n[r][j] = cb + local_count(C, rem_c, rem_cd, S_c, n_cd, (unsigned long long)n_c, inv_s);
         }
     }
     const unsigned int we = __shfl_sync(0xffffffffu, n[3][3], 31);
     const unsigned int total = we - ws;
     if (total == 0u) return;
-    if (total > kWarpHeavyCap) {
-        if (lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
-        // heavy warp tiles are expanded by the owning warp alone in this scheme (no whole-grid pass yet)
-    }
-    (void)overflow;
+    if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
+    // (heavy warp tiles are expanded by the owning warp alone in this scheme)
     const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile + warp * kWarpTile) - 1;
     for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kWarpChunk)
-        warp_expand_chunk<Real>(a, sh.head[warp], n, ws, total, chunk_lo, base.n_start + ws, src0);
+        warp_expand_chunk<Real>(a, head[warp], n, ws, total, chunk_lo, base.n_start + ws, src0);
 }
 
 }  // namespace mpl

@@ -20,6 +20,15 @@ __device__ __forceinline__ unsigned long long splitmix64_mix(unsigned long long 
     return z ^ (z >> 31);
 }
 
+// warp-wide maximum of non-NaN floats: one redux on the order-preserving integer image
+__device__ __forceinline__ float warp_max_f32(float v) {
+    int i = __float_as_int(v);
+    i ^= (i >> 31) & 0x7fffffff;
+    i = __reduce_max_sync(0xffffffffu, i);
+    i ^= (i >> 31) & 0x7fffffff;
+    return __int_as_float(i);
+}
+
 // integer weight of one particle against the chunk reference 2^e_c; y = lw * log2(e) already multiplied
 __device__ __forceinline__ unsigned long long nested_weight(float y, float e_c, int kbits, float* qf) {
     float z = fmaxf(__fsub_rn(y, e_c), -126.0f);            // fmaxf(NaN, x) = x; below -126 the weight rounds to 0
@@ -40,8 +49,7 @@ __device__ __forceinline__ void warp_quantise_chunk(const float (&w)[4], int kbi
     float y[4], ymax = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 4; ++j) { y[j] = __fmul_rn(w[j], 1.44269504088896341f); ymax = fmaxf(ymax, y[j]); }   // fmaxf skips NaN
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    ymax = warp_max_f32(ymax);
     if (!(ymax > -INFINITY)) {   // no finite weight in the chunk
         e_c = kChunkEmpty; S_c = 0ull; sq_c = 0.f;
 #pragma unroll
@@ -60,9 +68,11 @@ __device__ __forceinline__ void warp_quantise_chunk(const float (&w)[4], int kbi
         s += q;
         sq = fmaf(qf, qf, sq);
     }
+    // the lane's sum is below 2^42 (4 weights of at most 2^40): two integer redux instructions give the exact chunk sum
+    S_c = ((unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned int)(s >> 24)) << 24) + (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned int)s & 0xFFFFFFu);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
-    S_c = s; sq_c = sq;
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    sq_c = sq;
 }
 
 

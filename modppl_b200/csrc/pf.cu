@@ -325,6 +325,10 @@ static int ensure_chunk_records(mpl_ps* ps) {
     MPL_CUDA_OK(cudaMalloc(&ps->rec_e, nch * sizeof(int)));
     MPL_CUDA_OK(cudaMalloc(&ps->rec_S, nch * sizeof(unsigned long long)));
     MPL_CUDA_OK(cudaMalloc(&ps->rec_sq, nch * sizeof(float)));
+    const size_t ntile = ps->ld / kScanTile, nblk = (ntile + kTilesPerChunkBlock - 1) / kTilesPerChunkBlock;
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_tile_pre, nblk * kTilesPerChunkBlock * sizeof(unsigned long long)));
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_blk, nblk * sizeof(unsigned long long)));
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_blk_sq, nblk * sizeof(double)));
     return MPL_OK;
 }
 
@@ -335,6 +339,7 @@ static int resample_nested_t(mpl_ps* ps) {
     if (ps->world > 1 && (ps->n % kChunk)) return fail(MPL_ERR_UNSUPPORTED, "nested scheme, sharded: shard size must be a multiple of 128");
     FixedArgs<Real> a = fixed_args<Real>(ps, false, false);
     ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
+    NestedPrefixes nb{ps->nest_tile_pre, ps->nest_blk, ps->nest_blk_sq};
     const unsigned int num_tiles = (unsigned int)((ps->n + kScanTile - 1) / kScanTile);
     const unsigned int num_chunks = (unsigned int)((ps->n + kChunk - 1) / kChunk);
     if (!ps->prequantised) {
@@ -343,11 +348,11 @@ static int resample_nested_t(mpl_ps* ps) {
     }
     {
         ScopedLaunch sl(ps, "nested_chunk");
-        pdl_launch(nested_chunk_kernel<Real>, (num_tiles + 7) / 8, kScanThreads, ps->stream, a, rec, num_tiles, num_chunks);
+        pdl_launch(nested_chunk_kernel<Real>, (num_tiles + kTilesPerChunkBlock - 1) / kTilesPerChunkBlock, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
     }
     {
         ScopedLaunch sl(ps, "nested_scan");
-        pdl_launch(nested_scan_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec, num_tiles, num_chunks, (OverflowEntry2*)ps->overflow);
+        pdl_launch(nested_scan_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
     }
     if (ps->world > 1) {   // the "ancestors written" flag for the peers rides on the (empty) overflow pass
         ScopedLaunch sl(ps, "fixed_overflow");
@@ -554,6 +559,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
     ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
     ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = false;
+    ps->nest_tile_pre = nullptr; ps->nest_blk = nullptr; ps->nest_blk_sq = nullptr;
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
@@ -608,7 +614,7 @@ extern "C" void mpl_ps_destroy(mpl_ps* ps) {
     cudaFree(ps->stats); cudaFreeHost(ps->stats_host); cudaFree(ps->partials); cudaFree(ps->ipartials);
     cudaFree(ps->sq_partials); if (ps->host_flags) cudaFreeHost(ps->host_flags);
     cudaFree(ps->hist_state); cudaFree(ps->hist_anc);
-    cudaFree(ps->rec_e); cudaFree(ps->rec_S); cudaFree(ps->rec_sq);
+    cudaFree(ps->rec_e); cudaFree(ps->rec_S); cudaFree(ps->rec_sq); cudaFree(ps->nest_tile_pre); cudaFree(ps->nest_blk); cudaFree(ps->nest_blk_sq);
     if (ps->world > 1 && !ps->peer_virtual) mpl_ps_peer_detach(ps);
     cudaFree(ps->mailbox);
     cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
@@ -766,7 +772,7 @@ extern "C" int mpl_ps_history_enable(mpl_ps* ps, uint64_t max_steps) {
     if (ps->initialised) return fail(MPL_ERR_INVALID, "enable the trajectory log before init_step");
     MPL_CUDA_OK(cudaSetDevice(ps->device));
     cudaFree(ps->hist_state); cudaFree(ps->hist_anc);
-    cudaFree(ps->rec_e); cudaFree(ps->rec_S); cudaFree(ps->rec_sq); ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
+    ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
     const size_t es = elem_size(ps);
     cudaError_t e = cudaMalloc(&ps->hist_state, (size_t)max_steps * ps->D * ps->ld * es);
     if (e == cudaSuccess) e = cudaMalloc(&ps->hist_anc, (size_t)max_steps * ps->ld * sizeof(int32_t));
