@@ -88,6 +88,9 @@ int mpl_ps_init_step(mpl_ps*, const double* obs, size_t n_obs);                 
 int mpl_ps_step(mpl_ps*, const double* obs, size_t n_obs);                                          /* step        :73-95  */
 int mpl_ps_effective_sample_size(mpl_ps*, int stale_like_reference, double* out);                   /* ESS         :98-100 */
 int mpl_ps_resample(mpl_ps*, int scheme, double* log_total_weight);                                 /* resample    :103-116; log_total_weight may be NULL (no host sync) */
+/* step() then resample() -- the body of the reference's filtering loop (tests/smc.rs:78-81) -- as ONE call: same results as
+ * the two calls; with MPL_RESAMPLE_SYSTEMATIC_NESTED on fp32 the extend kernel quantises the weights in its epilogue */
+int mpl_ps_step_resample(mpl_ps*, const double* obs, size_t n_obs, int scheme, double* log_total_weight);
 int mpl_ps_log_marginal_likelihood_estimate(mpl_ps*, double* out);                                  /* lml         :119-121 */
 int mpl_ps_read(mpl_ps*, int what, void* host_dst, size_t bytes);                                   /* `pub traces` :13     */
 int mpl_ps_write(mpl_ps*, int what, const void* host_src, size_t bytes);                            /* parity hook: inject state / log-weights */
@@ -167,6 +170,10 @@ int mpl_ps_trace(mpl_ps*, long long* out16);   /* device time stamps (ns) of the
  * double[D * n_global] (SoA), log-weights double[n_global] and the log-ML estimate. */
 int mpl_test_virtual_shards(const mpl_model*, uint64_t n_global, int world, int dtype, uint64_t seed, const double* obs,
                             size_t n_steps, size_t n_obs, double* state_out, double* lw_out, double* lml_out, double* loop_ms);
+/* same, with the resampling scheme chosen: MPL_RESAMPLE_SYSTEMATIC_FIXED or MPL_RESAMPLE_SYSTEMATIC_NESTED (shards of
+ * whole 2^17-particle sections) */
+int mpl_test_virtual_shards_scheme(const mpl_model*, uint64_t n_global, int world, int dtype, uint64_t seed, int scheme, const double* obs,
+                                   size_t n_steps, size_t n_obs, double* state_out, double* lw_out, double* lml_out, double* loop_ms);
 
 #ifdef __cplusplus
 }

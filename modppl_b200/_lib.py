@@ -64,6 +64,7 @@ SYMBOLS = {
     "mpl_ps_step": (C.c_int, C.c_void_p, c_double_p, C.c_size_t),
     "mpl_ps_effective_sample_size": (C.c_int, C.c_void_p, C.c_int, c_double_p),
     "mpl_ps_resample": (C.c_int, C.c_void_p, C.c_int, c_double_p),
+    "mpl_ps_step_resample": (C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_int, c_double_p),
     "mpl_ps_log_marginal_likelihood_estimate": (C.c_int, C.c_void_p, c_double_p),
     "mpl_ps_read": (C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t),
     "mpl_ps_write": (C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t),
@@ -98,6 +99,7 @@ SYMBOLS = {
     "mpl_ps_peer_error": (C.c_int, C.c_void_p, C.POINTER(C.c_int)),
     "mpl_ps_trace": (C.c_int, C.c_void_p, C.POINTER(C.c_longlong)),
     "mpl_test_virtual_shards": (C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, c_double_p, C.c_size_t, C.c_size_t, c_double_p, c_double_p, c_double_p, c_double_p),
+    "mpl_test_virtual_shards_scheme": (C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int, c_double_p, C.c_size_t, C.c_size_t, c_double_p, c_double_p, c_double_p, c_double_p),
 }
 for _name, _s in SYMBOLS.items():
     _sig(_name, _s[0], *_s[1:])

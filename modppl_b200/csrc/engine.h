@@ -62,7 +62,7 @@ struct mpl_ps {
     // trajectory reconstruction (reference keeps traces[i].retv as a Vec<State>, dynunfold.rs:91-92): optional log of the
     // per-step states and ancestors, back-traced on demand
     int* rec_e; unsigned long long* rec_S; float* rec_sq;   // chunk records of the nested scheme (ld / 128 entries), lazily allocated
-    unsigned long long* nest_tile_pre; unsigned long long* nest_blk; double* nest_blk_sq;   // nested scheme: tile prefixes inside a 32-tile block, block prefixes
+    unsigned long long* nest_tile_pre; unsigned long long* nest_sec; void* nest_slots;   // nested scheme: tile prefixes inside a section; section records + top-level prefixes
     bool prequantised;           // the last extend already left integer weights + chunk records (fused epilogue)
     void* hist_state;            // [hist_cap][D][ld] Real
     int32_t* hist_anc;           // [hist_cap][ld]
@@ -83,7 +83,8 @@ struct mpl_ps {
 
 namespace mpl {
 // step phases, callable separately so that shards emulated on one GPU can be advanced phase by phase
-int ps_phase_extend(mpl_ps* ps, bool init);
+int ps_phase_extend(mpl_ps* ps, bool init, bool fuse_nested = false);
+int ps_phase_nested(mpl_ps* ps, int phase);
 int ps_phase_reduce(mpl_ps* ps);
 int ps_phase_scan(mpl_ps* ps);
 }

@@ -6,6 +6,7 @@
 //   (4) parents that live in another shard      -> remote loads in the next extend's fused gather,
 // with step-numbered flags that the consuming kernels spin on locally.  The caller only has to all-gather one
 // MPL_PEER_BLOB_BYTES blob per rank once (bench.py does it with torch.distributed).
+#include <cstddef>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -119,10 +120,8 @@ extern "C" int mpl_ps_peer_error(mpl_ps* ps, int* out) {
     if (!ps || !out) return fail(MPL_ERR_INVALID, "null argument");
     *out = 0;
     if (!ps->mailbox) return MPL_OK;
-    Mailbox h;
     MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
-    MPL_CUDA_OK(cudaMemcpy(&h, ps->mailbox, sizeof h, cudaMemcpyDeviceToHost));
-    *out = h.error;
+    MPL_CUDA_OK(cudaMemcpy(out, (const char*)ps->mailbox + offsetof(Mailbox, error), sizeof(int), cudaMemcpyDeviceToHost));
     return MPL_OK;
 }
 
@@ -133,6 +132,14 @@ extern "C" int mpl_ps_peer_error(mpl_ps* ps, int* out) {
 // The kernels executed are exactly the multi-GPU ones (remote loads/stores become local ones).
 extern "C" int mpl_test_virtual_shards(const mpl_model* model, uint64_t n_global, int world, int dtype, uint64_t seed, const double* obs, size_t n_steps,
                                        size_t n_obs, double* state_out, double* lw_out, double* lml_out, double* loop_ms) {
+    return mpl_test_virtual_shards_scheme(model, n_global, world, dtype, seed, MPL_RESAMPLE_SYSTEMATIC_FIXED, obs, n_steps, n_obs, state_out, lw_out, lml_out, loop_ms);
+}
+
+extern "C" int mpl_test_virtual_shards_scheme(const mpl_model* model, uint64_t n_global, int world, int dtype, uint64_t seed, int scheme, const double* obs,
+                                              size_t n_steps, size_t n_obs, double* state_out, double* lw_out, double* lml_out, double* loop_ms) {
+    if (scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED && scheme != MPL_RESAMPLE_SYSTEMATIC_NESTED) return fail(MPL_ERR_INVALID, "scheme: single-level or nested systematic");
+    const bool nested = scheme == MPL_RESAMPLE_SYSTEMATIC_NESTED;
+    const bool fuse = nested && dtype == MPL_F32;   // the extend kernel quantises in its epilogue, like mpl_ps_run
     // runs init, resample, then (n_steps - 1) x (step, resample) except that the last step is NOT followed by a
     // resample; returns the final state [D * n_global], log-weights [n_global] and the log-ML estimate.
     if (!model || !obs || n_steps < 1 || world < 1 || world > kMaxPeers || n_global % world) return fail(MPL_ERR_INVALID, "bad argument");
@@ -158,10 +165,11 @@ extern "C" int mpl_test_virtual_shards(const mpl_model* model, uint64_t n_global
     }
     auto wall0 = std::chrono::steady_clock::now();
     for (size_t t = 0; t < n_steps && rc == MPL_OK; ++t) {
-        for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = ps_phase_extend(sh[g], t == 0); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
-        if (t + 1 == n_steps) break;
-        for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = ps_phase_reduce(sh[g]); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
-        for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = ps_phase_scan(sh[g]); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
+        const bool last = t + 1 == n_steps;   // (the last step keeps its log-weights: no fused quantisation)
+        for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = ps_phase_extend(sh[g], t == 0, fuse && !last); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
+        if (last) break;
+        for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = nested ? ps_phase_nested(sh[g], 1) : ps_phase_reduce(sh[g]); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
+        for (int g = 0; g < world && rc == MPL_OK; ++g) { rc = nested ? ps_phase_nested(sh[g], 2) : ps_phase_scan(sh[g]); if (rc == MPL_OK) rc = mpl_ps_sync(sh[g]); }
     }
     if (loop_ms) *loop_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     const int D = model->state_dim;

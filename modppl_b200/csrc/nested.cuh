@@ -1,28 +1,41 @@
 // nested.cuh -- nested systematic resampling on integer weights (MPL_RESAMPLE_SYSTEMATIC_NESTED).
 //
 // The single-level integer scheme quantises every weight against the GLOBAL maximum, so a whole pass over the
-// log-weights (the reduce pass) has to wait for that maximum before it can even start.  Here every 128-particle chunk
-// (one warp iteration of the extend kernel) is quantised against a power of two just above its OWN maximum:
-//     e_c = ceil(max_i lw_i * log2 e),   q_i = rint(2^(lw_i log2 e - e_c) * 2^k),   S_c = sum q_i          (chunk c)
-// which needs nothing global and therefore fuses into the extend kernel's epilogue.  Globally only the chunk records
-// (e_c, S_c) are reduced -- 1/128 of the data:
-//     E = max e_c,   G_c = S_c >> (E - e_c),   W = sum G_c
-// Level 1 resamples chunks systematically by G_c (slot j at j*W + U): chunk c gets n_c consecutive slots.  Level 2
-// places those n_c slots systematically inside the chunk by q_i (local slot l at l*S_c + U_c).  Both levels are exact
-// integer arithmetic, unbiased (E[#offspring of i] = N q_i 2^(e_c - E) / W up to the floor in G_c), and independent of
-// thread order and of how the particles are sharded (chunks are aligned groups of global ids).
+// log-weights (the reduce pass) has to wait for that maximum -- on several GPUs, for an exchange -- before it can even
+// start.  Here nothing is ever scaled against a global quantity until only a handful of numbers is left:
+//   chunk c   (128 particles, one warp iteration of the extend kernel):
+//       e_c = ceil(max_i lw_i * log2 e),   q_i = rint(2^(lw_i log2 e - e_c) * 2^k),   S_c = sum q_i
+//     -> needs nothing outside the warp, fuses into the extend kernel's epilogue
+//   section s (2^17 particles = 1024 chunks, one block of the chunk pass):
+//       E_s = max e_c,   G_c = S_c >> (E_s - e_c),   T_s = sum G_c
+//   top       (at most 2048 sections; across GPUs: the ONLY exchange, one record per section):
+//       E = max E_s,   M_s = T_s >> (E - E_s),   W = sum M_s
+// Resampling runs the exact integer systematic scheme three times: the N output slots over the sections by M_s (slot j
+// at j*W + U), a section's n_s slots over its chunks by G_c (local slot l at l*T_s + U_s), a chunk's n_c slots over its
+// particles by q_i (l*S_c + U_c); U_s and U_c are hashed from the step's random word and the section / chunk number.
+// All of it is integer arithmetic: unbiased up to the floors (relative 2^-k), independent of thread order and of how
+// the particles are sharded (sections are aligned groups of global ids).
 #pragma once
 
 namespace mpl {
 
 constexpr int kChunksPerTile = kScanTile / kChunk;   // 32
-constexpr int kTilesPerChunkBlock = 32;              // tiles summarised by one block of the chunk pass (one warp scan)
+constexpr int kTilesPerSection = 32;                 // one block of the chunk pass (one warp scan over its tile sums)
+constexpr size_t kSection = (size_t)kTilesPerSection * kScanTile;   // 2^17 particles
 
-// level-1 prefixes: the exclusive prefix of a tile's chunk masses is blk[tile / 32] + tile_pre[tile]
 struct NestedPrefixes {
-    unsigned long long* tile_pre;   // exclusive prefix of the tile inside its 32-tile block
-    unsigned long long* blk;        // block totals, turned into exclusive prefixes by the last block of the chunk pass
-    double* blk_sq;                 // per-block sums of squared weights at the global scale (ESS)
+    unsigned long long* tile_pre;   // [local tile] exclusive prefix of the tile's chunk masses inside its section (scale E_s)
+    int* sec_E;                     // [GLOBAL section] E_s (kChunkEmpty: no finite weight)
+    unsigned long long* sec_T;      // [GLOBAL section] T_s
+    double* sec_sq;                 // [GLOBAL section] sum of squared integer weights at scale E_s (ESS)
+    unsigned long long* sec_pre;    // [GLOBAL section] exclusive prefix of M_s                       (top-level pass)
+    unsigned long long* sec_M;      // [GLOBAL section] M_s
+    unsigned long long* sec_a;      // [GLOBAL section] first output slot of the section                (top-level pass)
+    unsigned long long* sec_n;      // [GLOBAL section] number of output slots of the section
+    uint2* slots;                   // [local chunk] (first global output slot, number of slots)          (level-1 pass)
+    unsigned int sec0;              // global number of this shard's first section
+    unsigned int n_sec;             // sections of this shard
+    unsigned int n_sec_global;
 };
 
 // warp-wide sum of per-lane values below 2^48: two integer redux instructions instead of ten 32-bit shuffles
@@ -58,32 +71,111 @@ __global__ void __launch_bounds__(kScanThreads) nested_quantise_kernel(FixedArgs
     pdl_trigger();
 }
 
-__device__ __forceinline__ int nested_global_exp(float mx) { return (int)ceilf(__fmul_rn(mx, 1.44269504088896341f)); }
-__device__ __forceinline__ unsigned long long nested_chunk_mass(int e_c, unsigned long long S_c, int E) {
-    if (e_c == kChunkEmpty) return 0ull;
-    const int s = E - e_c;
-    return s < 64 ? (S_c >> s) : 0ull;
+__device__ __forceinline__ unsigned long long nested_shift(unsigned long long S, int e, int E) {   // S >> (E - e), e <= E
+    if (e == kChunkEmpty) return 0ull;
+    const int sft = E - e;
+    return sft < 64 ? (S >> sft) : 0ull;
+}
+__device__ __forceinline__ unsigned long long nested_section_offset(unsigned long long word, unsigned long long section, unsigned long long T_s) {
+    return __umul64hi(splitmix64_mix((word ^ 0x5851F42D4C957F2Dull) + (section + 1ull) * 0xD1B54A32D192ED03ull), T_s);
+}
+__device__ __forceinline__ unsigned long long nested_chunk_offset(unsigned long long word, unsigned long long chunk, unsigned long long S_c) {
+    return __umul64hi(splitmix64_mix(word + (chunk + 1ull) * 0x9E3779B97F4A7C15ull), S_c);
 }
 
-// ---- chunk pass: chunk masses at the global scale -> tile sums -> (per block) tile prefixes + block total; the last block
-// turns the block totals into prefixes and publishes W.  One warp per 4 tiles (32 chunks of a tile <-> the 32 lanes).
+struct NestedTopShared {
+    int wmax[kScanThreads / 32];
+    unsigned long long ws[kScanThreads / 32];
+    double wsq[kScanThreads / 32];
+    unsigned long long carry;
+};
+
+// Top level, by one whole block: E, M_s, their exclusive prefixes, W and the ESS from the section records.
+__device__ __forceinline__ void nested_top_level(const NestedPrefixes& nb, DeviceStats* st, NestedTopShared& sh, uint64_t seed, long long rt,
+                                                 unsigned long long n_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int n_sec = nb.n_sec_global;
+    int emax = kChunkEmpty;
+    for (unsigned int i = tid; i < n_sec; i += kScanThreads) emax = max(emax, __ldcg(nb.sec_E + i));
+    emax = __reduce_max_sync(0xffffffffu, emax);
+    if (lane == 0) sh.wmax[warp] = emax;
+    if (tid == 0) sh.carry = 0ull;
+    __syncthreads();
+    int E = kChunkEmpty;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) E = max(E, sh.wmax[w]);
+    double sqt = 0.;
+    for (unsigned int base = 0; base < n_sec; base += kScanThreads * 4) {
+        unsigned long long v[4], tot = 0;
+        const unsigned int first = base + tid * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i] = 0ull;
+            if (first + i < n_sec) {
+                const int e_s = __ldcg(nb.sec_E + first + i);
+                v[i] = nested_shift(__ldcg(nb.sec_T + first + i), e_s, E);
+                if (e_s != kChunkEmpty && E - e_s < 500) sqt += __ldcg(nb.sec_sq + first + i) * exp2(-2. * (double)(E - e_s));
+            }
+            tot += v[i];
+        }
+        unsigned long long incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        __syncthreads();
+        if (lane == 31) sh.ws[warp] = incl;
+        __syncthreads();
+        unsigned long long pre = sh.carry + incl - tot, all = 0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) { unsigned long long x = sh.ws[w]; if (w < warp) pre += x; all += x; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { if (first + i < n_sec) { nb.sec_pre[first + i] = pre; nb.sec_M[first + i] = v[i]; } pre += v[i]; }
+        __syncthreads();
+        if (tid == 0) sh.carry += all;
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sqt += __shfl_xor_sync(0xffffffffu, sqt, o);
+    if (lane == 0) sh.wsq[warp] = sqt;
+    __syncthreads();
+    const unsigned long long W = sh.carry;
+    const unsigned long long word = resample_rand_word(seed, rt, st);
+    if (tid == 0) {
+        double sq = 0.;
+        for (int i = 0; i < kScanThreads / 32; ++i) sq += sh.wsq[i];
+        st->W = W; st->c_offset = 0; st->nest_E = E; st->rand_word = word;
+        st->sumexp2 = sq;
+        st->ess = sq > 0. ? ((double)W * (double)W) / sq : 0.;
+    }
+    if (W == 0ull) return;
+    // level 0: slot j sits at j*W + U; section s owns the slots [a_s, a_s + n_s)
+    const unsigned long long U = __umul64hi(word, W);
+    const double inv_w = 1. / (double)W;
+    for (unsigned int i = tid; i < n_sec; i += kScanThreads) {
+        const TileBase sb = tile_base_exact(nb.sec_pre[i], W, U, n_out, inv_w);
+        nb.sec_a[i] = sb.n_start;
+        nb.sec_n[i] = local_count(nb.sec_M[i], sb.rem, (double)sb.rem, W, (double)n_out, n_out, inv_w);
+    }
+}
+
+// ---- chunk pass: one block per section.  Section scale, chunk masses, tile sums and their prefixes inside the section,
+// the section record; the last block runs the top level (one GPU) or nothing more (several: the records were already sent).
 template <typename Real>
 __global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
                                                                     unsigned int num_chunks) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ unsigned long long ts[kTilesPerChunkBlock];
-    __shared__ double tsq[kTilesPerChunkBlock];
-    __shared__ unsigned long long ws[kScanThreads / 32];
-    __shared__ double wsq[kScanThreads / 32];
-    __shared__ unsigned long long carry_s;
+    __shared__ unsigned long long ts[kTilesPerSection];
+    __shared__ double tsq[kTilesPerSection];
+    __shared__ int wmax[kScanThreads / 32];
+    __shared__ NestedTopShared top;
     __shared__ bool is_last;
     pdl_wait();
     pdl_trigger();   // the expansion kernel may become resident now: it loads its weights while this grid runs
-    constexpr int kTilesPerWarp = kTilesPerChunkBlock / (kScanThreads / 32);
-    const unsigned int tile0 = blockIdx.x * kTilesPerChunkBlock + warp * kTilesPerWarp;
+    constexpr int kTilesPerWarp = kTilesPerSection / (kScanThreads / 32);
+    const unsigned int tile0 = blockIdx.x * kTilesPerSection + warp * kTilesPerWarp;
     int e[kTilesPerWarp];
     unsigned long long S[kTilesPerWarp];
     float sqf[kTilesPerWarp];
+    int emax = kChunkEmpty;
 #pragma unroll
     for (int i = 0; i < kTilesPerWarp; ++i) {
         const unsigned int c = (tile0 + i) * kChunksPerTile + lane;
@@ -91,20 +183,26 @@ __global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Re
         e[i] = valid ? rec.e[c] : kChunkEmpty;
         S[i] = valid ? rec.S[c] : 0ull;
         sqf[i] = valid ? rec.sq[c] : 0.f;
+        emax = max(emax, e[i]);
     }
-    gate_stats(a.peer, a.stats, a.epoch < 0 ? a.stats->t : a.epoch);
-    const int E = nested_global_exp(fixed_max<Real>(a));
+    emax = __reduce_max_sync(0xffffffffu, emax);
+    if (lane == 0) wmax[warp] = emax;
+    __syncthreads();
+    int E_s = kChunkEmpty;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) E_s = max(E_s, wmax[w]);
 #pragma unroll
     for (int i = 0; i < kTilesPerWarp; ++i) {
-        unsigned long long g = nested_chunk_mass(e[i], S[i], E);
+        unsigned long long g = nested_shift(S[i], e[i], E_s);
         double sq = 0.;
-        if (e[i] != kChunkEmpty && E - e[i] < 500) sq = (double)sqf[i] * exp2(-2. * (double)(E - e[i]));
+        if (e[i] != kChunkEmpty && E_s - e[i] < 500) sq = (double)sqf[i] * exp2(-2. * (double)(E_s - e[i]));
         g = warp_sum_u48(g);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         if (lane == 0) { ts[warp * kTilesPerWarp + i] = g; tsq[warp * kTilesPerWarp + i] = sq; }
     }
     __syncthreads();
+    const unsigned int sg = nb.sec0 + blockIdx.x;   // global section number
     if (warp == 0) {
         const unsigned long long v = ts[lane];
         unsigned long long incl = v;
@@ -113,69 +211,105 @@ __global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Re
         double sq = tsq[lane];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const unsigned int tile = blockIdx.x * kTilesPerChunkBlock + lane;
+        const unsigned int tile = blockIdx.x * kTilesPerSection + lane;
         if (tile < num_tiles) nb.tile_pre[tile] = incl - v;
+        const unsigned long long T_s = __shfl_sync(0xffffffffu, incl, 31);
+        if (a.peer.world > 1) {   // the section record goes to every other rank right away (three tagged words each)
+            const long long epoch = a.epoch < 0 ? a.stats->t : a.epoch;
+            if (lane < a.peer.world && lane != a.peer.rank) {
+                unsigned long long* dst = a.peer.mail[lane]->sec_ll[sg];
+                ll_write64(dst, (unsigned long long)(unsigned int)E_s, (unsigned int)epoch);
+                ll_write64(dst + 2, T_s, (unsigned int)epoch);
+                ll_write64(dst + 4, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
+            }
+        }
         if (lane == 31) {
-            nb.blk[blockIdx.x] = incl; nb.blk_sq[blockIdx.x] = sq;
+            nb.sec_E[sg] = E_s; nb.sec_T[sg] = T_s; nb.sec_sq[sg] = sq;
             __threadfence();
             is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
-            carry_s = 0ull;
         }
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const unsigned int nblk = gridDim.x;
-    double sqt = 0.;
-    for (unsigned int base = 0; base < nblk; base += kScanThreads * 4) {   // exclusive scan of the block totals, in place
-        unsigned long long v[4], tot = 0;
-        const unsigned int first = base + tid * 4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            v[i] = (first + i < nblk) ? __ldcg(nb.blk + first + i) : 0ull; tot += v[i];
-            if (first + i < nblk) sqt += __ldcg(nb.blk_sq + first + i);
-        }
-        unsigned long long incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
-        __syncthreads();
-        if (lane == 31) ws[warp] = incl;
-        __syncthreads();
-        unsigned long long pre = carry_s + incl - tot, all = 0;
-#pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) { unsigned long long x = ws[w]; if (w < warp) pre += x; all += x; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { if (first + i < nblk) nb.blk[first + i] = pre; pre += v[i]; }
-        __syncthreads();
-        if (tid == 0) carry_s += all;
-        __syncthreads();
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sqt += __shfl_xor_sync(0xffffffffu, sqt, o);
-    if (lane == 0) wsq[warp] = sqt;
-    __syncthreads();
-    if (tid == 0) {
-        DeviceStats* st = a.stats;
-        st->overflow_count = 0; st->blocks_done = 0;
-        double sq = 0.;
-        for (int i = 0; i < kScanThreads / 32; ++i) sq += wsq[i];
-        const unsigned long long tot = carry_s;
-        if (a.peer.world <= 1) {
-            st->W = tot; st->c_offset = 0;
-            st->sumexp2 = sq;
-            st->ess = sq > 0. ? ((double)tot * (double)tot) / sq : 0.;
-        } else {   // the shard's total mass and squared sum go to every rank (the expansion kernel's gate adds them up)
-            const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-            st->trace[5] = global_ns();
-            for (int h = 0; h < a.peer.world; ++h) {
-                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank], tot, (unsigned int)epoch);
-                ll_write64(a.peer.mail[h]->w_ll[a.peer.rank] + 2, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
-            }
-        }
-    }
+    if (tid == 0) { a.stats->overflow_count = 0; a.stats->blocks_done = 0; a.stats->trace[5] = global_ns(); }
+    if (a.peer.world <= 1) nested_top_level(nb, a.stats, top, a.seed, a.rt, a.n_out);
 }
 
-// ---- expansion: one block per tile, one warp per 4 chunks; no block barrier ---------------------------------------------------
+// several GPUs: block 0 of the expansion kernel collects every other shard's section records, runs the top level, and
+// releases the kernel's other blocks through the local ready word
+__device__ __forceinline__ void gate_sections(const PeerTable& p, DeviceStats* st, long long epoch, const NestedPrefixes& nb, NestedTopShared& top,
+                                              uint64_t seed, long long rt, unsigned long long n_out) {
+    if (p.world <= 1) return;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) st->trace[6] = global_ns();
+        Mailbox* mb = p.mail[p.rank];
+        SpinGuard g(p);
+        for (unsigned int sg = threadIdx.x; sg < nb.n_sec_global; sg += kScanThreads) {
+            if (sg - nb.sec0 < nb.n_sec) continue;   // own sections: already in place
+            nb.sec_E[sg] = (int)(unsigned int)ll_read64(&mb->sec_ll[sg][0], (unsigned int)epoch, g);
+            nb.sec_T[sg] = ll_read64(&mb->sec_ll[sg][2], (unsigned int)epoch, g);
+            nb.sec_sq[sg] = __longlong_as_double((long long)ll_read64(&mb->sec_ll[sg][4], (unsigned int)epoch, g));
+        }
+        __threadfence();
+        __syncthreads();
+        nested_top_level(nb, st, top, seed, rt, n_out);
+        __syncthreads();
+        if (threadIdx.x == 0) { st->trace[7] = global_ns(); local_ready_set(&st->ready_w, epoch); }
+    } else if (threadIdx.x == 0) local_ready_wait(&st->ready_w, epoch, p);
+    __syncthreads();
+}
+
+// ---- level-1 pass: one warp per tile (lane <-> chunk): the tile's first slot inside its section, then the slot range of
+// every chunk.  Several GPUs: block 0 first collects the other shards' section records and runs the top level.
+template <typename Real>
+__global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
+                                                                     unsigned int num_chunks) {
+    __shared__ NestedTopShared top;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DeviceStats* st = a.stats;
+    const unsigned int tile = blockIdx.x * (kScanThreads / 32) + warp;
+    const unsigned int c_l = tile * kChunksPerTile + lane;
+    unsigned long long S_l = 0;
+    int e_l = kChunkEmpty;
+    if (tile < num_tiles && c_l < num_chunks) { S_l = rec.S[c_l]; e_l = rec.e[c_l]; }   // (written two kernels ago: complete)
+    pdl_wait();
+    pdl_trigger();   // the expansion kernel may become resident and load its weights
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    gate_sections(a.peer, st, epoch, nb, top, a.seed, a.rt, a.n_out);
+    const unsigned long long W = st->W;
+    if (blockIdx.x == 0 && tid == 0) {   // scalar bookkeeping of resample(): particle_filter.rs:104-105,114
+        if (W == 0ull) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1; }
+        else {
+            double lse = (double)st->nest_E * 0.6931471805599453 + log((double)W) - (double)a.kbits * 0.6931471805599453;
+            st->lse = lse;
+            st->ess_stale = st->ess;
+            if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
+            st->resampled = 1;
+            st->resampled_flag[epoch & 1] = 1;
+            st->n_resamples += 1;
+            st->degenerate = 0;
+        }
+    }
+    if (tile >= num_tiles || W == 0ull) return;
+    const unsigned int sg = nb.sec0 + tile / kTilesPerSection;
+    const unsigned long long T_s = nb.sec_T[sg], n_s = nb.sec_n[sg];
+    uint2 out = make_uint2(0u, 0u);
+    if (n_s != 0ull && T_s != 0ull) {
+        const double inv_t = 1. / (double)T_s;
+        const TileBase base = tile_base_exact(nb.tile_pre[tile], T_s, nested_section_offset(st->rand_word, sg, T_s), n_s, inv_t);
+        unsigned long long gi = nested_shift(S_l, e_l, nb.sec_E[sg]);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, gi, o); if (lane >= o) gi += up; }
+        const unsigned int slot_end = local_count(gi, base.rem, (double)base.rem, T_s, (double)n_s, n_s, inv_t);   // slots of the tile up to and including chunk l
+        unsigned int slot_beg = __shfl_up_sync(0xffffffffu, slot_end, 1);
+        if (lane == 0) slot_beg = 0;
+        out = make_uint2((unsigned int)(nb.sec_a[sg] + base.n_start) + slot_beg, slot_end - slot_beg);
+    }
+    if (c_l < num_chunks) nb.slots[c_l] = out;
+}
+
+// ---- expansion (level 2): one block per tile, one warp per 4 chunks; warps never meet ---------------------------------------
 template <typename Real>
 __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
                                                                       unsigned int num_chunks) {
@@ -183,9 +317,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x;
-    // The integer weights and chunk records come from the kernel BEFORE the chunk pass, and this grid is only released once
-    // every block of the chunk pass is past its own dependency wait -- so they are complete and visible already: load them
-    // (and do the warp-local scans) before waiting for the chunk pass' prefixes.
+    // The integer weights and chunk records come from the kernel before the chunk pass, and this grid is only released once
+    // every block of the two small passes in between is past its own dependency wait -- so they are complete and visible
+    // already: load them (and do the warp-local scans) before waiting for the level-1 pass' slot ranges.
     const size_t wt_base = (size_t)tile * kScanTile + (size_t)warp * kWarpTile;
     // integer weights stay in their float form (exact: at most 24 significant bits) to keep registers free
     float qf[4][4];
@@ -211,61 +345,34 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
         for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
         excl[r] = inc - own;
     }
-    const unsigned int c_l = tile * kChunksPerTile + lane;   // level 1: lane l <-> chunk l of the tile
-    unsigned long long S_l = 0;
-    int e_l = kChunkEmpty;
-    if (c_l < num_chunks) { S_l = rec.S[c_l]; e_l = rec.e[c_l]; }
+    const unsigned int c_w = tile * kChunksPerTile + 4 * warp + (lane & 3);   // this warp's 4 chunks (lanes 0..3 hold them)
+    const unsigned long long S_w = c_w < num_chunks ? rec.S[c_w] : 0ull;
     pdl_wait();
-    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-    gate_weights(a.peer, st, epoch, 0, 0.);
-    const unsigned long long W = st->W;
-    if (W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors, flagged
+    pdl_trigger();
+    if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the level-1 pass)
         for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
-        if (tile == 0 && tid == 0) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1; }
         return;
     }
-    const int E = nested_global_exp(fixed_max<Real>(a));
-    const double inv_w = 1. / (double)W;
-    const unsigned long long word = resample_rand_word(a.seed, a.rt, st);
-    // every warp derives the tile's exact slot base itself
-    const unsigned long long U = __umul64hi(word, W);
-    const TileBase base = tile_base_exact(st->c_offset + nb.blk[tile / kTilesPerChunkBlock] + nb.tile_pre[tile], W, U, a.n_out, inv_w);
-    // masses of the tile's 32 chunks, inclusive prefix, slot offsets of the chunk boundaries
-    unsigned long long gi = nested_chunk_mass(e_l, S_l, E);
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, gi, o); if (lane >= o) gi += up; }
-    const double rem_d = (double)base.rem, n_out_d = (double)a.n_out;
-    const unsigned int slot_end_l = local_count(gi, base.rem, rem_d, W, n_out_d, a.n_out, inv_w);        // slots of the tile up to and including chunk l
-    unsigned int slot_beg_l = __shfl_up_sync(0xffffffffu, slot_end_l, 1);
-    if (lane == 0) slot_beg_l = 0;
-    if (tile == 0 && tid == 0) {   // scalar bookkeeping of resample(): particle_filter.rs:104-105,114
-        double lse = (double)E * 0.6931471805599453 + log((double)W) - (double)a.kbits * 0.6931471805599453;
-        st->lse = lse;
-        st->ess_stale = st->ess;
-        if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
-        st->resampled = 1;
-        st->resampled_flag[epoch & 1] = 1;
-        st->n_resamples += 1;
-        st->degenerate = 0;
-    }
-    pdl_trigger();
-    // this warp's 4 chunks: 4*warp .. 4*warp + 3  (round r of the lane's 16 particles == chunk 4*warp + r)
+    const unsigned long long word = st->rand_word;
+    const uint2 slot_w = c_w < num_chunks ? nb.slots[c_w] : make_uint2(0u, 0u);
+    // round r of the lane's 16 particles == chunk 4*warp + r
     unsigned int n[4][4];
-    const unsigned int ws = __shfl_sync(0xffffffffu, slot_beg_l, 4 * warp);
+    const unsigned int ws = __shfl_sync(0xffffffffu, slot_w.x, 0);
+    unsigned int we = ws;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const unsigned int cb = __shfl_sync(0xffffffffu, slot_beg_l, 4 * warp + r), ce = __shfl_sync(0xffffffffu, slot_end_l, 4 * warp + r);
-        const unsigned long long S_c = __shfl_sync(0xffffffffu, S_l, 4 * warp + r);
-        const unsigned int n_c = ce - cb;
+        const unsigned int n_c = __shfl_sync(0xffffffffu, slot_w.y, r);
+        const unsigned int cb = we - ws;   // chunks of a tile own consecutive slot ranges
+        const unsigned long long S_c = __shfl_sync(0xffffffffu, S_w, r);
         if (n_c == 0u || S_c == 0ull) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) n[r][j] = cb;
             continue;
         }
+        we += n_c;
         // level 2: local slot l sits at l*S_c + U_c; particle with inclusive chunk prefix C owns the slots below C*n_c
         const unsigned long long chunk_gid = ((unsigned long long)a.out_base / kChunk) + (unsigned long long)tile * kChunksPerTile + 4 * warp + r;
-        const unsigned long long U_c = __umul64hi(splitmix64_mix(word + (chunk_gid + 1ull) * 0x9E3779B97F4A7C15ull), S_c);
-        const unsigned long long rem_c = S_c - U_c - 1ull;
+        const unsigned long long rem_c = S_c - nested_chunk_offset(word, chunk_gid, S_c) - 1ull;
         const double inv_s = 1. / (double)S_c, rem_cd = (double)rem_c, n_cd = (double)n_c;
         unsigned long long C = excl[r];
 #pragma unroll
@@ -274,14 +381,25 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
             n[r][j] = cb + local_count(C, rem_c, rem_cd, S_c, n_cd, (unsigned long long)n_c, inv_s);
         }
     }
-    const unsigned int we = __shfl_sync(0xffffffffu, n[3][3], 31);
     const unsigned int total = we - ws;
     if (total == 0u) return;
     if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
     // (heavy warp tiles are expanded by the owning warp alone in this scheme)
     const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile + warp * kWarpTile) - 1;
+    // n[][] counts from 0 at the warp tile's first slot
     for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kWarpChunk)
-        warp_expand_chunk<Real>(a, head[warp], n, ws, total, chunk_lo, base.n_start + ws, src0);
+        warp_expand_chunk<Real>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
+}
+
+// several GPUs: tells every rank that this shard's expansion kernel has completed (all remote ancestor stores performed)
+static __global__ void peer_done_kernel(PeerTable peer, DeviceStats* st, long long epoch_arg) {
+    pdl_wait();
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        const long long epoch = epoch_arg < 0 ? st->t : epoch_arg;
+        st->trace[8] = global_ns();
+        for (int h = 0; h < peer.world; ++h) *(volatile long long*)&peer.mail[h]->flag_done[peer.rank] = epoch;
+    }
 }
 
 }  // namespace mpl

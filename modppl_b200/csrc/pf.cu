@@ -325,41 +325,53 @@ static int ensure_chunk_records(mpl_ps* ps) {
     MPL_CUDA_OK(cudaMalloc(&ps->rec_e, nch * sizeof(int)));
     MPL_CUDA_OK(cudaMalloc(&ps->rec_S, nch * sizeof(unsigned long long)));
     MPL_CUDA_OK(cudaMalloc(&ps->rec_sq, nch * sizeof(float)));
-    const size_t ntile = ps->ld / kScanTile, nblk = (ntile + kTilesPerChunkBlock - 1) / kTilesPerChunkBlock;
-    MPL_CUDA_OK(cudaMalloc(&ps->nest_tile_pre, nblk * kTilesPerChunkBlock * sizeof(unsigned long long)));
-    MPL_CUDA_OK(cudaMalloc(&ps->nest_blk, nblk * sizeof(unsigned long long)));
-    MPL_CUDA_OK(cudaMalloc(&ps->nest_blk_sq, nblk * sizeof(double)));
+    const size_t nsec = (ps->ld + kSection - 1) / kSection;
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_tile_pre, nsec * kTilesPerSection * sizeof(unsigned long long)));
+    // section records and top-level results of EVERY shard: [E int | T u64 | sq f64 | pre u64 | M u64 | a u64 | n u64] x kMaxSections
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_sec, (size_t)kMaxSections * 7 * sizeof(unsigned long long)));
+    MPL_CUDA_OK(cudaMemset(ps->nest_sec, 0, (size_t)kMaxSections * 7 * sizeof(unsigned long long)));
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_slots, nch * sizeof(uint2)));
     return MPL_OK;
 }
 
+// phases: 1 = quantise (unless the extend did it) + chunk pass, 2 = expansion (+ the peers' "done" flag); 3 = both
 template <typename Real>
-static int resample_nested_t(mpl_ps* ps) {
+static int resample_nested_t(mpl_ps* ps, int phases = 3) {
     int rc = ensure_chunk_records(ps);
     if (rc) return rc;
-    if (ps->world > 1 && (ps->n % kChunk)) return fail(MPL_ERR_UNSUPPORTED, "nested scheme, sharded: shard size must be a multiple of 128");
+    if (ps->world > 1 && ((ps->n % kSection) || (ps->gid_offset % kSection)))
+        return fail(MPL_ERR_UNSUPPORTED, "nested scheme, sharded: shards must be whole sections (multiples of 131072 particles)");
+    const size_t n_sec_global = (ps->n_global + kSection - 1) / kSection;
+    if (n_sec_global > (size_t)kMaxSections) return fail(MPL_ERR_UNSUPPORTED, "nested scheme: at most 2^28 particles");
     FixedArgs<Real> a = fixed_args<Real>(ps, false, false);
     ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
-    NestedPrefixes nb{ps->nest_tile_pre, ps->nest_blk, ps->nest_blk_sq};
+    unsigned long long* sec = ps->nest_sec;
+    NestedPrefixes nb{ps->nest_tile_pre, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
+                      sec + 5 * kMaxSections, sec + 6 * kMaxSections, (uint2*)ps->nest_slots, (unsigned int)(ps->gid_offset / kSection), (unsigned int)((ps->n + kSection - 1) / kSection), (unsigned int)n_sec_global};
     const unsigned int num_tiles = (unsigned int)((ps->n + kScanTile - 1) / kScanTile);
     const unsigned int num_chunks = (unsigned int)((ps->n + kChunk - 1) / kChunk);
-    if (!ps->prequantised) {
+    if ((phases & 1) && !ps->prequantised) {
         ScopedLaunch sl(ps, "nested_quantise");
         pdl_launch(nested_quantise_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec);
     }
-    {
+    if (phases & 1) {
         ScopedLaunch sl(ps, "nested_chunk");
-        pdl_launch(nested_chunk_kernel<Real>, (num_tiles + kTilesPerChunkBlock - 1) / kTilesPerChunkBlock, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
+        pdl_launch(nested_chunk_kernel<Real>, nb.n_sec, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
     }
-    {
+    if (phases & 2) {
+        ScopedLaunch sl(ps, "nested_level1");
+        pdl_launch(nested_level1_kernel<Real>, (num_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32), kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
+    }
+    if (phases & 2) {
         ScopedLaunch sl(ps, "nested_scan");
         pdl_launch(nested_scan_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
     }
-    if (ps->world > 1) {   // the "ancestors written" flag for the peers rides on the (empty) overflow pass
-        ScopedLaunch sl(ps, "fixed_overflow");
-        pdl_launch(fixed_overflow2_kernel<Real, true>, kNumSMs * 2, kScanThreads, ps->stream, a, (const OverflowEntry2*)ps->overflow);
+    if ((phases & 2) && ps->world > 1) {   // "every ancestor I owe is written", once the expansion kernel has completed
+        ScopedLaunch sl(ps, "peer_done");
+        pdl_launch(peer_done_kernel, 1, 32, ps->stream, a.peer, ps->stats, a.epoch);
     }
     MPL_CUDA_OK(cudaGetLastError());
-    ps->prequantised = false;
+    if (phases & 1) ps->prequantised = false;
     return MPL_OK;
 }
 
@@ -450,17 +462,23 @@ static int do_resample(mpl_ps* ps, int scheme) {
     return MPL_OK;
 }
 
-int ps_phase_extend(mpl_ps* ps, bool init) {
+int ps_phase_extend(mpl_ps* ps, bool init, bool fuse_nested) {
     Obs dummy; std::memset(&dummy, 0, sizeof dummy);
     int rc;
+    if (fuse_nested && (rc = ensure_chunk_records(ps))) return rc;
     if (init) {
         ps->t = 0; ps->pending_gather = false;
-        rc = launch_extend(ps, EXT_INIT, dummy, true, false);
+        rc = launch_extend(ps, EXT_INIT, dummy, true, false, fuse_nested);
         ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
     } else {
-        rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false);
+        rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false, fuse_nested);
         ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
     }
+    return rc;
+}
+int ps_phase_nested(mpl_ps* ps, int phase) {
+    int rc = ps->dtype == MPL_F32 ? resample_nested_t<float>(ps, phase) : resample_nested_t<double>(ps, phase);
+    if (rc == MPL_OK && phase == 2) { ps->pending_gather = true; ps->stats_valid = false; ps->max_valid = false; }
     return rc;
 }
 int ps_phase_reduce(mpl_ps* ps) {
@@ -559,7 +577,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
     ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
     ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = false;
-    ps->nest_tile_pre = nullptr; ps->nest_blk = nullptr; ps->nest_blk_sq = nullptr;
+    ps->nest_tile_pre = nullptr; ps->nest_sec = nullptr; ps->nest_slots = nullptr;
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
@@ -614,7 +632,7 @@ extern "C" void mpl_ps_destroy(mpl_ps* ps) {
     cudaFree(ps->stats); cudaFreeHost(ps->stats_host); cudaFree(ps->partials); cudaFree(ps->ipartials);
     cudaFree(ps->sq_partials); if (ps->host_flags) cudaFreeHost(ps->host_flags);
     cudaFree(ps->hist_state); cudaFree(ps->hist_anc);
-    cudaFree(ps->rec_e); cudaFree(ps->rec_S); cudaFree(ps->rec_sq); cudaFree(ps->nest_tile_pre); cudaFree(ps->nest_blk); cudaFree(ps->nest_blk_sq);
+    cudaFree(ps->rec_e); cudaFree(ps->rec_S); cudaFree(ps->rec_sq); cudaFree(ps->nest_tile_pre); cudaFree(ps->nest_sec); cudaFree(ps->nest_slots);
     if (ps->world > 1 && !ps->peer_virtual) mpl_ps_peer_detach(ps);
     cudaFree(ps->mailbox);
     cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
@@ -659,6 +677,25 @@ extern "C" int mpl_ps_step(mpl_ps* ps, const double* obs, size_t n_obs) {
     ps->pending_gather = false;
     ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
     return MPL_OK;
+}
+
+// step() immediately followed by resample(): the pair of calls of the reference's filtering loop (tests/smc.rs:78-81) as one,
+// which lets the extend kernel hand the resampler its weights already quantised (nested scheme, fp32)
+extern "C" int mpl_ps_step_resample(mpl_ps* ps, const double* obs, size_t n_obs, int scheme, double* log_total_weight) {
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    if (!ps->initialised) return fail(MPL_ERR_INVALID, "step before init_step");
+    Obs o;
+    int rc = pack_obs(ps, obs, n_obs, o);
+    if (rc) return rc;
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    const bool fuse = scheme == MPL_RESAMPLE_SYSTEMATIC_NESTED && ps->dtype == MPL_F32 && ps->pending_gather &&
+                      !(ps->world > 1 && (ps->n % kSection || ps->gid_offset % kSection));
+    if (fuse && (rc = ensure_chunk_records(ps))) return rc;
+    rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, o, false, false, fuse);
+    if (rc) return rc;
+    ps->pending_gather = false;
+    ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
+    return mpl_ps_resample(ps, scheme, log_total_weight);
 }
 
 extern "C" int mpl_ps_effective_sample_size(mpl_ps* ps, int stale_like_reference, double* out) {

@@ -48,6 +48,8 @@ struct DeviceStats {
     unsigned long long max_bits[2];   // exact max of the log-weights written by the extend of step t, slot t & 1 (order-preserving bits)
     long long ready_stats, ready_w, ready_done;
     long long trace[16];           // %globaltimer stamps of the last step's phases (sharded runs; mpl_ps_trace)
+    int nest_E;                    // nested scheme: the global power-of-two reference of this resample
+    int pad2;
 };
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
@@ -57,6 +59,7 @@ __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mo
 // on the data path: (max, sum exp, sum exp^2) after the extend, the integer weight total after the reduce pass, and a
 // "my ancestors are written" flag after the scan.
 constexpr int kMaxPeers = 8;
+constexpr int kMaxSections = 2048;   // nested scheme: sections of 2^17 particles, up to 2^28 particles in all
 struct Mailbox {
     // self-validating words (the trick of NCCL's LL protocol): every 8-byte word carries 32 payload bits and the 32-bit
     // step number, and an aligned 8-byte store is performed atomically -- so neither side needs a memory fence (a
@@ -66,6 +69,8 @@ struct Mailbox {
     long long flag_done[kMaxPeers];              // shard h has written every ancestor it owes for this step
     int error;
     int pad;
+    // nested scheme: (E_s, T_s, sum q^2) of every section of every shard, indexed by the GLOBAL section number
+    unsigned long long sec_ll[kMaxSections][6];
 };
 __device__ __forceinline__ void ll_write64(unsigned long long* dst2, unsigned long long value, unsigned int epoch) {
     *(volatile unsigned long long*)(dst2 + 0) = (value & 0xffffffffull) | ((unsigned long long)epoch << 32);

@@ -49,7 +49,7 @@ def logpdf(dist, x, params):
     return out.value
 
 
-def virtual_shards(model, n_global, world, obs, dtype="f32", seed=0):
+def virtual_shards(model, n_global, world, obs, dtype="f32", seed=0, scheme=2):
     """Shards emulated on one GPU (include/modppl_b200.h: mpl_test_virtual_shards) -> (state [D, N], log-weights [N], log-ML)."""
     ys = np.ascontiguousarray(np.asarray(obs, dtype=np.float64))
     ys = ys.reshape(ys.shape[0], -1)
@@ -57,7 +57,7 @@ def virtual_shards(model, n_global, world, obs, dtype="f32", seed=0):
     st = np.empty((D, n_global), dtype=np.float64)
     lw = np.empty(n_global, dtype=np.float64)
     lml, ms = C.c_double(), C.c_double()
-    check(lib.mpl_test_virtual_shards(model._h, n_global, world, 1 if dtype == "f64" else 0, seed, ys.ctypes.data_as(_lib.c_double_p), ys.shape[0], ys.shape[1],
+    check(lib.mpl_test_virtual_shards_scheme(model._h, n_global, world, 1 if dtype == "f64" else 0, seed, int(scheme), ys.ctypes.data_as(_lib.c_double_p), ys.shape[0], ys.shape[1],
                                       st.ctypes.data_as(_lib.c_double_p), lw.ctypes.data_as(_lib.c_double_p), C.byref(lml), C.byref(ms)))
     virtual_shards.last_loop_ms = ms.value
     return st, lw, lml.value

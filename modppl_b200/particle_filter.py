@@ -48,6 +48,15 @@ class ParticleSystem:
         check(lib.mpl_ps_resample(self._h, scheme, C.byref(out) if sync else None))
         return out.value if sync else None
 
+    def step_resample(self, constraints, scheme=MULTINOMIAL, sync=True):
+        """`filter = filter.step(..); filter.resample()` (tests/smc.rs:78-81) as one call: same results, and the nested scheme
+        on fp32 gets its weights quantised by the extend kernel."""
+        a, p, n = _obs(constraints)
+        out = C.c_double()
+        check(lib.mpl_ps_step_resample(self._h, p, n, scheme, C.byref(out) if sync else None))
+        self._steps_done = getattr(self, "_steps_done", 0) + 1
+        return out.value if sync else None
+
     def log_marginal_likelihood_estimate(self):            # :119-121
         out = C.c_double()
         check(lib.mpl_ps_log_marginal_likelihood_estimate(self._h, C.byref(out)))

@@ -367,18 +367,22 @@ inline uint64_t slots_below(uint64_t C, uint64_t W, uint64_t U, uint64_t n_out) 
 }
 }  // namespace
 
+// Nested systematic resampling on integer weights, three levels (section of 2^17 particles > chunk of 128 > particle);
+// restates modppl_b200/csrc/nested.cuh.  Every level is an exact systematic scheme on integers:
+//   chunk c:   e_c = ceil(max y), q_i = rint(2^(y_i - e_c + k)), S_c = sum q_i
+//   section s: E_s = max e_c, G_c = S_c >> (E_s - e_c), T_s = sum G_c
+//   top:       E = max E_s,  M_s = T_s >> (E - E_s),  W = sum M_s
 extern "C" uint64_t mo_nested_systematic(const float* lw, size_t n, uint64_t u64rand, int32_t* anc, double* lse_out) {
-    const size_t CH = 128;
+    const size_t CH = 128, SEC = (size_t)1 << 17, CPS = SEC / CH;
     const int kbits = mo_fixed_kbits(n);
-    const size_t nch = (n + CH - 1) / CH;
+    const size_t nch = (n + CH - 1) / CH, nsec = (n + SEC - 1) / SEC;
     std::vector<uint64_t> q(n, 0), S(nch, 0);
     std::vector<int> e(nch, 0);
     std::vector<char> empty(nch, 1);
-    float M = -std::numeric_limits<float>::infinity();
     for (size_t c = 0; c < nch; ++c) {
         float Y = -std::numeric_limits<float>::infinity();
         for (size_t i = c * CH; i < std::min(n, (c + 1) * CH); ++i) {
-            if (lw[i] == lw[i]) { float y = lw[i] * 1.44269504088896341f; if (y > Y) Y = y; if (lw[i] > M) M = lw[i]; }
+            if (lw[i] == lw[i]) { float y = lw[i] * 1.44269504088896341f; if (y > Y) Y = y; }
         }
         if (!(Y > -std::numeric_limits<float>::infinity())) continue;
         empty[c] = 0;
@@ -395,28 +399,45 @@ extern "C" uint64_t mo_nested_systematic(const float* lw, size_t n, uint64_t u64
             S[c] += q[i];
         }
     }
-    if (!(M > -std::numeric_limits<float>::infinity())) { if (lse_out) *lse_out = kNegInf; return 0; }
-    const int E = (int)std::ceil(M * 1.44269504088896341f);
-    std::vector<uint64_t> G(nch, 0);
+    std::vector<uint64_t> G(nch, 0), T(nsec, 0), M(nsec, 0);
+    std::vector<int> Es(nsec, 0);
+    std::vector<char> sec_empty(nsec, 1);
+    bool any = false;
+    int E = 0;
+    for (size_t s = 0; s < nsec; ++s) {
+        const size_t c0 = s * CPS, c1 = std::min(nch, (s + 1) * CPS);
+        for (size_t c = c0; c < c1; ++c) if (!empty[c] && (sec_empty[s] || e[c] > Es[s])) { Es[s] = e[c]; sec_empty[s] = 0; }
+        if (sec_empty[s]) continue;
+        for (size_t c = c0; c < c1; ++c) { if (!empty[c] && Es[s] - e[c] < 64) G[c] = S[c] >> (Es[s] - e[c]); T[s] += G[c]; }
+        if (!any || Es[s] > E) { E = Es[s]; any = true; }
+    }
+    if (!any) { if (lse_out) *lse_out = kNegInf; return 0; }
     uint64_t W = 0;
-    for (size_t c = 0; c < nch; ++c) { if (!empty[c] && E - e[c] < 64) G[c] = S[c] >> (E - e[c]); W += G[c]; }
+    for (size_t s = 0; s < nsec; ++s) { if (!sec_empty[s] && E - Es[s] < 64) M[s] = T[s] >> (E - Es[s]); W += M[s]; }
     if (lse_out) *lse_out = W ? (double)E * 0.6931471805599453 + std::log((double)W) - (double)kbits * 0.6931471805599453 : kNegInf;
     if (W == 0) return 0;
     const uint64_t U = mulhi64(u64rand, W);
-    uint64_t Gam = 0;
-    for (size_t c = 0; c < nch; ++c) {
-        const uint64_t a = slots_below(Gam, W, U, n);
-        Gam += G[c];
-        const uint64_t nc = slots_below(Gam, W, U, n) - a;
-        if (nc == 0) continue;
-        const uint64_t rc = splitmix64_mix(u64rand + (uint64_t)(c + 1) * 0x9E3779B97F4A7C15ull);
-        const uint64_t Uc = mulhi64(rc, S[c]);
-        uint64_t C = 0, prev = 0;
-        for (size_t i = c * CH; i < std::min(n, (c + 1) * CH); ++i) {
-            C += q[i];
-            const uint64_t cnt = slots_below(C, S[c], Uc, nc);
-            for (uint64_t l = prev; l < cnt; ++l) anc[a + l] = (int32_t)i;
-            prev = cnt;
+    uint64_t Mu = 0;
+    for (size_t s = 0; s < nsec; ++s) {
+        const uint64_t a_s = slots_below(Mu, W, U, n);
+        Mu += M[s];
+        const uint64_t n_s = slots_below(Mu, W, U, n) - a_s;
+        if (n_s == 0) continue;
+        const uint64_t Us = mulhi64(splitmix64_mix((u64rand ^ 0x5851F42D4C957F2Dull) + (uint64_t)(s + 1) * 0xD1B54A32D192ED03ull), T[s]);
+        uint64_t Gam = 0;
+        for (size_t c = s * CPS; c < std::min(nch, (s + 1) * CPS); ++c) {
+            const uint64_t a = slots_below(Gam, T[s], Us, n_s);
+            Gam += G[c];
+            const uint64_t nc = slots_below(Gam, T[s], Us, n_s) - a;
+            if (nc == 0) continue;
+            const uint64_t Uc = mulhi64(splitmix64_mix(u64rand + (uint64_t)(c + 1) * 0x9E3779B97F4A7C15ull), S[c]);
+            uint64_t C = 0, prev = 0;
+            for (size_t i = c * CH; i < std::min(n, (c + 1) * CH); ++i) {
+                C += q[i];
+                const uint64_t cnt = slots_below(C, S[c], Uc, nc);
+                for (uint64_t l = prev; l < cnt; ++l) anc[a_s + a + l] = (int32_t)i;
+                prev = cnt;
+            }
         }
     }
     return W;
