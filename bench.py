@@ -167,7 +167,7 @@ def run_ours(args):
     steps_prof = min(K, T - ps2_first)
     for k in range(steps_prof):
         ps.step(ys[ps2_first + k]); ps.resample(scheme, sync=False)
-    prof = {k: ps.profile_get(k) for k in ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "fixed_cumsum", "fixed_search", "nested_quantise", "nested_chunk", "nested_level1", "nested_scan")}
+    prof = {k: ps.profile_get(k) for k in ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "fixed_cumsum", "fixed_search", "nested_quantise", "nested_sections", "nested_level1", "nested_scan")}
     ps.profile_enable(False)
     peak, peak_src = measured_peak()
     ext_ms = prof["extend"][0] / max(1, prof["extend"][1])

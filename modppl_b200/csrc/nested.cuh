@@ -83,6 +83,9 @@ __device__ __forceinline__ unsigned long long nested_chunk_offset(unsigned long 
     return __umul64hi(splitmix64_mix(word + (chunk + 1ull) * 0x9E3779B97F4A7C15ull), S_c);
 }
 
+// 2^(-2d), exactly, for 0 <= d < 500 (rescales a sum of squares between two power-of-two references)
+__device__ __forceinline__ double pow2_neg2(int d) { return __longlong_as_double((long long)(1023 - 2 * d) << 52); }
+
 struct NestedTopShared {
     int wmax[kScanThreads / 32];
     unsigned long long ws[kScanThreads / 32];
@@ -90,45 +93,70 @@ struct NestedTopShared {
     unsigned long long carry;
 };
 
-// Top level, by one whole block: E, M_s, their exclusive prefixes, W and the ESS from the section records.
+// Top level, by one whole block: E, M_s, W, the ESS, and level 0 of the resampling (slot j sits at j*W + U; section s owns
+// the slots [a_s, a_s + n_s)) from the section records.  Written for latency: with up to 1024 sections (2^27 particles)
+// every thread loads its 4 records once and everything else stays in registers.
 __device__ __forceinline__ void nested_top_level(const NestedPrefixes& nb, DeviceStats* st, NestedTopShared& sh, uint64_t seed, long long rt,
                                                  unsigned long long n_out) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n_sec = nb.n_sec_global;
-    int emax = kChunkEmpty;
-    for (unsigned int i = tid; i < n_sec; i += kScanThreads) emax = max(emax, __ldcg(nb.sec_E + i));
-    emax = __reduce_max_sync(0xffffffffu, emax);
-    if (lane == 0) sh.wmax[warp] = emax;
     if (tid == 0) sh.carry = 0ull;
-    __syncthreads();
     int E = kChunkEmpty;
+    if (n_sec > kScanThreads * 4) {   // more sections than one pass holds: the maximum needs its own pass
+        int emax = kChunkEmpty;
+        for (unsigned int i = tid; i < n_sec; i += kScanThreads) emax = max(emax, __ldcg(nb.sec_E + i));
+        emax = __reduce_max_sync(0xffffffffu, emax);
+        if (lane == 0) sh.wmax[warp] = emax;
+        __syncthreads();
 #pragma unroll
-    for (int w = 0; w < kScanThreads / 32; ++w) E = max(E, sh.wmax[w]);
+        for (int w = 0; w < kScanThreads / 32; ++w) E = max(E, sh.wmax[w]);
+        __syncthreads();
+    }
+    const unsigned long long word = resample_rand_word(seed, rt, st);   // (independent of the loads below)
     double sqt = 0.;
+    unsigned long long v[4], pre0 = 0;   // the last pass' values stay in registers for level 0
+    unsigned int first = 0;
     for (unsigned int base = 0; base < n_sec; base += kScanThreads * 4) {
-        unsigned long long v[4], tot = 0;
-        const unsigned int first = base + tid * 4;
+        first = base + tid * 4;
+        int e_s[4];
+        unsigned long long T[4];
+        double sq[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            v[i] = 0ull;
-            if (first + i < n_sec) {
-                const int e_s = __ldcg(nb.sec_E + first + i);
-                v[i] = nested_shift(__ldcg(nb.sec_T + first + i), e_s, E);
-                if (e_s != kChunkEmpty && E - e_s < 500) sqt += __ldcg(nb.sec_sq + first + i) * exp2(-2. * (double)(E - e_s));
-            }
+            const bool ok = first + i < n_sec;
+            e_s[i] = ok ? __ldcg(nb.sec_E + first + i) : kChunkEmpty;
+            T[i] = ok ? __ldcg(nb.sec_T + first + i) : 0ull;
+            sq[i] = ok ? __ldcg(nb.sec_sq + first + i) : 0.;
+        }
+        if (n_sec <= kScanThreads * 4) {   // single pass: the maximum from the values just loaded
+            int emax = max(max(e_s[0], e_s[1]), max(e_s[2], e_s[3]));
+            emax = __reduce_max_sync(0xffffffffu, emax);
+            if (lane == 0) sh.wmax[warp] = emax;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < kScanThreads / 32; ++w) E = max(E, sh.wmax[w]);
+        }
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[i] = nested_shift(T[i], e_s[i], E);
+            if (e_s[i] != kChunkEmpty && E - e_s[i] < 500) sqt += sq[i] * pow2_neg2(E - e_s[i]);
             tot += v[i];
         }
         unsigned long long incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
-        __syncthreads();
         if (lane == 31) sh.ws[warp] = incl;
         __syncthreads();
-        unsigned long long pre = sh.carry + incl - tot, all = 0;
+        unsigned long long all = 0;
+        pre0 = sh.carry + incl - tot;
 #pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) { unsigned long long x = sh.ws[w]; if (w < warp) pre += x; all += x; }
+        for (int w = 0; w < kScanThreads / 32; ++w) { unsigned long long x = sh.ws[w]; if (w < warp) pre0 += x; all += x; }
+        if (base + kScanThreads * 4 < n_sec) {   // more passes follow: their level 0 reads the prefixes back
+            unsigned long long pre = pre0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { if (first + i < n_sec) { nb.sec_pre[first + i] = pre; nb.sec_M[first + i] = v[i]; } pre += v[i]; }
+            for (int i = 0; i < 4; ++i) { if (first + i < n_sec) { nb.sec_pre[first + i] = pre; nb.sec_M[first + i] = v[i]; } pre += v[i]; }
+        }
         __syncthreads();
         if (tid == 0) sh.carry += all;
         __syncthreads();
@@ -136,9 +164,27 @@ __device__ __forceinline__ void nested_top_level(const NestedPrefixes& nb, Devic
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sqt += __shfl_xor_sync(0xffffffffu, sqt, o);
     if (lane == 0) sh.wsq[warp] = sqt;
-    __syncthreads();
     const unsigned long long W = sh.carry;
-    const unsigned long long word = resample_rand_word(seed, rt, st);
+    if (W != 0ull) {
+        const unsigned long long U = __umul64hi(word, W);
+        const double inv_w = 1. / (double)W;
+        for (unsigned int base = 0; base < n_sec; base += kScanThreads * 4) {
+            const bool in_regs = base + kScanThreads * 4 >= n_sec;
+            const unsigned int f = base + tid * 4;
+            unsigned long long pre = in_regs ? pre0 : 0ull;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (f + i >= n_sec) break;
+                const unsigned long long m = in_regs ? v[i] : nb.sec_M[f + i];
+                if (!in_regs) pre = nb.sec_pre[f + i];
+                const TileBase sb = tile_base_exact(pre, W, U, n_out, inv_w);
+                nb.sec_a[f + i] = sb.n_start;
+                nb.sec_n[f + i] = local_count(m, sb.rem, (double)sb.rem, W, (double)n_out, n_out, inv_w);
+                pre += m;
+            }
+        }
+    }
+    __syncthreads();
     if (tid == 0) {
         double sq = 0.;
         for (int i = 0; i < kScanThreads / 32; ++i) sq += sh.wsq[i];
@@ -146,32 +192,66 @@ __device__ __forceinline__ void nested_top_level(const NestedPrefixes& nb, Devic
         st->sumexp2 = sq;
         st->ess = sq > 0. ? ((double)W * (double)W) / sq : 0.;
     }
-    if (W == 0ull) return;
-    // level 0: slot j sits at j*W + U; section s owns the slots [a_s, a_s + n_s)
-    const unsigned long long U = __umul64hi(word, W);
-    const double inv_w = 1. / (double)W;
-    for (unsigned int i = tid; i < n_sec; i += kScanThreads) {
-        const TileBase sb = tile_base_exact(nb.sec_pre[i], W, U, n_out, inv_w);
-        nb.sec_a[i] = sb.n_start;
-        nb.sec_n[i] = local_count(nb.sec_M[i], sb.rem, (double)sb.rem, W, (double)n_out, n_out, inv_w);
-    }
 }
 
-// ---- chunk pass: one block per section.  Section scale, chunk masses, tile sums and their prefixes inside the section,
-// the section record; the last block runs the top level (one GPU) or nothing more (several: the records were already sent).
+// several GPUs: collect every other shard's section records (the caller then runs the top level)
+__device__ __forceinline__ void collect_section_records(const PeerTable& p, long long epoch, const NestedPrefixes& nb) {
+    Mailbox* mb = p.mail[p.rank];
+    SpinGuard g(p);
+    for (unsigned int sg = threadIdx.x; sg < nb.n_sec_global; sg += kScanThreads) {
+        if (sg - nb.sec0 < nb.n_sec) continue;   // own sections: already in place
+        nb.sec_E[sg] = (int)(unsigned int)ll_read64(&mb->sec_ll[sg][0], (unsigned int)epoch, g);
+        nb.sec_T[sg] = ll_read64(&mb->sec_ll[sg][2], (unsigned int)epoch, g);
+        nb.sec_sq[sg] = __longlong_as_double((long long)ll_read64(&mb->sec_ll[sg][4], (unsigned int)epoch, g));
+    }
+    __threadfence();
+    __syncthreads();
+}
+
+// scalar bookkeeping of resample(): particle_filter.rs:104-105,114 (one thread of the expansion kernel)
 template <typename Real>
-__global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
-                                                                    unsigned int num_chunks) {
+__device__ __forceinline__ void nested_bookkeeping(const FixedArgs<Real>& a, DeviceStats* st, long long epoch) {
+    const unsigned long long W = st->W;
+    if (W == 0ull) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1; return; }
+    const double lse = (double)st->nest_E * 0.6931471805599453 + log((double)W) - (double)a.kbits * 0.6931471805599453;
+    st->lse = lse;
+    st->ess_stale = st->ess;
+    if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
+    st->resampled = 1;
+    st->resampled_flag[epoch & 1] = 1;
+    st->n_resamples += 1;
+    st->degenerate = 0;
+}
+
+// ---- section pass: one small kernel between the extend and the expansion.
+//   phase A (a block per section): section scale, chunk masses, tile sums and their prefixes inside the section; the
+//            section record (sent to every other GPU right away)
+//   top      the last block to finish phase A collects the other shards' records (several GPUs) and runs the top level
+// PHASES = 3: both.  1: phase A only, 2: (collect +) top level only, one block -- separate launches for the test hook that
+// emulates shards on one GPU, where a kernel must never wait for one that has not been launched.
+template <typename Real, int PHASES>
+__global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
+                                                                       unsigned int num_chunks) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ unsigned long long ts[kTilesPerSection];
     __shared__ double tsq[kTilesPerSection];
     __shared__ int wmax[kScanThreads / 32];
     __shared__ NestedTopShared top;
     __shared__ bool is_last;
+    DeviceStats* st = a.stats;
     pdl_wait();
     pdl_trigger();   // the expansion kernel may become resident now: it loads its weights while this grid runs
     constexpr int kTilesPerWarp = kTilesPerSection / (kScanThreads / 32);
-    const unsigned int tile0 = blockIdx.x * kTilesPerSection + warp * kTilesPerWarp;
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    if (blockIdx.x == 0 && tid == 0) st->trace[9] = global_ns();
+    if constexpr (PHASES == 2) {
+        if (a.peer.world > 1) { if (tid == 0) st->trace[6] = global_ns(); collect_section_records(a.peer, epoch, nb); }
+        nested_top_level(nb, st, top, a.seed, a.rt, a.n_out);
+        if (tid == 0) st->trace[7] = global_ns();
+        return;
+    }
+    const unsigned int sec = blockIdx.x;
+    const unsigned int tile0 = sec * kTilesPerSection + warp * kTilesPerWarp;
     int e[kTilesPerWarp];
     unsigned long long S[kTilesPerWarp];
     float sqf[kTilesPerWarp];
@@ -195,14 +275,14 @@ __global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Re
     for (int i = 0; i < kTilesPerWarp; ++i) {
         unsigned long long g = nested_shift(S[i], e[i], E_s);
         double sq = 0.;
-        if (e[i] != kChunkEmpty && E_s - e[i] < 500) sq = (double)sqf[i] * exp2(-2. * (double)(E_s - e[i]));
+        if (e[i] != kChunkEmpty && E_s - e[i] < 500) sq = (double)sqf[i] * pow2_neg2(E_s - e[i]);
         g = warp_sum_u48(g);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
         if (lane == 0) { ts[warp * kTilesPerWarp + i] = g; tsq[warp * kTilesPerWarp + i] = sq; }
     }
     __syncthreads();
-    const unsigned int sg = nb.sec0 + blockIdx.x;   // global section number
+    const unsigned int sg = nb.sec0 + sec;   // global section number
     if (warp == 0) {
         const unsigned long long v = ts[lane];
         unsigned long long incl = v;
@@ -211,61 +291,50 @@ __global__ void __launch_bounds__(kScanThreads) nested_chunk_kernel(FixedArgs<Re
         double sq = tsq[lane];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        const unsigned int tile = blockIdx.x * kTilesPerSection + lane;
+        const unsigned int tile = sec * kTilesPerSection + lane;
         if (tile < num_tiles) nb.tile_pre[tile] = incl - v;
         const unsigned long long T_s = __shfl_sync(0xffffffffu, incl, 31);
-        if (a.peer.world > 1) {   // the section record goes to every other rank right away (three tagged words each)
-            const long long epoch = a.epoch < 0 ? a.stats->t : a.epoch;
-            if (lane < a.peer.world && lane != a.peer.rank) {
-                unsigned long long* dst = a.peer.mail[lane]->sec_ll[sg];
-                ll_write64(dst, (unsigned long long)(unsigned int)E_s, (unsigned int)epoch);
-                ll_write64(dst + 2, T_s, (unsigned int)epoch);
-                ll_write64(dst + 4, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
-            }
+        if (a.peer.world > 1 && lane < a.peer.world && lane != a.peer.rank) {   // the record goes to every other rank right away
+            unsigned long long* dst = a.peer.mail[lane]->sec_ll[sg];
+            ll_write64(dst, (unsigned long long)(unsigned int)E_s, (unsigned int)epoch);
+            ll_write64(dst + 2, T_s, (unsigned int)epoch);
+            ll_write64(dst + 4, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
         }
         if (lane == 31) {
             nb.sec_E[sg] = E_s; nb.sec_T[sg] = T_s; nb.sec_sq[sg] = sq;
             __threadfence();
-            is_last = (atomicAdd(&a.stats->blocks_done, 1u) == gridDim.x - 1);
+            is_last = (atomicAdd(&st->blocks_done, 1u) == gridDim.x - 1);
         }
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (tid == 0) { a.stats->overflow_count = 0; a.stats->blocks_done = 0; a.stats->trace[5] = global_ns(); }
-    if (a.peer.world <= 1) nested_top_level(nb, a.stats, top, a.seed, a.rt, a.n_out);
+    if (tid == 0) { st->overflow_count = 0; st->blocks_done = 0; st->trace[5] = global_ns(); }
+    if constexpr (PHASES == 3) {
+        if (a.peer.world > 1) { if (tid == 0) st->trace[6] = global_ns(); collect_section_records(a.peer, epoch, nb); }
+        nested_top_level(nb, st, top, a.seed, a.rt, a.n_out);
+        if (tid == 0) st->trace[7] = global_ns();
+    }
 }
 
-// several GPUs: block 0 of the expansion kernel collects every other shard's section records, runs the top level, and
-// releases the kernel's other blocks through the local ready word
-__device__ __forceinline__ void gate_sections(const PeerTable& p, DeviceStats* st, long long epoch, const NestedPrefixes& nb, NestedTopShared& top,
-                                              uint64_t seed, long long rt, unsigned long long n_out) {
-    if (p.world <= 1) return;
-    if (blockIdx.x == 0) {
-        if (threadIdx.x == 0) st->trace[6] = global_ns();
-        Mailbox* mb = p.mail[p.rank];
-        SpinGuard g(p);
-        for (unsigned int sg = threadIdx.x; sg < nb.n_sec_global; sg += kScanThreads) {
-            if (sg - nb.sec0 < nb.n_sec) continue;   // own sections: already in place
-            nb.sec_E[sg] = (int)(unsigned int)ll_read64(&mb->sec_ll[sg][0], (unsigned int)epoch, g);
-            nb.sec_T[sg] = ll_read64(&mb->sec_ll[sg][2], (unsigned int)epoch, g);
-            nb.sec_sq[sg] = __longlong_as_double((long long)ll_read64(&mb->sec_ll[sg][4], (unsigned int)epoch, g));
-        }
-        __threadfence();
-        __syncthreads();
-        nested_top_level(nb, st, top, seed, rt, n_out);
-        __syncthreads();
-        if (threadIdx.x == 0) { st->trace[7] = global_ns(); local_ready_set(&st->ready_w, epoch); }
-    } else if (threadIdx.x == 0) local_ready_wait(&st->ready_w, epoch, p);
-    __syncthreads();
+// exclusive prefix (over the warp) of each lane's 4 particles inside chunk r, for the 4 chunks of a warp tile
+__device__ __forceinline__ void chunk_exclusive_prefixes(const float (&qf)[4][4], unsigned long long (&excl)[4]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const unsigned long long own = __float2ull_rz(qf[r][0]) + __float2ull_rz(qf[r][1]) + __float2ull_rz(qf[r][2]) + __float2ull_rz(qf[r][3]);
+        unsigned long long inc = own;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+        excl[r] = inc - own;
+    }
 }
 
 // ---- level-1 pass: one warp per tile (lane <-> chunk): the tile's first slot inside its section, then the slot range of
-// every chunk.  Several GPUs: block 0 first collects the other shards' section records and runs the top level.
+// every chunk.  (Kept out of the expansion kernel: there it would hold up seven warps per tile behind one.)
 template <typename Real>
 __global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
                                                                      unsigned int num_chunks) {
-    __shared__ NestedTopShared top;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x * (kScanThreads / 32) + warp;
@@ -275,36 +344,23 @@ __global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<R
     if (tile < num_tiles && c_l < num_chunks) { S_l = rec.S[c_l]; e_l = rec.e[c_l]; }   // (written two kernels ago: complete)
     pdl_wait();
     pdl_trigger();   // the expansion kernel may become resident and load its weights
-    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-    gate_sections(a.peer, st, epoch, nb, top, a.seed, a.rt, a.n_out);
+    if (blockIdx.x == 0 && tid == 0) { st->trace[10] = global_ns(); nested_bookkeeping(a, st, a.epoch < 0 ? st->t : a.epoch); }
     const unsigned long long W = st->W;
-    if (blockIdx.x == 0 && tid == 0) {   // scalar bookkeeping of resample(): particle_filter.rs:104-105,114
-        if (W == 0ull) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1; }
-        else {
-            double lse = (double)st->nest_E * 0.6931471805599453 + log((double)W) - (double)a.kbits * 0.6931471805599453;
-            st->lse = lse;
-            st->ess_stale = st->ess;
-            if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
-            st->resampled = 1;
-            st->resampled_flag[epoch & 1] = 1;
-            st->n_resamples += 1;
-            st->degenerate = 0;
-        }
-    }
     if (tile >= num_tiles || W == 0ull) return;
     const unsigned int sg = nb.sec0 + tile / kTilesPerSection;
-    const unsigned long long T_s = nb.sec_T[sg], n_s = nb.sec_n[sg];
+    const unsigned long long T_s = nb.sec_T[sg], n_s = nb.sec_n[sg], a_s = nb.sec_a[sg], pre_t = nb.tile_pre[tile];
+    const int E_s = nb.sec_E[sg];
     uint2 out = make_uint2(0u, 0u);
     if (n_s != 0ull && T_s != 0ull) {
         const double inv_t = 1. / (double)T_s;
-        const TileBase base = tile_base_exact(nb.tile_pre[tile], T_s, nested_section_offset(st->rand_word, sg, T_s), n_s, inv_t);
-        unsigned long long gi = nested_shift(S_l, e_l, nb.sec_E[sg]);
+        const TileBase base = tile_base_exact(pre_t, T_s, nested_section_offset(st->rand_word, sg, T_s), n_s, inv_t);
+        unsigned long long gi = nested_shift(S_l, e_l, E_s);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, gi, o); if (lane >= o) gi += up; }
         const unsigned int slot_end = local_count(gi, base.rem, (double)base.rem, T_s, (double)n_s, n_s, inv_t);   // slots of the tile up to and including chunk l
         unsigned int slot_beg = __shfl_up_sync(0xffffffffu, slot_end, 1);
         if (lane == 0) slot_beg = 0;
-        out = make_uint2((unsigned int)(nb.sec_a[sg] + base.n_start) + slot_beg, slot_end - slot_beg);
+        out = make_uint2((unsigned int)(a_s + base.n_start) + slot_beg, slot_end - slot_beg);
     }
     if (c_l < num_chunks) nb.slots[c_l] = out;
 }
@@ -317,9 +373,9 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x;
-    // The integer weights and chunk records come from the kernel before the chunk pass, and this grid is only released once
-    // every block of the two small passes in between is past its own dependency wait -- so they are complete and visible
-    // already: load them (and do the warp-local scans) before waiting for the level-1 pass' slot ranges.
+    // The integer weights and chunk records come from the kernel before the section pass, and this grid is only released
+    // once every block of the two small passes in between is past its own dependency wait -- so they are complete and
+    // visible already: load them (and do the warp-local scans) before waiting for the level-1 pass' slot ranges.
     const size_t wt_base = (size_t)tile * kScanTile + (size_t)warp * kWarpTile;
     // integer weights stay in their float form (exact: at most 24 significant bits) to keep registers free
     float qf[4][4];
@@ -337,18 +393,12 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
             }
         } else { qf[r][0] = qf[r][1] = qf[r][2] = qf[r][3] = 0.f; }
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {   // exclusive prefix of the lane's 4 particles inside chunk r
-        const unsigned long long own = __float2ull_rz(qf[r][0]) + __float2ull_rz(qf[r][1]) + __float2ull_rz(qf[r][2]) + __float2ull_rz(qf[r][3]);
-        unsigned long long inc = own;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
-        excl[r] = inc - own;
-    }
     const unsigned int c_w = tile * kChunksPerTile + 4 * warp + (lane & 3);   // this warp's 4 chunks (lanes 0..3 hold them)
     const unsigned long long S_w = c_w < num_chunks ? rec.S[c_w] : 0ull;
+    chunk_exclusive_prefixes(qf, excl);
     pdl_wait();
     pdl_trigger();
+    if (tile == 0 && tid == 0) st->trace[11] = global_ns();
     if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the level-1 pass)
         for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
         return;

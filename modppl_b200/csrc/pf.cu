@@ -354,9 +354,11 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3) {
         ScopedLaunch sl(ps, "nested_quantise");
         pdl_launch(nested_quantise_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec);
     }
-    if (phases & 1) {
-        ScopedLaunch sl(ps, "nested_chunk");
-        pdl_launch(nested_chunk_kernel<Real>, nb.n_sec, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
+    {
+        ScopedLaunch sl(ps, "nested_sections");
+        if (phases == 3) pdl_launch(nested_sections_kernel<Real, 3>, nb.n_sec, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
+        else if (phases == 1) pdl_launch(nested_sections_kernel<Real, 1>, nb.n_sec, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
+        else pdl_launch(nested_sections_kernel<Real, 2>, 1, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
     }
     if (phases & 2) {
         ScopedLaunch sl(ps, "nested_level1");
@@ -434,7 +436,7 @@ static int do_resample(mpl_ps* ps, int scheme) {
     int rc = materialise(ps);   // resample twice in a row: apply the first one
     if (rc) return rc;
     const bool exact = scheme == MPL_RESAMPLE_MULTINOMIAL || scheme == MPL_RESAMPLE_SYSTEMATIC;
-    if (exact || !ps->max_valid) {   // the reference scheme needs log-sum-exp; the integer schemes only the max (left by the extend)
+    if (exact || (!ps->max_valid && scheme != MPL_RESAMPLE_SYSTEMATIC_NESTED)) {   // the reference scheme needs log-sum-exp; the single-level integer schemes only the max (left by the extend); the nested one nothing
         rc = ensure_stats(ps);
         if (rc) return rc;
     }
@@ -469,10 +471,10 @@ int ps_phase_extend(mpl_ps* ps, bool init, bool fuse_nested) {
     if (init) {
         ps->t = 0; ps->pending_gather = false;
         rc = launch_extend(ps, EXT_INIT, dummy, true, false, fuse_nested);
-        ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
+        ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
     } else {
         rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false, fuse_nested);
-        ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
+        ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
     }
     return rc;
 }
@@ -661,7 +663,7 @@ extern "C" int mpl_ps_init_step(mpl_ps* ps, const double* obs, size_t n_obs) {
     ps->pending_gather = false;
     rc = launch_extend(ps, EXT_INIT, o, false, false);
     if (rc) return rc;
-    ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
+    ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
     return MPL_OK;
 }
 
@@ -675,7 +677,7 @@ extern "C" int mpl_ps_step(mpl_ps* ps, const double* obs, size_t n_obs) {
     rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, o, false, false);
     if (rc) return rc;
     ps->pending_gather = false;
-    ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
+    ps->t += 1; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
     return MPL_OK;
 }
 
@@ -694,7 +696,7 @@ extern "C" int mpl_ps_step_resample(mpl_ps* ps, const double* obs, size_t n_obs,
     rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, o, false, false, fuse);
     if (rc) return rc;
     ps->pending_gather = false;
-    ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
+    ps->t += 1; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
     return mpl_ps_resample(ps, scheme, log_total_weight);
 }
 
@@ -898,14 +900,14 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
         if (tt == 0) {
             ps->t = 0; ps->pending_gather = false;
             rc = launch_extend(ps, EXT_INIT, dummy, true, false, fuse_nested);
-            ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = true;
+            ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
         } else if (dynamic) {
             // whether the previous step resampled is only known on the device: the extend reads stats->resampled_flag[t & 1]
             rc = launch_extend(ps, EXT_DYNAMIC, dummy, true, false);
-            ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
+            ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
         } else {
             rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false, fuse_nested);
-            ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = true;
+            ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
         }
         if (rc != MPL_OK) break;
         if (dynamic) {

@@ -49,7 +49,7 @@ struct DeviceStats {
     long long ready_stats, ready_w, ready_done;
     long long trace[16];           // %globaltimer stamps of the last step's phases (sharded runs; mpl_ps_trace)
     int nest_E;                    // nested scheme: the global power-of-two reference of this resample
-    int pad2;
+    unsigned int nest_gen;         // nested scheme: generation word that releases the section pass' blocks after the top level
 };
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
     if (sharded && gather) gate_done(a.peer, a.stats, t);   // ancestors written everywhere; old buffer no longer read
 
     Real run_max = (Real)-INFINITY;
-    if (blockIdx.x == 0 && tid == 0) a.stats->max_bits[(t + 1) & 1] = 0ull;   // slot of the next step (its last reader finished before this launch)
+    if (blockIdx.x == 0 && tid == 0) { a.stats->max_bits[(t + 1) & 1] = 0ull; a.stats->trace[13] = global_ns(); }   // slot of the next step (its last reader finished before this launch)
     const size_t stride = (size_t)gridDim.x * kExtendThreads * V;
     typedef typename std::conditional<V == 4, int4, int2>::type AncVec;
     size_t base = ((size_t)blockIdx.x * kExtendThreads + tid) * V;
@@ -295,14 +295,18 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
         // exact running max of the log-weights (NaN and padding lanes count as -inf, quirk Q9).  Sum statistics are not
         // needed on this path: the integer resampler derives the log total weight and the ESS from its own sums, and
         // ESS / log-ML queries run weight_reduce_kernel on demand.
+        if constexpr (!NESTED) {
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            bool ok = (full || base + v < a.n) && (w[v] == w[v]);
-            run_max = fmax(run_max, ok ? w[v] : (Real)-INFINITY);
+            for (int v = 0; v < V; ++v) {
+                bool ok = (full || base + v < a.n) && (w[v] == w[v]);
+                run_max = fmax(run_max, ok ? w[v] : (Real)-INFINITY);
+            }
         }
     }
 
     pdl_trigger();
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) a.stats->trace[14] = global_ns();
+    if constexpr (NESTED) return;   // the nested resampler needs no global maximum (and, sharded, no exchange here)
     __shared__ Real warp_max_s[kExtendThreads / 32];
     __shared__ bool is_last;
 #pragma unroll

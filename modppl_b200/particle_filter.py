@@ -57,6 +57,12 @@ class ParticleSystem:
         self._steps_done = getattr(self, "_steps_done", 0) + 1
         return out.value if sync else None
 
+    def device_trace(self):
+        """%globaltimer stamps (ns) left by the kernels of the last step (diagnostics; include/modppl_b200.h: mpl_ps_trace)."""
+        buf = (C.c_longlong * 16)()
+        check(lib.mpl_ps_trace(self._h, buf))
+        return list(buf)
+
     def log_marginal_likelihood_estimate(self):            # :119-121
         out = C.c_double()
         check(lib.mpl_ps_log_marginal_likelihood_estimate(self._h, C.byref(out)))
