@@ -82,7 +82,10 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline_port(steps=6, log2n=20):
+ORACLE_SCHEME = {"systematic": 2, "multinomial": 3, "nested": 4}
+
+
+def cpu_baseline_port(steps=6, log2n=20, scheme=4):
     """The oracle's particle filter (restates inference/particle_filter.rs) on a bounded sample of the workload, one
     host thread (the reference is single-threaded: ThreadRng is !Send).  Resampling uses cumsum + binary search, i.e.
     the reference's algorithm without its O(N^2) per-draw clone-and-sum; the faithful cost is reported separately."""
@@ -91,10 +94,10 @@ def cpu_baseline_port(steps=6, log2n=20):
     n = 1 << log2n
     ys = observations(steps + 1)
     ps = O.OraclePS("lgssm4", [0.1, 0.5, 1.0], n, dtype="f32", seed=1)
-    ps.init_step(ys[0]); ps.resample(2)
+    ps.init_step(ys[0]); ps.resample(scheme)
     t0 = time.perf_counter()
     for t in range(1, steps + 1):
-        ps.step(ys[t]); ps.resample(2)
+        ps.step(ys[t]); ps.resample(scheme)
     dt = time.perf_counter() - t0
     fair = n * steps / dt
     # faithful reference cost (categorical.rs:22-32: clone + sum + linear scan per draw) at N = 2^12: O(N^2)
@@ -105,7 +108,7 @@ def cpu_baseline_port(steps=6, log2n=20):
     pf.resample_faithful_cost(); pf.step(ys[1]); pf.resample_faithful_cost()
     dtf = time.perf_counter() - t0
     return {"value": fair, "unit": "particle-steps/s", "cores": 1, "kind": "port",
-            "sample": f"oracle PF, lgssm4 f32, N=2^{log2n}, {steps} steps, systematic resampling on integer weights (O(N)); "
+            "sample": f"oracle PF, lgssm4 f32, N=2^{log2n}, {steps} steps, {'nested ' if scheme == 4 else ''}{'multinomial' if scheme == 3 else 'systematic'} resampling on integer weights (O(N)); "
                       f"faithful O(N^2) reference resample at N=2^12: {nf * 2 / dtf:.3g} particle-steps/s (extrapolates to ~{nf * 2 / dtf * nf / (1 << 24):.2g}/s at N=2^24)",
             "seconds": dt + dtf}
 
@@ -114,7 +117,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_baseline_port(steps=max(2, min(args.steps, 8)))
+    base = cpu_baseline_port(steps=max(2, min(args.steps, 8)), scheme=ORACLE_SCHEME[args.scheme])
     line = {"impl": "reference", "metric": "particle-steps/sec (SMC step incl. resample)", "value": base["value"], "unit": "particle-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -166,14 +169,14 @@ def run_ours(args):
     ps.profile_enable(True)
     steps_prof = min(K, T - ps2_first)
     for k in range(steps_prof):
-        ps.step(ys[ps2_first + k]); ps.resample(scheme, sync=False)
+        ps.step_resample(ys[ps2_first + k], scheme, sync=False)   # (the same kernels as the timed loop, each between its own pair of events)
     prof = {k: ps.profile_get(k) for k in ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "fixed_cumsum", "fixed_search", "nested_quantise", "nested_sections", "nested_level1", "nested_scan")}
     ps.profile_enable(False)
     peak, peak_src = measured_peak()
     ext_ms = prof["extend"][0] / max(1, prof["extend"][1])
     achieved = EXTEND_BYTES_PER_PARTICLE * n_global / (ext_ms * 1e-3) / 1e9
     step_gbs = BYTES_PER_PARTICLE_STEP * value / 1e9
-    base = cpu_baseline_port()
+    base = cpu_baseline_port(scheme=ORACLE_SCHEME[args.scheme])
     line = {
         "metric": "particle-steps/sec (SMC step incl. resample)", "value": value, "unit": "particle-steps/s", "n_gpus": 1, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -181,7 +184,7 @@ def run_ours(args):
                    "T_timed": K, "resampling": args.scheme + " on integer weights", "l2": "inputs exceed L2 (2 x 256 MiB state buffers stream every step)",
                    "log_ml": lml},
         "e2e": {"value": n_global * K / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 128,
-                "note": "mpl_ps_step(host obs) + mpl_ps_resample(-> host log total weight) per step; particles stay in HBM by design"},
+                "note": "mpl_ps_step_resample(host obs -> host log total weight) per step; particles stay in HBM by design"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "pf_extend_kernel<Lgssm4<float>, GATHER>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -200,7 +203,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scheme", default="systematic", choices=["systematic", "multinomial", "nested"])
+    ap.add_argument("--scheme", default="nested", choices=["systematic", "multinomial", "nested"],
+                    help="resampler on integer weights: nested systematic (default, fastest), single-level systematic, multinomial")
     ap.add_argument("--log2-particles", type=int, default=LOG2_PARTICLES)
     args = ap.parse_args()
     if args.warmup < 3:

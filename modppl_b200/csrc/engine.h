@@ -61,7 +61,7 @@ struct mpl_ps {
     int* host_flags_dev;
     // trajectory reconstruction (reference keeps traces[i].retv as a Vec<State>, dynunfold.rs:91-92): optional log of the
     // per-step states and ancestors, back-traced on demand
-    int* rec_e; unsigned long long* rec_S; float* rec_sq;   // chunk records of the nested scheme (ld / 128 entries), lazily allocated
+    int* rec_e; unsigned int* rec_S; float* rec_sq;   // chunk records of the nested scheme (ld / 128 entries), lazily allocated
     unsigned long long* nest_tile_pre; unsigned long long* nest_sec; void* nest_slots;   // nested scheme: tile prefixes inside a section; section records + top-level prefixes
     bool prequantised;           // the last extend already left integer weights + chunk records (fused epilogue)
     void* hist_state;            // [hist_cap][D][ld] Real

@@ -60,12 +60,12 @@ __global__ void __launch_bounds__(kScanThreads) nested_quantise_kernel(FixedArgs
         else { double2 u = *reinterpret_cast<const double2*>(a.lw + idx), v = *reinterpret_cast<const double2*>(a.lw + idx + 2); w[0] = (float)u.x; w[1] = (float)u.y; w[2] = (float)v.x; w[3] = (float)v.y; }
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (idx + j >= a.n) w[j] = -INFINITY;
-        float qv[4], sq;
+        unsigned int qv[4], S_c;
+        float sq;
         int e_c;
-        unsigned long long S_c;
-        warp_quantise_chunk(w, a.kbits, qv, e_c, S_c, sq);
-        if constexpr (sizeof(Real) == 4) *reinterpret_cast<float4*>(a.lw + idx) = make_float4(qv[0], qv[1], qv[2], qv[3]);
-        else { *reinterpret_cast<double2*>(a.lw + idx) = make_double2(qv[0], qv[1]); *reinterpret_cast<double2*>(a.lw + idx + 2) = make_double2(qv[2], qv[3]); }
+        warp_quantise_chunk(w, qv, e_c, S_c, sq);
+        if constexpr (sizeof(Real) == 4) *reinterpret_cast<float4*>(a.lw + idx) = make_float4(nested_store<float>(qv[0]), nested_store<float>(qv[1]), nested_store<float>(qv[2]), nested_store<float>(qv[3]));
+        else { *reinterpret_cast<double2*>(a.lw + idx) = make_double2((double)qv[0], (double)qv[1]); *reinterpret_cast<double2*>(a.lw + idx + 2) = make_double2((double)qv[2], (double)qv[3]); }
         if (lane == 0) { rec.e[chunk] = e_c; rec.S[chunk] = S_c; rec.sq[chunk] = sq; }
     }
     pdl_trigger();
@@ -213,7 +213,7 @@ template <typename Real>
 __device__ __forceinline__ void nested_bookkeeping(const FixedArgs<Real>& a, DeviceStats* st, long long epoch) {
     const unsigned long long W = st->W;
     if (W == 0ull) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1; return; }
-    const double lse = (double)st->nest_E * 0.6931471805599453 + log((double)W) - (double)a.kbits * 0.6931471805599453;
+    const double lse = (double)st->nest_E * 0.6931471805599453 + log((double)W) - (double)kNestedBits * 0.6931471805599453;
     st->lse = lse;
     st->ess_stale = st->ess;
     if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     const unsigned int sec = blockIdx.x;
     const unsigned int tile0 = sec * kTilesPerSection + warp * kTilesPerWarp;
     int e[kTilesPerWarp];
-    unsigned long long S[kTilesPerWarp];
+    unsigned int S[kTilesPerWarp];
     float sqf[kTilesPerWarp];
     int emax = kChunkEmpty;
 #pragma unroll
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
         const unsigned int c = (tile0 + i) * kChunksPerTile + lane;
         const bool valid = c < num_chunks;
         e[i] = valid ? rec.e[c] : kChunkEmpty;
-        S[i] = valid ? rec.S[c] : 0ull;
+        S[i] = valid ? rec.S[c] : 0u;
         sqf[i] = valid ? rec.sq[c] : 0.f;
         emax = max(emax, e[i]);
     }
@@ -318,16 +318,37 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
 }
 
 // exclusive prefix (over the warp) of each lane's 4 particles inside chunk r, for the 4 chunks of a warp tile
-__device__ __forceinline__ void chunk_exclusive_prefixes(const float (&qf)[4][4], unsigned long long (&excl)[4]) {
+__device__ __forceinline__ void chunk_exclusive_prefixes(const unsigned int (&q)[4][4], unsigned int (&excl)[4]) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const unsigned long long own = __float2ull_rz(qf[r][0]) + __float2ull_rz(qf[r][1]) + __float2ull_rz(qf[r][2]) + __float2ull_rz(qf[r][3]);
-        unsigned long long inc = own;
+        const unsigned int own = q[r][0] + q[r][1] + q[r][2] + q[r][3];
+        unsigned int inc = own;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
+        for (int o = 1; o < 32; o <<= 1) { unsigned int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
         excl[r] = inc - own;
     }
+}
+
+// Level 2 count: floor((C * n_c + rem_c) / S_c) for C <= S_c < 2^30, n_c <= kLevel2FloatMax.  The quotient is estimated in
+// fp32 (nine roundings, each 2^-24 relative: the estimate is off by less than (n_c + 1) 2^-20.8) and rounded to the nearest
+// integer by the adder (no conversion instruction); only when the estimate is within `eps` = (n_c + 2) 2^-19 of an integer
+// -- where the floor could go either way -- is the exact 64-bit form evaluated.  The result is exact either way.
+constexpr unsigned int kLevel2FloatMax = 2048u;
+__device__ __forceinline__ unsigned int level2_count(unsigned int C, float Cf, unsigned int n_c, float n_cf, unsigned int rem_c, float rem_cf, unsigned int S_c,
+                                                    float inv_sf, float eps) {
+    const float fd = __fmul_rn(fmaf(Cf, n_cf, rem_cf), inv_sf);
+    const float t = __fadd_rn(fd, 8388608.0f);
+    const float diff = __fsub_rn(fd, __fsub_rn(t, 8388608.0f));   // fd - nearest integer, in [-0.5, 0.5]
+    unsigned int f = ((unsigned int)__float_as_int(t) & 0x7fffffu);
+    if (fabsf(diff) < eps) {
+        const unsigned long long y = (unsigned long long)C * n_c + rem_c;
+        unsigned long long p = (unsigned long long)f * S_c;
+        while (p > y) { --f; p -= S_c; }
+        while (p + S_c <= y) { ++f; p += S_c; }
+        return f;
+    }
+    return diff < 0.f ? f - 1u : f;
 }
 
 // ---- level-1 pass: one warp per tile (lane <-> chunk): the tile's first slot inside its section, then the slot range of
@@ -339,7 +360,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<R
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x * (kScanThreads / 32) + warp;
     const unsigned int c_l = tile * kChunksPerTile + lane;
-    unsigned long long S_l = 0;
+    unsigned int S_l = 0;
     int e_l = kChunkEmpty;
     if (tile < num_tiles && c_l < num_chunks) { S_l = rec.S[c_l]; e_l = rec.e[c_l]; }   // (written two kernels ago: complete)
     pdl_wait();
@@ -377,25 +398,23 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
     // once every block of the two small passes in between is past its own dependency wait -- so they are complete and
     // visible already: load them (and do the warp-local scans) before waiting for the level-1 pass' slot ranges.
     const size_t wt_base = (size_t)tile * kScanTile + (size_t)warp * kWarpTile;
-    // integer weights stay in their float form (exact: at most 24 significant bits) to keep registers free
-    float qf[4][4];
-    unsigned long long excl[4];
+    unsigned int q[4][4], excl[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const size_t idx = wt_base + (size_t)r * kChunk + (size_t)lane * 4;
         if (idx < a.n) {   // (chunks are quantised whole: entries past n inside the last chunk hold 0)
             if constexpr (sizeof(Real) == 4) {
-                float4 v = __ldcs(reinterpret_cast<const float4*>(a.lw + idx));   // last use
-                qf[r][0] = v.x; qf[r][1] = v.y; qf[r][2] = v.z; qf[r][3] = v.w;
+                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.lw + idx));   // last use; the integers' bit patterns
+                q[r][0] = v.x; q[r][1] = v.y; q[r][2] = v.z; q[r][3] = v.w;
             } else {
-                double2 u = *reinterpret_cast<const double2*>(a.lw + idx), v = *reinterpret_cast<const double2*>(a.lw + idx + 2);
-                qf[r][0] = (float)u.x; qf[r][1] = (float)u.y; qf[r][2] = (float)v.x; qf[r][3] = (float)v.y;
+                const double2 u = *reinterpret_cast<const double2*>(a.lw + idx), v = *reinterpret_cast<const double2*>(a.lw + idx + 2);
+                q[r][0] = nested_load<double>(u.x); q[r][1] = nested_load<double>(u.y); q[r][2] = nested_load<double>(v.x); q[r][3] = nested_load<double>(v.y);
             }
-        } else { qf[r][0] = qf[r][1] = qf[r][2] = qf[r][3] = 0.f; }
+        } else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0u; }
     }
     const unsigned int c_w = tile * kChunksPerTile + 4 * warp + (lane & 3);   // this warp's 4 chunks (lanes 0..3 hold them)
-    const unsigned long long S_w = c_w < num_chunks ? rec.S[c_w] : 0ull;
-    chunk_exclusive_prefixes(qf, excl);
+    const unsigned int S_w = c_w < num_chunks ? rec.S[c_w] : 0u;
+    chunk_exclusive_prefixes(q, excl);
     pdl_wait();
     pdl_trigger();
     if (tile == 0 && tid == 0) st->trace[11] = global_ns();
@@ -413,8 +432,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
     for (int r = 0; r < 4; ++r) {
         const unsigned int n_c = __shfl_sync(0xffffffffu, slot_w.y, r);
         const unsigned int cb = we - ws;   // chunks of a tile own consecutive slot ranges
-        const unsigned long long S_c = __shfl_sync(0xffffffffu, S_w, r);
-        if (n_c == 0u || S_c == 0ull) {
+        const unsigned int S_c = __shfl_sync(0xffffffffu, S_w, r);
+        if (n_c == 0u || S_c == 0u) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) n[r][j] = cb;
             continue;
@@ -422,13 +441,24 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
         we += n_c;
         // level 2: local slot l sits at l*S_c + U_c; particle with inclusive chunk prefix C owns the slots below C*n_c
         const unsigned long long chunk_gid = ((unsigned long long)a.out_base / kChunk) + (unsigned long long)tile * kChunksPerTile + 4 * warp + r;
-        const unsigned long long rem_c = S_c - nested_chunk_offset(word, chunk_gid, S_c) - 1ull;
-        const double inv_s = 1. / (double)S_c, rem_cd = (double)rem_c, n_cd = (double)n_c;
-        unsigned long long C = excl[r];
+        const unsigned int rem_c = S_c - (unsigned int)nested_chunk_offset(word, chunk_gid, (unsigned long long)S_c) - 1u;
+        unsigned int C = excl[r];
+        if (n_c <= kLevel2FloatMax) {   // (warp-uniform)
+            const float n_cf = (float)n_c, rem_cf = (float)rem_c, inv_sf = __frcp_rn((float)S_c), eps = (n_cf + 2.f) * 0x1.0p-19f;
+            float Cf = (float)C;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            C += __float2ull_rz(qf[r][j]);
-            n[r][j] = cb + local_count(C, rem_c, rem_cd, S_c, n_cd, (unsigned long long)n_c, inv_s);
+            for (int j = 0; j < 4; ++j) {
+                C += q[r][j];
+                Cf += __uint_as_float(q[r][j] | 0x4B000000u) - 8388608.0f;   // (float)q, exact for q <= 2^22
+                n[r][j] = cb + level2_count(C, Cf, n_c, n_cf, rem_c, rem_cf, S_c, inv_sf, eps);
+            }
+        } else {   // a chunk that owns thousands of slots: fp64 estimate with its own exact fallback
+            const double inv_s = 1. / (double)S_c, rem_cd = (double)rem_c, n_cd = (double)n_c;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                C += q[r][j];
+                n[r][j] = cb + local_count((unsigned long long)C, (unsigned long long)rem_c, rem_cd, (unsigned long long)S_c, n_cd, (unsigned long long)n_c, inv_s);
+            }
         }
     }
     const unsigned int total = we - ws;

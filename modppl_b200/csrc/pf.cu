@@ -323,7 +323,7 @@ static int ensure_chunk_records(mpl_ps* ps) {
     if (ps->rec_e) return MPL_OK;
     const size_t nch = ps->ld / kChunk;
     MPL_CUDA_OK(cudaMalloc(&ps->rec_e, nch * sizeof(int)));
-    MPL_CUDA_OK(cudaMalloc(&ps->rec_S, nch * sizeof(unsigned long long)));
+    MPL_CUDA_OK(cudaMalloc(&ps->rec_S, nch * sizeof(unsigned int)));
     MPL_CUDA_OK(cudaMalloc(&ps->rec_sq, nch * sizeof(float)));
     const size_t nsec = (ps->ld + kSection - 1) / kSection;
     MPL_CUDA_OK(cudaMalloc(&ps->nest_tile_pre, nsec * kTilesPerSection * sizeof(unsigned long long)));

@@ -271,15 +271,16 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             vec_store_stream<Real>(a.state_out + (size_t)d * a.ld + base, tmp);
         }
         if constexpr (NESTED) {
-            float wm[4], qv[4], sqc;
+            float wm[4], sqc;
+            unsigned int qv[4];
 #pragma unroll
             for (int v = 0; v < V; ++v) wm[v] = (full || base + v < a.n) ? (float)w[v] : -INFINITY;
             int e_c;
-            unsigned long long S_c;
-            warp_quantise_chunk(wm, a.kbits, qv, e_c, S_c, sqc);
-            Real qr[V];
+            unsigned int S_c;
+            warp_quantise_chunk(wm, qv, e_c, S_c, sqc);
+            Real qr[V];   // fp32: the integer's bit pattern takes the log-weight's slot; fp64: its value
 #pragma unroll
-            for (int v = 0; v < V; ++v) qr[v] = (Real)qv[v];
+            for (int v = 0; v < V; ++v) qr[v] = nested_store<Real>(qv[v]);
             vec_store<Real>(a.lw + base, qr);
             if ((tid & 31) == 0) { const size_t chunk = base / kChunk; a.rec.e[chunk] = e_c; a.rec.S[chunk] = S_c; a.rec.sq[chunk] = sqc; }
         } else {

@@ -115,8 +115,13 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
     ms = max_over_ranks(ms)
     launches = ps.launch_count() - l0
     tr = ps.trace()     # last step of the timed run, this rank's clock (ns)
-    phases = {"extend_gate_wait": tr[1] - tr[0], "extend_body": tr[2] - tr[1], "to_reduce_gate": tr[3] - tr[2], "reduce_gate_wait": tr[4] - tr[3],
-              "reduce_body": tr[5] - tr[4], "to_scan_gate": tr[6] - tr[5], "scan_gate_wait": tr[7] - tr[6], "scan_to_signal": tr[8] - tr[7]}
+    if scheme == m.SYSTEMATIC_NESTED:   # stamps: see scripts/step_timeline.py
+        phases = {"extend_gate_wait": tr[1] - tr[0], "extend_start_to_last_block": tr[14] - tr[13], "to_section_pass": tr[9] - tr[14], "section_phase_a": tr[5] - tr[9],
+                  "collect_records_and_top_level": tr[7] - tr[6], "to_level1": tr[10] - tr[7], "level1_to_expansion": tr[11] - tr[10],
+                  "expansion_to_done_signal": tr[8] - tr[11]}
+    else:
+        phases = {"extend_gate_wait": tr[1] - tr[0], "extend_body": tr[2] - tr[1], "to_reduce_gate": tr[3] - tr[2], "reduce_gate_wait": tr[4] - tr[3],
+                  "reduce_body": tr[5] - tr[4], "to_scan_gate": tr[6] - tr[5], "scan_gate_wait": tr[7] - tr[6], "scan_to_signal": tr[8] - tr[7]}
     all_phases = [None] * world
     dist.all_gather_object(all_phases, phases)
     # e2e: one host round trip per step on every rank
@@ -133,7 +138,7 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
     ps.profile_enable(True)
     t_prof = t_first + K
     for k in range(min(K, len(ys) - t_prof)):
-        ps.step(ys[t_prof + k]); ps.resample(scheme, sync=False)
+        ps.step_resample(ys[t_prof + k], scheme, sync=False)
     prof = {k: ps.profile_get(k) for k in ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "nested_quantise", "nested_sections", "nested_level1", "nested_scan", "peer_done")}
     ps.profile_enable(False)
     kernel_ms = {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}
@@ -147,7 +152,7 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
             "metric": "particle-steps/sec (SMC step incl. resample)", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "lgssm4 (4-D linear-Gaussian SSM) bootstrap particle filter, resample every step", "particles": f"2^{args.log2_particles} in total, sharded",
-                       "T_timed": K, "resampling": "global systematic on integer weights; NVLink peer loads/stores inside the kernels, no NCCL on the data path",
+                       "T_timed": K, "resampling": f"global {args.scheme} resampling on integer weights; NVLink peer loads/stores inside the kernels, no NCCL on the data path",
                        "l2": "per-GPU state buffers stream every step", "log_ml": lml, "peer_wait_timeouts": err},
             "e2e": {"value": n_global * K / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 128},
             "gpu_launches": int(launches) * world, "clocks": clocks,

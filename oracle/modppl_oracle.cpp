@@ -374,7 +374,7 @@ inline uint64_t slots_below(uint64_t C, uint64_t W, uint64_t U, uint64_t n_out) 
 //   top:       E = max E_s,  M_s = T_s >> (E - E_s),  W = sum M_s
 extern "C" uint64_t mo_nested_systematic(const float* lw, size_t n, uint64_t u64rand, int32_t* anc, double* lse_out) {
     const size_t CH = 128, SEC = (size_t)1 << 17, CPS = SEC / CH;
-    const int kbits = mo_fixed_kbits(n);
+    const int kbits = 22;   // kNestedBits: a chunk's integer weights are at most 2^22, its sum fits 32 bits
     const size_t nch = (n + CH - 1) / CH, nsec = (n + SEC - 1) / SEC;
     std::vector<uint64_t> q(n, 0), S(nch, 0);
     std::vector<int> e(nch, 0);
