@@ -335,6 +335,9 @@ __device__ __forceinline__ void chunk_exclusive_prefixes(const unsigned int (&q)
 // integer by the adder (no conversion instruction); only when the estimate is within `eps` = (n_c + 2) 2^-19 of an integer
 // -- where the floor could go either way -- is the exact 64-bit form evaluated.  The result is exact either way.
 constexpr unsigned int kLevel2FloatMax = 2048u;
+// slots expanded per pass by one warp: a warp tile (512 particles) owns 512 slots on average, so 512 would need a second
+// pass half of the time; 768 almost never does
+constexpr int kNestedWarpSlots = 768;
 __device__ __forceinline__ unsigned int level2_count(unsigned int C, float Cf, unsigned int n_c, float n_cf, unsigned int rem_c, float rem_cf, unsigned int S_c,
                                                     float inv_sf, float eps) {
     const float fd = __fmul_rn(fmaf(Cf, n_cf, rem_cf), inv_sf);
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<R
 template <typename Real>
 __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
                                                                       unsigned int num_chunks) {
-    __shared__ __align__(16) unsigned short head[kScanThreads / 32][kWarpChunk];
+    __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DeviceStats* st = a.stats;
     const unsigned int tile = blockIdx.x;
@@ -467,8 +470,8 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
     // (heavy warp tiles are expanded by the owning warp alone in this scheme)
     const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile + warp * kWarpTile) - 1;
     // n[][] counts from 0 at the warp tile's first slot
-    for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kWarpChunk)
-        warp_expand_chunk<Real>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
+    for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kNestedWarpSlots)
+        warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
 }
 
 // several GPUs: tells every rank that this shard's expansion kernel has completed (all remote ancestor stores performed)

@@ -76,15 +76,18 @@ __device__ __forceinline__ void warp_tile_counts(unsigned long long wp, const un
     }
 }
 
-// One warp expands slots [chunk_lo, chunk_lo + kWarpChunk) of its own range [0, total) (relative to ws).
-template <typename Real>
+// One warp expands slots [chunk_lo, chunk_lo + CAP) of its own range [0, total) (relative to ws).  CAP = 32 * (slots per
+// lane), a multiple of 256: `head` holds CAP 16-bit entries.
+template <typename Real, int CAP = kWarpChunk>
 __device__ __forceinline__ void warp_expand_chunk(const FixedArgs<Real>& a, unsigned short* head, const unsigned int (&n)[4][4], unsigned int ws,
                                                   unsigned int total, unsigned int chunk_lo, unsigned long long slot_base /* global slot of ws */,
                                                   int32_t src0 /* value for local element 0, minus 1 */) {
+    constexpr int PER_LANE = CAP / 32, VEC = PER_LANE / 8;   // uint4 = 8 entries
+    static_assert(CAP % 256 == 0, "CAP");
     const int lane = threadIdx.x & 31;
     uint4* head4 = reinterpret_cast<uint4*>(head);
-    head4[lane * 2] = make_uint4(0, 0, 0, 0);
-    head4[lane * 2 + 1] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) head4[lane * VEC + k] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     // run heads: element e (order r, lane, j) owns relative slots [n_prev - ws, n_e - ws)
 #pragma unroll
@@ -95,40 +98,45 @@ __device__ __forceinline__ void warp_expand_chunk(const FixedArgs<Real>& a, unsi
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const unsigned int start = prev - ws, end = n[r][j] - ws;
-            if (end > start && start < chunk_lo + kWarpChunk && end > chunk_lo)
+            if (end > start && start < chunk_lo + CAP && end > chunk_lo)
                 head[max(start, chunk_lo) - chunk_lo] = (unsigned short)(r * 128 + lane * 4 + j + 1);
             prev = n[r][j];
         }
     }
     __syncwarp();
-    // max-scan: lane owns slots [16*lane, 16*lane + 16) of the chunk
-    uint4 h0 = head4[lane * 2], h1 = head4[lane * 2 + 1];
-    unsigned int v[16] = {h0.x & 0xffffu, h0.x >> 16, h0.y & 0xffffu, h0.y >> 16, h0.z & 0xffffu, h0.z >> 16, h0.w & 0xffffu, h0.w >> 16,
-                          h1.x & 0xffffu, h1.x >> 16, h1.y & 0xffffu, h1.y >> 16, h1.z & 0xffffu, h1.z >> 16, h1.w & 0xffffu, h1.w >> 16};
+    // max-scan: lane owns slots [PER_LANE*lane, PER_LANE*lane + PER_LANE) of the chunk
+    unsigned int v[PER_LANE];
 #pragma unroll
-    for (int i = 1; i < 16; ++i) v[i] = max(v[i], v[i - 1]);
-    unsigned int incl = v[15];
+    for (int k = 0; k < VEC; ++k) {
+        const uint4 h = head4[lane * VEC + k];
+        v[8 * k + 0] = h.x & 0xffffu; v[8 * k + 1] = h.x >> 16; v[8 * k + 2] = h.y & 0xffffu; v[8 * k + 3] = h.y >> 16;
+        v[8 * k + 4] = h.z & 0xffffu; v[8 * k + 5] = h.z >> 16; v[8 * k + 6] = h.w & 0xffffu; v[8 * k + 7] = h.w >> 16;
+    }
+#pragma unroll
+    for (int i = 1; i < PER_LANE; ++i) v[i] = max(v[i], v[i - 1]);
+    unsigned int incl = v[PER_LANE - 1];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = max(incl, up); }
     unsigned int pre = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) pre = 0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = max(v[i], pre);
-    head4[lane * 2] = make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-    head4[lane * 2 + 1] = make_uint4(v[8] | (v[9] << 16), v[10] | (v[11] << 16), v[12] | (v[13] << 16), v[14] | (v[15] << 16));
+    for (int i = 0; i < PER_LANE; ++i) v[i] = max(v[i], pre);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+        head4[lane * VEC + k] = make_uint4(v[8 * k] | (v[8 * k + 1] << 16), v[8 * k + 2] | (v[8 * k + 3] << 16), v[8 * k + 4] | (v[8 * k + 5] << 16), v[8 * k + 6] | (v[8 * k + 7] << 16));
     __syncwarp();
-    const unsigned int valid = min((unsigned int)kWarpChunk, total - chunk_lo);
+    const unsigned int valid = min((unsigned int)CAP, total - chunk_lo);
     const unsigned long long slot0 = slot_base + chunk_lo;
     if (slot0 >= a.out_base && slot0 + valid <= a.out_base + a.n_out_local) {   // whole chunk lands in this shard (always, on one GPU)
         int32_t* dst = a.anc + (slot0 - a.out_base);
 #pragma unroll
-        for (int k = 0; k < kWarpChunk / 32; ++k) {
+        for (int k = 0; k < CAP / 32; ++k) {
             unsigned int o = k * 32 + lane;
             if (o < valid) dst[o] = src0 + (int32_t)head[o];
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kWarpChunk / 32; ++k) {   // slots of other shards: remote stores into the owner's array
+        for (int k = 0; k < CAP / 32; ++k) {   // slots of other shards: remote stores into the owner's array
             unsigned int o = k * 32 + lane;
             if (o < valid) {
                 unsigned int slot = (unsigned int)(slot0 + o);
