@@ -194,15 +194,27 @@ __device__ __forceinline__ void nested_top_level(const NestedPrefixes& nb, Devic
     }
 }
 
-// several GPUs: collect every other shard's section records (the caller then runs the top level)
+// several GPUs: collect every other shard's section records (the caller then runs the top level).  The records are PULLED:
+// every rank publishes its own in its own mailbox and the readers poll them over NVLink -- a kernel that stores into
+// another GPU's memory cannot complete before those stores are acknowledged (~4 us at every kernel boundary), a kernel
+// that only loads has nothing to wait for.
 __device__ __forceinline__ void collect_section_records(const PeerTable& p, long long epoch, const NestedPrefixes& nb) {
-    Mailbox* mb = p.mail[p.rank];
     SpinGuard g(p);
     for (unsigned int sg = threadIdx.x; sg < nb.n_sec_global; sg += kScanThreads) {
         if (sg - nb.sec0 < nb.n_sec) continue;   // own sections: already in place
-        nb.sec_E[sg] = (int)(unsigned int)ll_read64(&mb->sec_ll[sg][0], (unsigned int)epoch, g);
-        nb.sec_T[sg] = ll_read64(&mb->sec_ll[sg][2], (unsigned int)epoch, g);
-        nb.sec_sq[sg] = __longlong_as_double((long long)ll_read64(&mb->sec_ll[sg][4], (unsigned int)epoch, g));
+        const volatile unsigned long long* src = p.mail[sg / nb.n_sec]->sec_ll[sg];   // (equal shards of whole sections: the owner of global section sg)
+        unsigned long long w[6];
+        for (;;) {   // all six tagged words in flight together: one NVLink round trip per poll
+#pragma unroll
+            for (int k = 0; k < 6; ++k) w[k] = src[k];
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ok = ok && (unsigned int)(w[k] >> 32) == (unsigned int)epoch;
+            if (ok || g.give_up()) break;
+        }
+        nb.sec_E[sg] = (int)(unsigned int)w[0];
+        nb.sec_T[sg] = (w[2] & 0xffffffffull) | (w[3] << 32);
+        nb.sec_sq[sg] = __longlong_as_double((long long)((w[4] & 0xffffffffull) | (w[5] << 32)));
     }
     __threadfence();
     __syncthreads();
@@ -294,8 +306,8 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
         const unsigned int tile = sec * kTilesPerSection + lane;
         if (tile < num_tiles) nb.tile_pre[tile] = incl - v;
         const unsigned long long T_s = __shfl_sync(0xffffffffu, incl, 31);
-        if (a.peer.world > 1 && lane < a.peer.world && lane != a.peer.rank) {   // the record goes to every other rank right away
-            unsigned long long* dst = a.peer.mail[lane]->sec_ll[sg];
+        if (a.peer.world > 1 && lane == 0) {   // published in this GPU's own mailbox (tagged words); the other ranks read it from there
+            unsigned long long* dst = a.peer.mail[a.peer.rank]->sec_ll[sg];
             ll_write64(dst, (unsigned long long)(unsigned int)E_s, (unsigned int)epoch);
             ll_write64(dst + 2, T_s, (unsigned int)epoch);
             ll_write64(dst + 4, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
@@ -389,6 +401,22 @@ __global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<R
     if (c_l < num_chunks) nb.slots[c_l] = out;
 }
 
+// several GPUs, end of the expansion kernel (every thread of every block calls it): once ALL blocks are through, the last
+// one tells every rank that this shard has written every ancestor it owes.  Blocks that stored into another GPU's array
+// make those stores visible system-wide first; the ticket orders everything else.
+__device__ __forceinline__ void nested_signal_done(const PeerTable& peer, DeviceStats* st, long long epoch, bool remote) {
+    const int any_remote = __syncthreads_or(remote ? 1 : 0);
+    if (threadIdx.x == 0) {
+        if (any_remote) __threadfence_system(); else __threadfence();
+        if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) {
+            st->ticket = 0;
+            __threadfence();
+            st->trace[8] = global_ns();
+            for (int h = 0; h < peer.world; ++h) *(volatile long long*)&peer.mail[h]->flag_done[peer.rank] = epoch;
+        }
+    }
+}
+
 // ---- expansion (level 2): one block per tile, one warp per 4 chunks; warps never meet ---------------------------------------
 template <typename Real>
 __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
@@ -421,8 +449,10 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
     pdl_wait();
     pdl_trigger();
     if (tile == 0 && tid == 0) st->trace[11] = global_ns();
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
     if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the level-1 pass)
         for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
+        if (a.peer.world > 1) nested_signal_done(a.peer, st, epoch, false);
         return;
     }
     const unsigned long long word = st->rand_word;
@@ -465,24 +495,16 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
         }
     }
     const unsigned int total = we - ws;
-    if (total == 0u) return;
-    if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
-    // (heavy warp tiles are expanded by the owning warp alone in this scheme)
-    const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile + warp * kWarpTile) - 1;
-    // n[][] counts from 0 at the warp tile's first slot
-    for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kNestedWarpSlots)
-        warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
-}
-
-// several GPUs: tells every rank that this shard's expansion kernel has completed (all remote ancestor stores performed)
-static __global__ void peer_done_kernel(PeerTable peer, DeviceStats* st, long long epoch_arg) {
-    pdl_wait();
-    pdl_trigger();
-    if (threadIdx.x == 0) {
-        const long long epoch = epoch_arg < 0 ? st->t : epoch_arg;
-        st->trace[8] = global_ns();
-        for (int h = 0; h < peer.world; ++h) *(volatile long long*)&peer.mail[h]->flag_done[peer.rank] = epoch;
+    bool remote = false;
+    if (total != 0u) {
+        if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
+        // (heavy warp tiles are expanded by the owning warp alone in this scheme)
+        const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile + warp * kWarpTile) - 1;
+        // n[][] counts from 0 at the warp tile's first slot
+        for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kNestedWarpSlots)
+            remote |= warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
     }
+    if (a.peer.world > 1) nested_signal_done(a.peer, st, epoch, remote);
 }
 
 }  // namespace mpl

@@ -339,8 +339,8 @@ template <typename Real>
 static int resample_nested_t(mpl_ps* ps, int phases = 3) {
     int rc = ensure_chunk_records(ps);
     if (rc) return rc;
-    if (ps->world > 1 && ((ps->n % kSection) || (ps->gid_offset % kSection)))
-        return fail(MPL_ERR_UNSUPPORTED, "nested scheme, sharded: shards must be whole sections (multiples of 131072 particles)");
+    if (ps->world > 1 && ((ps->n % kSection) || (ps->gid_offset % kSection) || ps->n * (uint64_t)ps->world != ps->n_global))
+        return fail(MPL_ERR_UNSUPPORTED, "nested scheme, sharded: equal shards of whole sections (multiples of 131072 particles)");
     const size_t n_sec_global = (ps->n_global + kSection - 1) / kSection;
     if (n_sec_global > (size_t)kMaxSections) return fail(MPL_ERR_UNSUPPORTED, "nested scheme: at most 2^28 particles");
     FixedArgs<Real> a = fixed_args<Real>(ps, false, false);
@@ -367,10 +367,6 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3) {
     if (phases & 2) {
         ScopedLaunch sl(ps, "nested_scan");
         pdl_launch(nested_scan_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
-    }
-    if ((phases & 2) && ps->world > 1) {   // "every ancestor I owe is written", once the expansion kernel has completed
-        ScopedLaunch sl(ps, "peer_done");
-        pdl_launch(peer_done_kernel, 1, 32, ps->stream, a.peer, ps->stats, a.epoch);
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (phases & 1) ps->prequantised = false;

@@ -79,7 +79,7 @@ __device__ __forceinline__ void warp_tile_counts(unsigned long long wp, const un
 // One warp expands slots [chunk_lo, chunk_lo + CAP) of its own range [0, total) (relative to ws).  CAP = 32 * (slots per
 // lane), a multiple of 256: `head` holds CAP 16-bit entries.
 template <typename Real, int CAP = kWarpChunk>
-__device__ __forceinline__ void warp_expand_chunk(const FixedArgs<Real>& a, unsigned short* head, const unsigned int (&n)[4][4], unsigned int ws,
+__device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsigned short* head, const unsigned int (&n)[4][4], unsigned int ws,
                                                   unsigned int total, unsigned int chunk_lo, unsigned long long slot_base /* global slot of ws */,
                                                   int32_t src0 /* value for local element 0, minus 1 */) {
     constexpr int PER_LANE = CAP / 32, VEC = PER_LANE / 8;   // uint4 = 8 entries
@@ -127,7 +127,8 @@ __device__ __forceinline__ void warp_expand_chunk(const FixedArgs<Real>& a, unsi
     __syncwarp();
     const unsigned int valid = min((unsigned int)CAP, total - chunk_lo);
     const unsigned long long slot0 = slot_base + chunk_lo;
-    if (slot0 >= a.out_base && slot0 + valid <= a.out_base + a.n_out_local) {   // whole chunk lands in this shard (always, on one GPU)
+    const bool local = slot0 >= a.out_base && slot0 + valid <= a.out_base + a.n_out_local;   // whole chunk lands in this shard (always, on one GPU)
+    if (local) {
         int32_t* dst = a.anc + (slot0 - a.out_base);
 #pragma unroll
         for (int k = 0; k < CAP / 32; ++k) {
@@ -146,6 +147,7 @@ __device__ __forceinline__ void warp_expand_chunk(const FixedArgs<Real>& a, unsi
         }
     }
     __syncwarp();
+    return !local;   // stores went to another GPU's array
 }
 
 template <typename Real, bool STORED>

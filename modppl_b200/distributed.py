@@ -139,7 +139,7 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
     t_prof = t_first + K
     for k in range(min(K, len(ys) - t_prof)):
         ps.step_resample(ys[t_prof + k], scheme, sync=False)
-    prof = {k: ps.profile_get(k) for k in ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "nested_quantise", "nested_sections", "nested_level1", "nested_scan", "peer_done")}
+    prof = {k: ps.profile_get(k) for k in ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "nested_quantise", "nested_sections", "nested_level1", "nested_scan")}
     ps.profile_enable(False)
     kernel_ms = {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}
     err = ps.peer_error()
