@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 LOG2_PARTICLES = 24
 BYTES_PER_PARTICLE_STEP = 48      # 2*D*s + 2*w + 8 with D = 4, s = w = 4
 EXTEND_BYTES_PER_PARTICLE = 40    # ancestor 4 + parent state 16 + child state 16 + log-weight 4
-EXTEND_DRAM_BYTES_NCU = 626915072  # measured DRAM traffic of one extend launch at N = 2^24 (profiles/README.md)
+EXTEND_DRAM_BYTES_NCU = 571104000   # dram__bytes_read.sum + dram__bytes_write.sum of one pf_extend_kernel<.., GATHER, NESTED> launch at N = 2^24 (profiles/r1_ncu_summary_nested.txt)
 
 
 def observations(T, seed=4):
@@ -187,9 +187,9 @@ def run_ours(args):
                 "note": "mpl_ps_step_resample(host obs -> host log total weight) per step; particles stay in HBM by design"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "pf_extend_kernel<Lgssm4<float>, GATHER>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": EXTEND_DRAM_BYTES_NCU if args.log2_particles == 24 else None, "peak_source": peak_src, "algorithmic_bytes_per_particle": EXTEND_BYTES_PER_PARTICLE,
-                     "algorithmic_bytes_per_launch": EXTEND_BYTES_PER_PARTICLE * n_global, "traffic_source": "profiles/r1_ncu_summary_final.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+        "roofline": {"bound": "hbm", "kernel": "pf_extend_kernel<Lgssm4<float>, GATHER" + (", NESTED>" if args.scheme == "nested" else ">"), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": EXTEND_DRAM_BYTES_NCU if (args.log2_particles == 24 and args.scheme == "nested") else None, "peak_source": peak_src, "algorithmic_bytes_per_particle": EXTEND_BYTES_PER_PARTICLE,
+                     "algorithmic_bytes_per_launch": EXTEND_BYTES_PER_PARTICLE * n_global, "traffic_source": "profiles/r1_ncu_summary_nested.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch; nested scheme)",
                      "whole_step": {"bytes_per_particle": BYTES_PER_PARTICLE_STEP, "achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0},
                      "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}},
         "cpu_baseline": base,
