@@ -417,19 +417,10 @@ __device__ __forceinline__ void nested_signal_done(const PeerTable& peer, Device
     }
 }
 
-// ---- expansion (level 2): one block per tile, one warp per 4 chunks; warps never meet ---------------------------------------
+// The lane's 16 integer weights of a warp tile (round r == chunk 4*warp + r of the tile) and their exclusive prefixes
 template <typename Real>
-__global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
-                                                                      unsigned int num_chunks) {
-    __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    DeviceStats* st = a.stats;
-    const unsigned int tile = blockIdx.x;
-    // The integer weights and chunk records come from the kernel before the section pass, and this grid is only released
-    // once every block of the two small passes in between is past its own dependency wait -- so they are complete and
-    // visible already: load them (and do the warp-local scans) before waiting for the level-1 pass' slot ranges.
-    const size_t wt_base = (size_t)tile * kScanTile + (size_t)warp * kWarpTile;
-    unsigned int q[4][4], excl[4];
+__device__ __forceinline__ void nested_load_warp_tile(const FixedArgs<Real>& a, size_t wt_base, unsigned int (&q)[4][4], unsigned int (&excl)[4]) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const size_t idx = wt_base + (size_t)r * kChunk + (size_t)lane * 4;
@@ -443,23 +434,16 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
             }
         } else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0u; }
     }
-    const unsigned int c_w = tile * kChunksPerTile + 4 * warp + (lane & 3);   // this warp's 4 chunks (lanes 0..3 hold them)
-    const unsigned int S_w = c_w < num_chunks ? rec.S[c_w] : 0u;
     chunk_exclusive_prefixes(q, excl);
-    pdl_wait();
-    pdl_trigger();
-    if (tile == 0 && tid == 0) st->trace[11] = global_ns();
-    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-    if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the level-1 pass)
-        for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
-        if (a.peer.world > 1) nested_signal_done(a.peer, st, epoch, false);
-        return;
-    }
-    const unsigned long long word = st->rand_word;
-    const uint2 slot_w = c_w < num_chunks ? nb.slots[c_w] : make_uint2(0u, 0u);
-    // round r of the lane's 16 particles == chunk 4*warp + r
-    unsigned int n[4][4];
-    const unsigned int ws = __shfl_sync(0xffffffffu, slot_w.x, 0);
+}
+
+// Level 2 for one warp tile: inclusive offspring counts n[r][j] of the lane's 16 particles, counted from the warp tile's
+// first output slot `ws` (global); returns the number of slots the warp tile owns.
+template <typename Real>
+__device__ __forceinline__ unsigned int nested_warp_tile_counts(const FixedArgs<Real>& a, unsigned int tile, int warp, uint2 slot_w, unsigned int S_w,
+                                                               unsigned long long word, const unsigned int (&q)[4][4], const unsigned int (&excl)[4],
+                                                               unsigned int (&n)[4][4], unsigned int& ws) {
+    ws = __shfl_sync(0xffffffffu, slot_w.x, 0);
     unsigned int we = ws;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -472,7 +456,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
             continue;
         }
         we += n_c;
-        // level 2: local slot l sits at l*S_c + U_c; particle with inclusive chunk prefix C owns the slots below C*n_c
+        // local slot l sits at l*S_c + U_c; particle with inclusive chunk prefix C owns the slots below C*n_c
         const unsigned long long chunk_gid = ((unsigned long long)a.out_base / kChunk) + (unsigned long long)tile * kChunksPerTile + 4 * warp + r;
         const unsigned int rem_c = S_c - (unsigned int)nested_chunk_offset(word, chunk_gid, (unsigned long long)S_c) - 1u;
         unsigned int C = excl[r];
@@ -494,15 +478,81 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
             }
         }
     }
-    const unsigned int total = we - ws;
+    return we - ws;
+}
+
+struct NestedHeavyEntry { unsigned int tile, warp; };
+
+// ---- expansion (level 2): one block per tile, one warp per 4 chunks; warps never meet ---------------------------------------
+template <typename Real>
+__global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
+                                                                      unsigned int num_chunks, NestedHeavyEntry* heavy) {
+    __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DeviceStats* st = a.stats;
+    const unsigned int tile = blockIdx.x;
+    // The integer weights and chunk records come from the kernel before the section pass, and this grid is only released
+    // once every block of the two small passes in between is past its own dependency wait -- so they are complete and
+    // visible already: load them (and do the warp-local scans) before waiting for the level-1 pass' slot ranges.
+    unsigned int q[4][4], excl[4];
+    nested_load_warp_tile<Real>(a, (size_t)tile * kScanTile + (size_t)warp * kWarpTile, q, excl);
+    const unsigned int c_w = tile * kChunksPerTile + 4 * warp + (lane & 3);   // this warp's 4 chunks (lanes 0..3 hold them)
+    const unsigned int S_w = c_w < num_chunks ? rec.S[c_w] : 0u;
+    pdl_wait();
+    pdl_trigger();
+    if (tile == 0 && tid == 0) st->trace[11] = global_ns();
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    const bool signal_here = a.peer.world > 1 && !a.overflow_follows;   // else the heavy-tile pass signals
+    if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the level-1 pass)
+        for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
+        if (signal_here) nested_signal_done(a.peer, st, epoch, false);
+        return;
+    }
+    const uint2 slot_w = c_w < num_chunks ? nb.slots[c_w] : make_uint2(0u, 0u);
+    unsigned int n[4][4], ws;
+    const unsigned int total = nested_warp_tile_counts<Real>(a, tile, warp, slot_w, S_w, st->rand_word, q, excl, n, ws);
     bool remote = false;
-    if (total != 0u) {
+    if (total > kWarpHeavyCap && a.overflow_follows) {   // a few particles own a large share of the offspring: the whole grid expands this warp tile
+        if (lane == 0) heavy[atomicAdd(&st->overflow_count, 1u)] = NestedHeavyEntry{tile, (unsigned int)warp};
+    } else if (total != 0u) {
+        // no heavy-tile pass was launched for this step (none had been needed so far): the warp expands alone, and the raised
+        // host word makes every later step launch the pass
         if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
-        // (heavy warp tiles are expanded by the owning warp alone in this scheme)
         const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile + warp * kWarpTile) - 1;
         // n[][] counts from 0 at the warp tile's first slot
         for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kNestedWarpSlots)
             remote |= warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
+    }
+    if (signal_here) nested_signal_done(a.peer, st, epoch, remote);
+}
+
+// ---- heavy warp tiles: every warp of the grid recomputes the tile's counts (512 particles) and expands its share of the passes.
+// Launched only once a heavy tile has been seen (host-mapped flag), like the single-level scheme's overflow pass.
+template <typename Real>
+__global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_chunks,
+                                                                    const NestedHeavyEntry* heavy) {
+    __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
+    DeviceStats* st = a.stats;
+    pdl_wait();
+    pdl_trigger();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    const unsigned int count = st->overflow_count;
+    bool remote = false;
+    if (count != 0u && st->W != 0ull) {
+        const unsigned int gw = blockIdx.x * (kScanThreads / 32) + warp, nw = gridDim.x * (kScanThreads / 32);
+        for (unsigned int k = 0; k < count; ++k) {
+            const NestedHeavyEntry e = heavy[k];
+            unsigned int q[4][4], excl[4], n[4][4], ws;
+            nested_load_warp_tile<Real>(a, (size_t)e.tile * kScanTile + (size_t)e.warp * kWarpTile, q, excl);
+            const unsigned int c_w = e.tile * kChunksPerTile + 4 * e.warp + (lane & 3);
+            const unsigned int S_w = c_w < num_chunks ? rec.S[c_w] : 0u;
+            const uint2 slot_w = c_w < num_chunks ? nb.slots[c_w] : make_uint2(0u, 0u);
+            const unsigned int total = nested_warp_tile_counts<Real>(a, e.tile, (int)e.warp, slot_w, S_w, st->rand_word, q, excl, n, ws);
+            const int32_t src0 = a.src_base + (int32_t)(e.tile * (unsigned int)kScanTile + e.warp * kWarpTile) - 1;
+            for (unsigned long long chunk_lo = (unsigned long long)gw * kNestedWarpSlots; chunk_lo < total; chunk_lo += (unsigned long long)nw * kNestedWarpSlots)
+                remote |= warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, (unsigned int)chunk_lo, (unsigned long long)ws, src0);
+        }
     }
     if (a.peer.world > 1) nested_signal_done(a.peer, st, epoch, remote);
 }

@@ -344,6 +344,7 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3) {
     const size_t n_sec_global = (ps->n_global + kSection - 1) / kSection;
     if (n_sec_global > (size_t)kMaxSections) return fail(MPL_ERR_UNSUPPORTED, "nested scheme: at most 2^28 particles");
     FixedArgs<Real> a = fixed_args<Real>(ps, false, false);
+    a.overflow_follows = ps->host_flags[0] != 0 ? 1 : 0;   // the heavy-tile pass runs only once a heavy warp tile has been seen
     ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
     unsigned long long* sec = ps->nest_sec;
     NestedPrefixes nb{ps->nest_tile_pre, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
@@ -366,7 +367,11 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3) {
     }
     if (phases & 2) {
         ScopedLaunch sl(ps, "nested_scan");
-        pdl_launch(nested_scan_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
+        pdl_launch(nested_scan_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks, (NestedHeavyEntry*)ps->overflow);
+    }
+    if ((phases & 2) && a.overflow_follows) {
+        ScopedLaunch sl(ps, "nested_heavy");
+        pdl_launch(nested_heavy_kernel<Real>, kNumSMs * 2, kScanThreads, ps->stream, a, rec, nb, num_chunks, (const NestedHeavyEntry*)ps->overflow);
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (phases & 1) ps->prequantised = false;

@@ -571,12 +571,11 @@ def test_nested_fused_epilogue_equals_standalone_quantisation():
     assert abs(a.log_marginal_likelihood_estimate() - truth) < 1.0
 
 
-@pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("dtype", ["f32", "f64"])
+@pytest.mark.parametrize("world,dtype", [(2, "f32"), (4, "f32"), (8, "f32"), (2, "f64"), (4, "f64")])
 def test_virtual_shards_nested_scheme_reproduces_single_gpu(world, dtype):
     # the nested scheme's only exchange is one record per 2^17-particle section; sections are groups of global ids, so
     # the sharded run (fused quantisation in the extend kernel for f32) equals the unsharded one bit for bit
-    n, T = 1 << 19, 5
+    n, T = (1 << 20) if world == 8 else (1 << 19), 5
     ys = lgssm_data(T)
     st, lw, lml = m.parity.virtual_shards(m.lgssm4(), n, world, ys, dtype=dtype, seed=29, scheme=m.SYSTEMATIC_NESTED)
     one = m.ParticleSystem(m.lgssm4(), n, seed=29, dtype=dtype)
@@ -611,3 +610,41 @@ def test_step_resample_call_equals_the_two_calls(scheme):
         assert np.array_equal(a.parents, b.parents)
     assert np.array_equal(a.traces, b.traces)
     assert a.log_marginal_likelihood_estimate() == b.log_marginal_likelihood_estimate()
+
+
+def test_nested_heavy_warp_tiles_go_through_the_whole_grid_pass():
+    # a few particles own nearly all offspring: the first such resample is expanded by the owning warps alone and raises a
+    # host-visible flag; from then on the whole-grid pass for heavy warp tiles is launched -- both must match the oracle
+    n = 1 << 20
+    params, gen = MODELS["lgssm4"]
+    ys = gen(4)
+    ps = m.ParticleSystem(m.lgssm4(*params), n, seed=5, dtype="f32")
+    ref = O.OraclePS("lgssm4", params, n, dtype="f32", seed=5)
+    ps.init_step(ys[0]); ref.init_step(ys[0])
+    rng = np.random.default_rng(1)
+    for t in range(1, 4):
+        lw = rng.normal(size=n) - 40.0
+        lw[[12345, 700000 + t, n - 1]] = [0.0, -0.7, -1.3]          # three particles share ~all of the 2^20 slots
+        ps.write_state(ref.traces); ps.write_log_weights(lw); ref.write_log_weights(lw)
+        lse, ref_lse = ps.resample(m.SYSTEMATIC_NESTED), ref.resample(4)
+        assert abs(lse - ref_lse) <= 2e-6 * max(1.0, abs(ref_lse))
+        par = ps.parents
+        assert np.array_equal(par, ref.parents), t
+        assert np.bincount(par, minlength=n)[12345] > n // 3
+        ps.step(ys[t]); ref.step(ys[t])
+
+
+def test_nested_device_loop_fp64_equals_call_per_step():
+    # fp64 keeps the stand-alone quantisation kernel inside the device-resident loop (the fused epilogue is fp32 only)
+    T, n = 8, 50000
+    ys = lgssm_data(T)
+    a = m.ParticleSystem(m.lgssm4(), n, seed=6, dtype="f64")
+    a.upload_observations(ys)
+    a.run(0, T, m.SYSTEMATIC_NESTED)
+    b = m.ParticleSystem(m.lgssm4(), n, seed=6, dtype="f64")
+    b.init_step(ys[0]); b.resample(m.SYSTEMATIC_NESTED)
+    for y in ys[1:]:
+        b.step(y); b.resample(m.SYSTEMATIC_NESTED)
+    assert a.log_marginal_likelihood_estimate() == b.log_marginal_likelihood_estimate()
+    assert np.array_equal(a.parents, b.parents) and np.array_equal(a.traces, b.traces)
+    assert a.num_resamples() == T
