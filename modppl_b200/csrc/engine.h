@@ -63,7 +63,7 @@ struct mpl_ps {
     // per-step states and ancestors, back-traced on demand
     int* rec_e; unsigned int* rec_S; float* rec_sq;   // chunk records of the nested scheme (ld / 128 entries), lazily allocated
     unsigned long long* nest_tile_pre; unsigned long long* nest_sec; void* nest_slots;   // nested scheme: tile prefixes inside a section; section records + top-level prefixes
-    bool prequantised;           // the last extend already left integer weights + chunk records (fused epilogue)
+    int prequantised;            // the last extend's fused epilogue left 1: integer weights + chunk records, 2: chunk records only (log-weights kept)
     void* hist_state;            // [hist_cap][D][ld] Real
     int32_t* hist_anc;           // [hist_cap][ld]
     size_t hist_cap;

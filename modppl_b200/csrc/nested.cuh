@@ -45,7 +45,8 @@ __device__ __forceinline__ unsigned long long warp_sum_u48(unsigned long long v)
 }
 
 // ---- stand-alone quantisation pass (call-per-step API; the device-resident loop fuses this into the extend kernel) -----
-template <typename Real>
+// KEEP: only the chunk records are written, the log-weights stay (ESS-triggered loop: the resample may be skipped)
+template <typename Real, bool KEEP>
 __global__ void __launch_bounds__(kScanThreads) nested_quantise_kernel(FixedArgs<Real> a, ChunkRecords rec) {
     pdl_wait();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -64,8 +65,10 @@ __global__ void __launch_bounds__(kScanThreads) nested_quantise_kernel(FixedArgs
         float sq;
         int e_c;
         warp_quantise_chunk(w, qv, e_c, S_c, sq);
-        if constexpr (sizeof(Real) == 4) *reinterpret_cast<float4*>(a.lw + idx) = make_float4(nested_store<float>(qv[0]), nested_store<float>(qv[1]), nested_store<float>(qv[2]), nested_store<float>(qv[3]));
-        else { *reinterpret_cast<double2*>(a.lw + idx) = make_double2((double)qv[0], (double)qv[1]); *reinterpret_cast<double2*>(a.lw + idx + 2) = make_double2((double)qv[2], (double)qv[3]); }
+        if constexpr (!KEEP) {
+            if constexpr (sizeof(Real) == 4) *reinterpret_cast<float4*>(a.lw + idx) = make_float4(nested_store<float>(qv[0]), nested_store<float>(qv[1]), nested_store<float>(qv[2]), nested_store<float>(qv[3]));
+            else { *reinterpret_cast<double2*>(a.lw + idx) = make_double2((double)qv[0], (double)qv[1]); *reinterpret_cast<double2*>(a.lw + idx + 2) = make_double2((double)qv[2], (double)qv[3]); }
+        }
         if (lane == 0) { rec.e[chunk] = e_c; rec.S[chunk] = S_c; rec.sq[chunk] = sq; }
     }
     pdl_trigger();
@@ -97,7 +100,7 @@ struct NestedTopShared {
 // the slots [a_s, a_s + n_s)) from the section records.  Written for latency: with up to 1024 sections (2^27 particles)
 // every thread loads its 4 records once and everything else stays in registers.
 __device__ __forceinline__ void nested_top_level(const NestedPrefixes& nb, DeviceStats* st, NestedTopShared& sh, uint64_t seed, long long rt,
-                                                 unsigned long long n_out) {
+                                                 unsigned long long n_out, int dynamic, double ess_threshold) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n_sec = nb.n_sec_global;
     if (tid == 0) sh.carry = 0ull;
@@ -190,7 +193,9 @@ __device__ __forceinline__ void nested_top_level(const NestedPrefixes& nb, Devic
         for (int i = 0; i < kScanThreads / 32; ++i) sq += sh.wsq[i];
         st->W = W; st->c_offset = 0; st->nest_E = E; st->rand_word = word;
         st->sumexp2 = sq;
-        st->ess = sq > 0. ? ((double)W * (double)W) / sq : 0.;
+        const double ess = sq > 0. ? ((double)W * (double)W) / sq : 0.;
+        st->ess = ess;
+        if (dynamic) st->do_resample = (ess < ess_threshold) ? 1 : 0;   // ESS trigger, decided where the numbers are
     }
 }
 
@@ -258,7 +263,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     if (blockIdx.x == 0 && tid == 0) st->trace[9] = global_ns();
     if constexpr (PHASES == 2) {
         if (a.peer.world > 1) { if (tid == 0) st->trace[6] = global_ns(); collect_section_records(a.peer, epoch, nb); }
-        nested_top_level(nb, st, top, a.seed, a.rt, a.n_out);
+        nested_top_level(nb, st, top, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
         if (tid == 0) st->trace[7] = global_ns();
         return;
     }
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     if (tid == 0) { st->overflow_count = 0; st->blocks_done = 0; st->trace[5] = global_ns(); }
     if constexpr (PHASES == 3) {
         if (a.peer.world > 1) { if (tid == 0) st->trace[6] = global_ns(); collect_section_records(a.peer, epoch, nb); }
-        nested_top_level(nb, st, top, a.seed, a.rt, a.n_out);
+        nested_top_level(nb, st, top, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
         if (tid == 0) st->trace[7] = global_ns();
     }
 }
@@ -380,6 +385,10 @@ __global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<R
     if (tile < num_tiles && c_l < num_chunks) { S_l = rec.S[c_l]; e_l = rec.e[c_l]; }   // (written two kernels ago: complete)
     pdl_wait();
     pdl_trigger();   // the expansion kernel may become resident and load its weights
+    if (a.dynamic && !st->do_resample) {   // ESS above the threshold: keep the population, weights keep accumulating
+        if (blockIdx.x == 0 && tid == 0) st->resampled_flag[(a.epoch < 0 ? st->t : a.epoch) & 1] = 0;
+        return;
+    }
     if (blockIdx.x == 0 && tid == 0) { st->trace[10] = global_ns(); nested_bookkeeping(a, st, a.epoch < 0 ? st->t : a.epoch); }
     const unsigned long long W = st->W;
     if (tile >= num_tiles || W == 0ull) return;
@@ -417,13 +426,32 @@ __device__ __forceinline__ void nested_signal_done(const PeerTable& peer, Device
     }
 }
 
-// The lane's 16 integer weights of a warp tile (round r == chunk 4*warp + r of the tile) and their exclusive prefixes
-template <typename Real>
-__device__ __forceinline__ void nested_load_warp_tile(const FixedArgs<Real>& a, size_t wt_base, unsigned int (&q)[4][4], unsigned int (&excl)[4]) {
+// The lane's 16 integer weights of a warp tile (round r == chunk 4*warp + r of the tile) and their exclusive prefixes.
+// RECOMPUTE: the array still holds the log-weights (ESS-triggered loop); the integer weights are re-derived from them and the
+// chunk's reference e_c exactly as the quantisation did.
+template <typename Real, bool RECOMPUTE>
+__device__ __forceinline__ void nested_load_warp_tile(const FixedArgs<Real>& a, const ChunkRecords& rec, unsigned int num_chunks, size_t wt_base,
+                                                      unsigned int (&q)[4][4], unsigned int (&excl)[4]) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const size_t idx = wt_base + (size_t)r * kChunk + (size_t)lane * 4;
+        if constexpr (RECOMPUTE) {
+            const size_t c = wt_base / kChunk + r;
+            const int e_c = c < num_chunks ? rec.e[c] : kChunkEmpty;
+            float w[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (idx < a.n) {
+                if constexpr (sizeof(Real) == 4) { const float4 v = *reinterpret_cast<const float4*>(a.lw + idx); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+                else { const double2 u = *reinterpret_cast<const double2*>(a.lw + idx), v = *reinterpret_cast<const double2*>(a.lw + idx + 2); w[0] = (float)u.x; w[1] = (float)u.y; w[2] = (float)v.x; w[3] = (float)v.y; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float qf;
+                const bool live = e_c != kChunkEmpty && idx + j < a.n;
+                q[r][j] = live ? nested_weight(__fmul_rn(w[j], 1.44269504088896341f), (float)e_c, &qf) : 0u;
+            }
+            continue;
+        }
         if (idx < a.n) {   // (chunks are quantised whole: entries past n inside the last chunk hold 0)
             if constexpr (sizeof(Real) == 4) {
                 const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.lw + idx));   // last use; the integers' bit patterns
@@ -484,7 +512,7 @@ __device__ __forceinline__ unsigned int nested_warp_tile_counts(const FixedArgs<
 struct NestedHeavyEntry { unsigned int tile, warp; };
 
 // ---- expansion (level 2): one block per tile, one warp per 4 chunks; warps never meet ---------------------------------------
-template <typename Real>
+template <typename Real, bool RECOMPUTE>
 __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
                                                                       unsigned int num_chunks, NestedHeavyEntry* heavy) {
     __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
@@ -495,12 +523,13 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
     // once every block of the two small passes in between is past its own dependency wait -- so they are complete and
     // visible already: load them (and do the warp-local scans) before waiting for the level-1 pass' slot ranges.
     unsigned int q[4][4], excl[4];
-    nested_load_warp_tile<Real>(a, (size_t)tile * kScanTile + (size_t)warp * kWarpTile, q, excl);
+    nested_load_warp_tile<Real, RECOMPUTE>(a, rec, num_chunks, (size_t)tile * kScanTile + (size_t)warp * kWarpTile, q, excl);
     const unsigned int c_w = tile * kChunksPerTile + 4 * warp + (lane & 3);   // this warp's 4 chunks (lanes 0..3 hold them)
     const unsigned int S_w = c_w < num_chunks ? rec.S[c_w] : 0u;
     pdl_wait();
     pdl_trigger();
     if (tile == 0 && tid == 0) st->trace[11] = global_ns();
+    if (a.dynamic && !st->do_resample) return;   // ESS above the threshold (the level-1 pass cleared the step's flag)
     const long long epoch = a.epoch < 0 ? st->t : a.epoch;
     const bool signal_here = a.peer.world > 1 && !a.overflow_follows;   // else the heavy-tile pass signals
     if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the level-1 pass)
@@ -528,7 +557,7 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
 
 // ---- heavy warp tiles: every warp of the grid recomputes the tile's counts (512 particles) and expands its share of the passes.
 // Launched only once a heavy tile has been seen (host-mapped flag), like the single-level scheme's overflow pass.
-template <typename Real>
+template <typename Real, bool RECOMPUTE>
 __global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_chunks,
                                                                     const NestedHeavyEntry* heavy) {
     __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
@@ -536,6 +565,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Re
     pdl_wait();
     pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (a.dynamic && !st->do_resample) return;
     const long long epoch = a.epoch < 0 ? st->t : a.epoch;
     const unsigned int count = st->overflow_count;
     bool remote = false;
@@ -544,7 +574,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Re
         for (unsigned int k = 0; k < count; ++k) {
             const NestedHeavyEntry e = heavy[k];
             unsigned int q[4][4], excl[4], n[4][4], ws;
-            nested_load_warp_tile<Real>(a, (size_t)e.tile * kScanTile + (size_t)e.warp * kWarpTile, q, excl);
+            nested_load_warp_tile<Real, RECOMPUTE>(a, rec, num_chunks, (size_t)e.tile * kScanTile + (size_t)e.warp * kWarpTile, q, excl);
             const unsigned int c_w = e.tile * kChunksPerTile + 4 * e.warp + (lane & 3);
             const unsigned int S_w = c_w < num_chunks ? rec.S[c_w] : 0u;
             const uint2 slot_w = c_w < num_chunks ? nb.slots[c_w] : make_uint2(0u, 0u);

@@ -121,7 +121,7 @@ static int grid_for(size_t work_items, int per_block, int max_blocks) {
 
 // ---- extend dispatch ----------------------------------------------------------------------------------------
 template <class Model, typename Real>
-static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& obs, bool from_dev_obs, bool dev_t, bool nested = false) {
+static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& obs, bool from_dev_obs, bool dev_t, int nested = 0) {
     ExtendArgs<Real> a;
     a.state_in = (const Real*)ps->state[ps->cur];
     a.state_out = (Real*)ps->state[mode == EXT_INIT || mode == EXT_ACCUM ? ps->cur : ps->cur ^ 1];
@@ -145,13 +145,22 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     {
         ScopedLaunch sl(ps, mode == EXT_INIT ? "init" : "extend");
         if constexpr (sizeof(Real) == 4) {
-            if (nested && (mode == EXT_INIT || mode == EXT_GATHER)) {   // fused per-chunk quantisation (nested scheme, device-resident loop)
-                if (mode == EXT_INIT) pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false, true>, grid, kExtendThreads, ps->stream, a, model);
-                else if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, true, true>, grid, kExtendThreads, ps->stream, a, model);
-                else pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, false, true>, grid, kExtendThreads, ps->stream, a, model);
+            if (nested == 1 && (mode == EXT_INIT || mode == EXT_GATHER)) {   // fused per-chunk quantisation (nested scheme, device-resident loop)
+                if (mode == EXT_INIT) pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false, 1>, grid, kExtendThreads, ps->stream, a, model);
+                else if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, true, 1>, grid, kExtendThreads, ps->stream, a, model);
+                else pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, false, 1>, grid, kExtendThreads, ps->stream, a, model);
                 MPL_CUDA_OK(cudaGetLastError());
                 if (mode == EXT_GATHER) ps->cur ^= 1;
-                ps->prequantised = true;
+                ps->prequantised = 1;
+                goto extend_done;
+            }
+            if (nested == 2 && (mode == EXT_INIT || mode == EXT_DYNAMIC)) {   // chunk records only; the log-weights stay (ESS-triggered loop)
+                if (mode == EXT_INIT) pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false, 2>, grid, kExtendThreads, ps->stream, a, model);
+                else if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, true, 2>, grid, kExtendThreads, ps->stream, a, model);
+                else pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, false, 2>, grid, kExtendThreads, ps->stream, a, model);
+                MPL_CUDA_OK(cudaGetLastError());
+                if (mode == EXT_DYNAMIC) ps->cur ^= 1;
+                ps->prequantised = 2;
                 goto extend_done;
             }
         }
@@ -170,7 +179,7 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (mode == EXT_GATHER || mode == EXT_DYNAMIC) ps->cur ^= 1;
-    ps->prequantised = false;
+    ps->prequantised = 0;
 extend_done:
     if (ps->hist_cap) {   // trajectory log: the state this step produced (kernel time index ps->t, not yet incremented by the caller)
         const size_t tt = (size_t)ps->t;
@@ -184,7 +193,7 @@ extend_done:
     return MPL_OK;
 }
 
-static int launch_extend(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs, bool dev_t, bool nested = false) {
+static int launch_extend(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs, bool dev_t, int nested = 0) {
     const mpl_model& m = ps->model;
     if (ps->dtype == MPL_F32) {
         switch (m.kind) {
@@ -335,15 +344,16 @@ static int ensure_chunk_records(mpl_ps* ps) {
 }
 
 // phases: 1 = quantise (unless the extend did it) + chunk pass, 2 = expansion (+ the peers' "done" flag); 3 = both
+// dynamic: ESS-triggered (decision on the device; the log-weights survive: quantisation keeps them, the expansion re-quantises)
 template <typename Real>
-static int resample_nested_t(mpl_ps* ps, int phases = 3) {
+static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     int rc = ensure_chunk_records(ps);
     if (rc) return rc;
     if (ps->world > 1 && ((ps->n % kSection) || (ps->gid_offset % kSection) || ps->n * (uint64_t)ps->world != ps->n_global))
         return fail(MPL_ERR_UNSUPPORTED, "nested scheme, sharded: equal shards of whole sections (multiples of 131072 particles)");
     const size_t n_sec_global = (ps->n_global + kSection - 1) / kSection;
     if (n_sec_global > (size_t)kMaxSections) return fail(MPL_ERR_UNSUPPORTED, "nested scheme: at most 2^28 particles");
-    FixedArgs<Real> a = fixed_args<Real>(ps, false, false);
+    FixedArgs<Real> a = fixed_args<Real>(ps, dynamic, false);
     a.overflow_follows = ps->host_flags[0] != 0 ? 1 : 0;   // the heavy-tile pass runs only once a heavy warp tile has been seen
     ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
     unsigned long long* sec = ps->nest_sec;
@@ -351,9 +361,11 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3) {
                       sec + 5 * kMaxSections, sec + 6 * kMaxSections, (uint2*)ps->nest_slots, (unsigned int)(ps->gid_offset / kSection), (unsigned int)((ps->n + kSection - 1) / kSection), (unsigned int)n_sec_global};
     const unsigned int num_tiles = (unsigned int)((ps->n + kScanTile - 1) / kScanTile);
     const unsigned int num_chunks = (unsigned int)((ps->n + kChunk - 1) / kChunk);
+    if (dynamic && ps->prequantised == 1) return fail(MPL_ERR_INVALID, "ESS-triggered nested resampling after a step that dropped the log-weights");
     if ((phases & 1) && !ps->prequantised) {
         ScopedLaunch sl(ps, "nested_quantise");
-        pdl_launch(nested_quantise_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec);
+        if (dynamic) pdl_launch(nested_quantise_kernel<Real, true>, num_tiles, kScanThreads, ps->stream, a, rec);
+        else pdl_launch(nested_quantise_kernel<Real, false>, num_tiles, kScanThreads, ps->stream, a, rec);
     }
     {
         ScopedLaunch sl(ps, "nested_sections");
@@ -367,14 +379,16 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3) {
     }
     if (phases & 2) {
         ScopedLaunch sl(ps, "nested_scan");
-        pdl_launch(nested_scan_kernel<Real>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks, (NestedHeavyEntry*)ps->overflow);
+        if (dynamic) pdl_launch(nested_scan_kernel<Real, true>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks, (NestedHeavyEntry*)ps->overflow);
+        else pdl_launch(nested_scan_kernel<Real, false>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks, (NestedHeavyEntry*)ps->overflow);
     }
     if ((phases & 2) && a.overflow_follows) {
         ScopedLaunch sl(ps, "nested_heavy");
-        pdl_launch(nested_heavy_kernel<Real>, kNumSMs * 2, kScanThreads, ps->stream, a, rec, nb, num_chunks, (const NestedHeavyEntry*)ps->overflow);
+        if (dynamic) pdl_launch(nested_heavy_kernel<Real, true>, kNumSMs * 2, kScanThreads, ps->stream, a, rec, nb, num_chunks, (const NestedHeavyEntry*)ps->overflow);
+        else pdl_launch(nested_heavy_kernel<Real, false>, kNumSMs * 2, kScanThreads, ps->stream, a, rec, nb, num_chunks, (const NestedHeavyEntry*)ps->overflow);
     }
     MPL_CUDA_OK(cudaGetLastError());
-    if (phases & 1) ps->prequantised = false;
+    if (phases & 1) ps->prequantised = 0;
     return MPL_OK;
 }
 
@@ -579,7 +593,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->D = model->state_dim;
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
     ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
-    ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = false;
+    ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = 0;
     ps->nest_tile_pre = nullptr; ps->nest_sec = nullptr; ps->nest_slots = nullptr;
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
@@ -886,7 +900,11 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
     if (first_step > 0 && (long long)first_step != ps->t) return fail(MPL_ERR_INVALID, "first_step must equal the filter's current time index");
     const bool dynamic = ess_threshold > 0.;
     int rc0 = MPL_OK;
-    if (dynamic && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED) return fail(MPL_ERR_UNSUPPORTED, "ESS-triggered device loop: MPL_RESAMPLE_SYSTEMATIC_FIXED only");
+    if (dynamic && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED && scheme != MPL_RESAMPLE_SYSTEMATIC_NESTED)
+        return fail(MPL_ERR_UNSUPPORTED, "ESS-triggered device loop: MPL_RESAMPLE_SYSTEMATIC_FIXED or MPL_RESAMPLE_SYSTEMATIC_NESTED");
+    const bool dyn_nested = dynamic && scheme == MPL_RESAMPLE_SYSTEMATIC_NESTED;
+    const int dyn_records = dyn_nested && ps->dtype == MPL_F32 ? 2 : 0;   // fp32: the extend leaves the chunk records (log-weights kept)
+    if (dyn_nested && (rc0 = ensure_chunk_records(ps))) return rc0;
     if (dynamic && first_step > 0 && !ps->dynamic_state_known) return fail(MPL_ERR_INVALID, "ESS-triggered run must start at step 0 or continue a previous ESS-triggered run");
     MPL_CUDA_OK(cudaSetDevice(ps->device));
     ps->ess_threshold_abs = dynamic ? ess_threshold * (double)ps->n_global : 0.;
@@ -900,18 +918,20 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
         size_t tt = first_step + k;
         if (tt == 0) {
             ps->t = 0; ps->pending_gather = false;
-            rc = launch_extend(ps, EXT_INIT, dummy, true, false, fuse_nested);
+            rc = launch_extend(ps, EXT_INIT, dummy, true, false, fuse_nested ? 1 : dyn_records);
             ps->t = 1; ps->initialised = true; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
         } else if (dynamic) {
             // whether the previous step resampled is only known on the device: the extend reads stats->resampled_flag[t & 1]
-            rc = launch_extend(ps, EXT_DYNAMIC, dummy, true, false);
+            rc = launch_extend(ps, EXT_DYNAMIC, dummy, true, false, dyn_records);
             ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
         } else {
             rc = launch_extend(ps, ps->pending_gather ? EXT_GATHER : EXT_ACCUM, dummy, true, false, fuse_nested);
             ps->pending_gather = false; ps->t += 1; ps->stats_valid = false; ps->max_valid = !ps->prequantised;
         }
         if (rc != MPL_OK) break;
-        if (dynamic) {
+        if (dyn_nested) {
+            rc = ps->dtype == MPL_F32 ? resample_nested_t<float>(ps, 3, true) : resample_nested_t<double>(ps, 3, true);
+        } else if (dynamic) {
             rc = ps->dtype == MPL_F32 ? resample_fixed_t<float>(ps, scheme, true, false) : resample_fixed_t<double>(ps, scheme, true, false);
         } else rc = do_resample(ps, scheme);
     }
@@ -925,7 +945,7 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
     if (rc == MPL_OK && dynamic) {   // learn from the device whether the last step resampled
         if ((rc = fetch_stats(ps))) return rc;
         ps->pending_gather = ps->stats_host->resampled_flag[ps->t & 1] != 0;
-        ps->stats_valid = false; ps->max_valid = !ps->pending_gather;
+        ps->stats_valid = false; ps->max_valid = !ps->pending_gather && !dyn_nested;
         ps->dynamic_state_known = true;
     }
     return rc;

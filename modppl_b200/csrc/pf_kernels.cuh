@@ -175,9 +175,10 @@ struct ExtendArgs {
 constexpr int kExtendThreads = 256;
 
 // NESTED (fp32 only): every warp iteration covers one aligned 128-particle chunk, whose log-weights are quantised on the
-// spot against the chunk's own maximum (nested.cuh) -- the integer weights replace the log-weights in HBM and the
-// reduce pass over the particles disappears.
-template <class Model, typename Real, int MODE, bool SHARDED = false, bool NESTED = false>
+// spot against the chunk's own maximum (nested.cuh) -- the reduce pass over the particles disappears.  NESTED == 1: the
+// integer weights replace the log-weights in HBM (a resample follows for sure); NESTED == 2: only the chunk records are
+// kept and the log-weights stay (ESS-triggered loop: the resample may be skipped, the expansion re-quantises if not).
+template <class Model, typename Real, int MODE, bool SHARDED = false, int NESTED = 0>
 __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs<Real> a, Model model) {
     constexpr int D = Model::D;
     constexpr int V = VecOf<Real>::N;
@@ -278,10 +279,13 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
             int e_c;
             unsigned int S_c;
             warp_quantise_chunk(wm, qv, e_c, S_c, sqc);
-            Real qr[V];   // fp32: the integer's bit pattern takes the log-weight's slot; fp64: its value
+            if constexpr (NESTED == 2) vec_store<Real>(a.lw + base, w);
+            else {
+                Real qr[V];   // fp32: the integer's bit pattern takes the log-weight's slot; fp64: its value
 #pragma unroll
-            for (int v = 0; v < V; ++v) qr[v] = nested_store<Real>(qv[v]);
-            vec_store<Real>(a.lw + base, qr);
+                for (int v = 0; v < V; ++v) qr[v] = nested_store<Real>(qv[v]);
+                vec_store<Real>(a.lw + base, qr);
+            }
             if ((tid & 31) == 0) { const size_t chunk = base / kChunk; a.rec.e[chunk] = e_c; a.rec.S[chunk] = S_c; a.rec.sq[chunk] = sqc; }
         } else {
             vec_store<Real>(a.lw + base, w);

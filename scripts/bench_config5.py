@@ -14,18 +14,18 @@ for t in range(T):
     x = -1.024 + 0.9702 * (x + 1.024) + 0.178 * rng.normal()
     ys.append([math.exp(x / 2) * rng.normal()])
 ys = np.array(ys)
-for log2n in (26, 24):
+for log2n, scheme, name in ((26, m.SYSTEMATIC_NESTED, "nested"), (26, m.SYSTEMATIC_FIXED, "single-level"), (24, m.SYSTEMATIC_NESTED, "nested")):
     n = 1 << log2n
     ps = m.ParticleSystem(m.stochastic_volatility(), n, seed=5, dtype="f32")
     ps.upload_observations(ys)
-    ps.run(0, 20, m.SYSTEMATIC_FIXED, ess_threshold=0.5)
+    ps.run(0, 20, scheme, ess_threshold=0.5)
     r0 = ps.num_resamples()
-    ms = ps.run(20, T - 20, m.SYSTEMATIC_FIXED, ess_threshold=0.5)
+    ms = ps.run(20, T - 20, scheme, ess_threshold=0.5)
     nres = ps.num_resamples() - r0
     steps = T - 20
     # 16 B/particle on steps without a resample, 24 B with (SURVEY 8d, D = 1 fp32)
     bytes_alg = n * (16.0 * (steps - nres) + 24.0 * nres)
-    out[f"sv_2^{log2n}"] = {"ms_per_step": ms / steps, "particle_steps_per_s": n * steps / (ms * 1e-3), "resampled_steps": int(nres), "of": steps,
+    out[f"sv_2^{log2n}_{name}"] = {"ms_per_step": ms / steps, "particle_steps_per_s": n * steps / (ms * 1e-3), "resampled_steps": int(nres), "of": steps,
                             "algorithmic_GBps": bytes_alg / (ms * 1e-3) / 1e9, "frac_of_6504": bytes_alg / (ms * 1e-3) / 1e9 / 6504.1, "lml": ps.log_marginal_likelihood_estimate()}
     ps.close()
 # config 1

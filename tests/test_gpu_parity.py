@@ -400,7 +400,7 @@ def test_parallel_cumsum_bad_inputs_fall_back_to_sequential_semantics():
 
 # ------------------------------------------------------------------------------------------------- ESS-triggered device loop (config 5)
 @pytest.mark.parametrize("dtype", ["f32", "f64"])
-def test_ess_triggered_device_loop_matches_call_per_step(dtype):
+def test_ess_triggered_device_loop_matches_call_per_step(dtype, scheme=2):
     # stochastic-volatility model, systematic resampling when the fresh ESS drops below N/2: the device-resident loop
     # (decision taken on the GPU, nothing copied to the host) against the same policy driven from the host
     T, n = 60, 1 << 15
@@ -412,7 +412,7 @@ def test_ess_triggered_device_loop_matches_call_per_step(dtype):
     ys = np.array(ys)
     dev = m.ParticleSystem(m.stochastic_volatility(), n, seed=9, dtype=dtype)
     dev.upload_observations(ys)
-    dev.run(0, T, m.SYSTEMATIC_FIXED, ess_threshold=0.5)
+    dev.run(0, T, scheme, ess_threshold=0.5)
     host = m.ParticleSystem(m.stochastic_volatility(), n, seed=9, dtype=dtype)
     host.init_step(ys[0])
     n_res = 0
@@ -420,7 +420,7 @@ def test_ess_triggered_device_loop_matches_call_per_step(dtype):
         if t > 0:
             host.step(ys[t])
         if host.effective_sample_size(False) < 0.5 * n:
-            host.resample(m.SYSTEMATIC_FIXED); n_res += 1
+            host.resample(scheme); n_res += 1
     assert 0 < n_res < T                                     # the trigger fires sometimes, not always
     assert dev.num_resamples() == n_res
     a, b = dev.log_marginal_likelihood_estimate(), host.log_marginal_likelihood_estimate()
@@ -433,8 +433,15 @@ def test_ess_triggered_device_loop_matches_call_per_step(dtype):
         if t > 0:
             ref.step(ys[t])
         if ref.effective_sample_size(False) < 0.5 * n:
-            ref.resample(2)
+            ref.resample(scheme)
     assert abs(a - ref.log_marginal_likelihood_estimate()) <= (1e-3 if dtype == "f32" else 1e-6) * abs(a)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_ess_triggered_device_loop_nested_scheme(dtype):
+    # same policy with the nested scheme: the extend kernel leaves only the chunk records (fp32) and keeps the log-weights,
+    # the section pass takes the ESS decision, the expansion re-quantises from the log-weights when it fires
+    test_ess_triggered_device_loop_matches_call_per_step(dtype, scheme=m.SYSTEMATIC_NESTED)
 
 
 # ------------------------------------------------------------------------------------------------- trajectories (next-tier row f.2)
