@@ -35,7 +35,7 @@ constexpr double kPi = 3.14159265358979323846;
 // (reference modppl/src/modeling/dists/distribution.rs:5-7): counter-based, so a draw depends only on
 // (seed, global id, step, purpose, block) and never on which GPU or thread computes it.
 // ------------------------------------------------------------------------------------------------
-enum Purpose : uint32_t { P_MODEL = 0, P_RESAMPLE_U = 1, P_RESAMPLE_OFFSET = 2, P_IS = 3, P_MH = 4, P_IS_RESAMPLE = 5, P_MH_INIT = 6 };
+enum Purpose : uint32_t { P_MODEL = 0, P_RESAMPLE_U = 1, P_RESAMPLE_OFFSET = 2, P_IS = 3, P_MH = 4, P_IS_RESAMPLE = 5, P_MH_INIT = 6, P_MODEL_GROUP = 7 };
 
 __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll

@@ -20,6 +20,7 @@ template <typename Real>
 struct Lgssm4 {
     static constexpr int D = 4;
     static constexpr int NOBS = 2;
+    static constexpr bool kGroupDraws = false;
     Real q, r, x0, ln_r, inv_r, lw_const;   // lw_const = ln 2pi + 2 ln r
     __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
         Real z[4];
@@ -45,6 +46,7 @@ template <typename Real>
 struct Spiral {
     static constexpr int D = 2;
     static constexpr int NOBS = 2;
+    static constexpr bool kGroupDraws = false;
     Real dr_std, dth_mean, dth_std;
     double prec[4], log_norm;   // mvnormal.rs:14-22 with det/inverse hoisted (quirk Q8)
     Real inv_var, log_norm_r;
@@ -79,12 +81,14 @@ template <typename Real>
 struct StochVol {
     static constexpr int D = 1;
     static constexpr int NOBS = 1;
+    // One normal deviate per particle and step: a Philox block (two Box-Muller pairs in fp32, one in fp64) serves the 4 (2)
+    // consecutive particles one thread handles -- stream id = global id / 4 (2), purpose P_MODEL_GROUP -- instead of one block
+    // per particle of which three quarters would be thrown away.
+    static constexpr bool kGroupDraws = true;
     Real mu, phi, sig, sd0;
-    __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
-        Real z[1];
-        draw_normals<1>(s, 0, z);
-        if (t == 0) x[0] = mu + sd0 * z[0];
-        else x[0] = mu + phi * (x[0] - mu) + sig * z[0];
+    __device__ __forceinline__ Real kernel_z(int64_t t, Real z, Real (&x)[D], const Obs& obs) const {
+        if (t == 0) x[0] = mu + sd0 * z;
+        else x[0] = mu + phi * (x[0] - mu) + sig * z;
         Real sd = exp(x[0] / 2);
         Real zz = (Real)obs.v[0] / sd;
         return -(zz * zz + (Real)1.8378770664093453) / 2 - x[0] / 2;
@@ -97,6 +101,7 @@ template <typename Real>
 struct Hmm {
     static constexpr int D = 1;
     static constexpr int NOBS = 1;
+    static constexpr bool kGroupDraws = false;
     int K, M;
     double prior[kHmmMaxK], log_emis[kHmmMaxK * kHmmMaxK], trans[kHmmMaxK * kHmmMaxK];   // log_emis[o*K+s], trans[to*K+from]
     __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {

@@ -580,6 +580,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     mpl_pf_config c;
     if (cfg) c = *cfg; else { c.dtype = MPL_F64; c.device = -1; c.seed = 0; c.gid_offset = 0; c.n_global = 0; }
     if (c.dtype != MPL_F32 && c.dtype != MPL_F64) { fail(MPL_ERR_INVALID, "dtype"); return nullptr; }
+    if (model->kind == M_SV && (c.gid_offset % 4)) { fail(MPL_ERR_INVALID, "stochastic-volatility model: shards start at multiples of 4 (4 particles share a Philox block)"); return nullptr; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); fail(MPL_ERR_CUDA, "no CUDA device: modppl_b200 has no CPU fallback"); return nullptr; }
     if (c.device >= 0) { if (cudaSetDevice(c.device) != cudaSuccess) { fail(MPL_ERR_CUDA, "cudaSetDevice failed"); return nullptr; } }

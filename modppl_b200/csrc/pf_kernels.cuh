@@ -259,10 +259,18 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
 #pragma unroll
             for (int v = 0; v < V; ++v) w[v] = 0;
         }
+        if constexpr (Model::kGroupDraws) {   // one Philox block for the thread's V particles (shards start at multiples of 4)
+            Real zs[V];
+            Stream sg(a.seed, (a.gid_offset + base) / V, (uint32_t)t, P_MODEL_GROUP);
+            draw_normals<V>(sg, 0, zs);
 #pragma unroll
-        for (int v = 0; v < V; ++v) {
-            Stream s(a.seed, a.gid_offset + base + v, (uint32_t)t, P_MODEL);
-            w[v] += model.kernel(t, s, x[v], obs);
+            for (int v = 0; v < V; ++v) w[v] += model.kernel_z(t, zs[v], x[v], obs);
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                Stream s(a.seed, a.gid_offset + base + v, (uint32_t)t, P_MODEL);
+                w[v] += model.kernel(t, s, x[v], obs);
+            }
         }
 #pragma unroll
         for (int d = 0; d < D; ++d) {

@@ -226,7 +226,7 @@ extern "C" double mo_u01_f64(uint32_t hi, uint32_t lo) { return (double)((((uint
 extern "C" float mo_u01_f32(uint32_t x) { return (float)(x >> 8) * 0x1.0p-24f; }
 
 namespace {
-enum Purpose : uint32_t { P_MODEL = 0, P_RESAMPLE_U = 1, P_RESAMPLE_OFFSET = 2, P_IS = 3, P_MH = 4, P_IS_RESAMPLE = 5, P_MH_INIT = 6 };
+enum Purpose : uint32_t { P_MODEL = 0, P_RESAMPLE_U = 1, P_RESAMPLE_OFFSET = 2, P_IS = 3, P_MH = 4, P_IS_RESAMPLE = 5, P_MH_INIT = 6, P_MODEL_GROUP = 7 };
 
 struct Stream {  // ctr = {id_lo, id_hi, t, purpose<<24 | blk}, key = seed
     uint32_t key[2]; uint32_t id_lo, id_hi, t, purpose;
@@ -475,6 +475,10 @@ template <typename Real> struct ModelBase {
     virtual int n_obs() const = 0;
     // t == 0: sample from the prior; t > 0: transition from x (in/out).  Returns the observation log-likelihood.
     virtual Real kernel(int64_t t, const Stream& s, Real* x, const double* obs) const = 0;
+    // models that need ONE normal deviate per particle and step share a Philox block between 4 (fp32) / 2 (fp64) consecutive
+    // global ids (stream id = gid / group, purpose P_MODEL_GROUP, deviate number gid % group): kernel_z gets the deviate
+    virtual bool group_draws() const { return false; }
+    virtual Real kernel_z(int64_t, Real, Real*, const double*) const { return 0; }
 };
 
 // -- 4-D constant-velocity linear-Gaussian tracker (config 4; not in the reference) ------------
@@ -531,10 +535,14 @@ template <typename Real> struct StochVol : ModelBase<Real> {
     StochVol(const double* p, size_t n) { mu = n > 0 ? p[0] : -1.024; phi = n > 1 ? p[1] : 0.9702; sig = n > 2 ? p[2] : 0.178; }
     int dim() const override { return 1; }
     int n_obs() const override { return 1; }
+    bool group_draws() const override { return true; }
     Real kernel(int64_t t, const Stream& s, Real* x, const double* obs) const override {
         Real z[1]; Draw<Real>::normals(s, 0, 1, z);
-        if (t == 0) x[0] = mu + (sig / std::sqrt(1 - phi * phi)) * z[0];
-        else x[0] = mu + phi * (x[0] - mu) + sig * z[0];
+        return kernel_z(t, z[0], x, obs);
+    }
+    Real kernel_z(int64_t t, Real z0, Real* x, const double* obs) const override {
+        if (t == 0) x[0] = mu + (sig / std::sqrt(1 - phi * phi)) * z0;
+        else x[0] = mu + phi * (x[0] - mu) + sig * z0;
         Real sd = std::exp(x[0] / 2);
         Real zz = (Real)obs[0] / sd;
         return -(zz * zz + (Real)std::log(2. * kPi)) / 2 - x[0] / 2;   // normal.rs:13-17 with ln(std) = x/2
@@ -615,13 +623,24 @@ template <typename Real> struct PS : mo_ps {
         return log_total_weight;
     }
 
+    // one particle through the model kernel with the engine's stream convention
+    Real propagate(uint64_t gid, Real* x, const double* obs) {
+        if (model->group_draws()) {
+            const uint64_t G = sizeof(Real) == 4 ? 4 : 2;
+            Stream sg(seed, gid / G, (uint32_t)t, P_MODEL_GROUP);
+            Real z[4]; Draw<Real>::normals(sg, 0, (int)G, z);
+            return model->kernel_z(t, z[gid % G], x, obs);
+        }
+        Stream s(seed, gid, (uint32_t)t, P_MODEL);
+        return model->kernel(t, s, x, obs);
+    }
+
     int init_step(const double* obs, size_t n) override {                             // :60-70 (reset instead of push: Q4)
         if ((int)n < model->n_obs()) return -1;
         t = 0;
         Real x[8];
         for (size_t i = 0; i < num_particles; ++i) {
-            Stream s(seed, gid_offset + i, (uint32_t)t, P_MODEL);
-            Real w = model->kernel(t, s, x, obs);
+            Real w = propagate(gid_offset + i, x, obs);
             for (int d = 0; d < D; ++d) state[(size_t)d * num_particles + i] = x[d];
             log_weights[i] = w;
         }
@@ -633,9 +652,8 @@ template <typename Real> struct PS : mo_ps {
         if ((int)n < model->n_obs()) return -1;
         Real x[8];
         for (size_t i = 0; i < num_particles; ++i) {
-            Stream s(seed, gid_offset + i, (uint32_t)t, P_MODEL);
             for (int d = 0; d < D; ++d) x[d] = state[(size_t)d * num_particles + i];
-            Real w = model->kernel(t, s, x, obs);
+            Real w = propagate(gid_offset + i, x, obs);
             for (int d = 0; d < D; ++d) state[(size_t)d * num_particles + i] = x[d];
             log_weights[i] = log_weights[i] + w;                                     // :81
         }
