@@ -4,23 +4,25 @@
 // log-weights (the reduce pass) has to wait for that maximum -- on several GPUs, for an exchange -- before it can even
 // start.  Here nothing is ever scaled against a global quantity until only a handful of numbers is left:
 //   chunk c   (128 particles, one warp iteration of the extend kernel):
-//       e_c = ceil(max_i lw_i * log2 e),   q_i = rint(2^(lw_i log2 e - e_c) * 2^k),   S_c = sum q_i
+//       e_c = ceil(max_i lw_i * log2 e),   q_i = rint(2^(lw_i log2 e - e_c) * 2^22) (32-bit),   S_c = sum q_i
 //     -> needs nothing outside the warp, fuses into the extend kernel's epilogue
-//   section s (2^17 particles = 1024 chunks, one block of the chunk pass):
+//   section s (2^17 particles = 1024 chunks, one block of the section pass):
 //       E_s = max e_c,   G_c = S_c >> (E_s - e_c),   T_s = sum G_c
 //   top       (at most 2048 sections; across GPUs: the ONLY exchange, one record per section):
 //       E = max E_s,   M_s = T_s >> (E - E_s),   W = sum M_s
 // Resampling runs the exact integer systematic scheme three times: the N output slots over the sections by M_s (slot j
 // at j*W + U), a section's n_s slots over its chunks by G_c (local slot l at l*T_s + U_s), a chunk's n_c slots over its
 // particles by q_i (l*S_c + U_c); U_s and U_c are hashed from the step's random word and the section / chunk number.
-// All of it is integer arithmetic: unbiased up to the floors (relative 2^-k), independent of thread order and of how
+// All of it is integer arithmetic: unbiased up to the floors (relative 2^-22), independent of thread order and of how
 // the particles are sharded (sections are aligned groups of global ids).
+// Kernels per resample: [quantise, unless the extend kernel's epilogue did it] -> section pass -> level-1 pass -> expansion
+// [-> heavy-tile pass once a heavy warp tile has been seen].
 #pragma once
 
 namespace mpl {
 
 constexpr int kChunksPerTile = kScanTile / kChunk;   // 32
-constexpr int kTilesPerSection = 32;                 // one block of the chunk pass (one warp scan over its tile sums)
+constexpr int kTilesPerSection = 32;                 // one block of the section pass (one warp scan over its tile sums)
 constexpr size_t kSection = (size_t)kTilesPerSection * kScanTile;   // 2^17 particles
 
 struct NestedPrefixes {

@@ -49,7 +49,7 @@ struct DeviceStats {
     long long ready_stats, ready_w, ready_done;
     long long trace[16];           // %globaltimer stamps of the last step's phases (sharded runs; mpl_ps_trace)
     int nest_E;                    // nested scheme: the global power-of-two reference of this resample
-    unsigned int nest_gen;         // nested scheme: generation word that releases the section pass' blocks after the top level
+    unsigned int pad2;
 };
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
