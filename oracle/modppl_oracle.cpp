@@ -14,6 +14,26 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <functional>
+#include <thread>
+
+// Host threads for the embarrassingly parallel loops (per-particle propagation, per-chunk quantisation, gather).  Results do
+// not depend on it: the RNG is counter-based per particle and every integer sum is taken by one thread per chunk.
+static int g_threads = 1;
+extern "C" void mo_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+extern "C" int mo_get_threads() { return g_threads; }
+static void parallel_for(size_t n, const std::function<void(size_t, size_t)>& body) {
+    const size_t nt = std::min<size_t>((size_t)g_threads, std::max<size_t>(1, n / 4096));
+    if (nt <= 1) { body(0, n); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (size_t k = 0; k < nt; ++k) {
+        const size_t lo = k * per, hi = std::min(n, lo + per);
+        if (lo >= hi) break;
+        th.emplace_back([&body, lo, hi] { body(lo, hi); });
+    }
+    for (auto& t : th) t.join();
+}
 
 namespace {
 const double kPi = 3.14159265358979323846;
@@ -379,7 +399,8 @@ extern "C" uint64_t mo_nested_systematic(const float* lw, size_t n, uint64_t u64
     std::vector<uint64_t> q(n, 0), S(nch, 0);
     std::vector<int> e(nch, 0);
     std::vector<char> empty(nch, 1);
-    for (size_t c = 0; c < nch; ++c) {
+    parallel_for(nch, [&](size_t c_lo, size_t c_hi) {
+    for (size_t c = c_lo; c < c_hi; ++c) {
         float Y = -std::numeric_limits<float>::infinity();
         for (size_t i = c * CH; i < std::min(n, (c + 1) * CH); ++i) {
             if (lw[i] == lw[i]) { float y = lw[i] * 1.44269504088896341f; if (y > Y) Y = y; }
@@ -399,6 +420,7 @@ extern "C" uint64_t mo_nested_systematic(const float* lw, size_t n, uint64_t u64
             S[c] += q[i];
         }
     }
+    });
     std::vector<uint64_t> G(nch, 0), T(nsec, 0), M(nsec, 0);
     std::vector<int> Es(nsec, 0);
     std::vector<char> sec_empty(nsec, 1);
@@ -638,25 +660,29 @@ template <typename Real> struct PS : mo_ps {
     int init_step(const double* obs, size_t n) override {                             // :60-70 (reset instead of push: Q4)
         if ((int)n < model->n_obs()) return -1;
         t = 0;
-        Real x[8];
-        for (size_t i = 0; i < num_particles; ++i) {
-            Real w = propagate(gid_offset + i, x, obs);
-            for (int d = 0; d < D; ++d) state[(size_t)d * num_particles + i] = x[d];
-            log_weights[i] = w;
-        }
+        parallel_for(num_particles, [&](size_t lo, size_t hi) {
+            Real x[8];
+            for (size_t i = lo; i < hi; ++i) {
+                Real w = propagate(gid_offset + i, x, obs);
+                for (int d = 0; d < D; ++d) state[(size_t)d * num_particles + i] = x[d];
+                log_weights[i] = w;
+            }
+        });
         t = 1;
         return 0;
     }
 
     int step(const double* obs, size_t n) override {                                  // :73-95
         if ((int)n < model->n_obs()) return -1;
-        Real x[8];
-        for (size_t i = 0; i < num_particles; ++i) {
-            for (int d = 0; d < D; ++d) x[d] = state[(size_t)d * num_particles + i];
-            Real w = propagate(gid_offset + i, x, obs);
-            for (int d = 0; d < D; ++d) state[(size_t)d * num_particles + i] = x[d];
-            log_weights[i] = log_weights[i] + w;                                     // :81
-        }
+        parallel_for(num_particles, [&](size_t lo, size_t hi) {
+            Real x[8];
+            for (size_t i = lo; i < hi; ++i) {
+                for (int d = 0; d < D; ++d) x[d] = state[(size_t)d * num_particles + i];
+                Real w = propagate(gid_offset + i, x, obs);
+                for (int d = 0; d < D; ++d) state[(size_t)d * num_particles + i] = x[d];
+                log_weights[i] = log_weights[i] + w;                                     // :81
+            }
+        });
         t += 1;
         return 0;
     }
@@ -671,8 +697,10 @@ template <typename Real> struct PS : mo_ps {
 
     void gather() {                                                                   // :109-113
         std::vector<Real> tmp(state.size());
-        for (size_t i = 0; i < num_particles; ++i)
-            for (int d = 0; d < D; ++d) tmp[(size_t)d * num_particles + i] = state[(size_t)d * num_particles + parents[i]];
+        parallel_for(num_particles, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i)
+                for (int d = 0; d < D; ++d) tmp[(size_t)d * num_particles + i] = state[(size_t)d * num_particles + parents[i]];
+        });
         state.swap(tmp);
         std::fill(log_weights.begin(), log_weights.end(), (Real)0);                   // :114
     }

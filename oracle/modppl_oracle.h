@@ -56,6 +56,9 @@ float mo_u01_f32(uint32_t x);                     /* [0,1), 24 bit */
 float mo_exp2_poly(float f);                      /* reproducible 2^f on [0,1) */
 uint64_t mo_fixed_weight(float d, int kbits);     /* rint(exp(d) * 2^kbits), d = lw - max <= 0 */
 int mo_fixed_kbits(uint64_t n_total);
+/* host threads used by the per-particle / per-chunk loops of the particle filter (default 1; results do not depend on it) */
+void mo_set_threads(int n);
+int mo_get_threads(void);
 /* lw: float log-weights.  Returns total W; writes ancestors (systematic, offset word `u64rand`). */
 uint64_t mo_fixed_systematic(const float* lw, size_t n, uint64_t u64rand, int32_t* anc, double* lse_out);
 uint64_t mo_fixed_multinomial(const float* lw, size_t n, uint64_t seed, uint32_t t, int32_t* anc, double* lse_out);

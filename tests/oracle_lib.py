@@ -51,6 +51,8 @@ _f("mo_u01_f32", C.c_float, C.c_uint32)
 _f("mo_exp2_poly", C.c_float, C.c_float)
 _f("mo_fixed_weight", C.c_uint64, C.c_float, C.c_int)
 _f("mo_fixed_kbits", C.c_int, C.c_uint64)
+_f("mo_set_threads", None, C.c_int)
+_f("mo_get_threads", C.c_int)
 _f("mo_fixed_systematic", C.c_uint64, fp, C.c_size_t, C.c_uint64, i32p, dp)
 _f("mo_fixed_multinomial", C.c_uint64, fp, C.c_size_t, C.c_uint64, C.c_uint32, i32p, dp)
 _f("mo_nested_systematic", C.c_uint64, fp, C.c_size_t, C.c_uint64, i32p, dp)

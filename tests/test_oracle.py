@@ -199,3 +199,19 @@ def test_mh_posterior_moves_toward_truth():
     for i in range(0, 64, 7):
         assert abs(st[4, i] - O.hier_logjp(xs, ys, st[:4, i])) < 1e-9
     assert st[4].mean() > -2000        # far above the prior draw's typical logjp (~ -1e5)
+
+
+def test_oracle_particle_filter_is_independent_of_host_threads():
+    # bench.py times the port on one and on all host threads: same numbers either way (counter-based RNG per particle,
+    # every integer sum taken by one thread per chunk)
+    ys = np.random.default_rng(0).normal(size=(4, 2))
+    out = []
+    for th in (1, 3):
+        O.L.mo_set_threads(th)
+        ps = O.OraclePS("lgssm4", [0.1, 0.5, 1.0], 40000, dtype="f32", seed=3)
+        ps.init_step(ys[0]); ps.resample(4)
+        for t in range(1, 4):
+            ps.step(ys[t]); ps.resample(4 if t % 2 else 2)
+        out.append((ps.log_marginal_likelihood_estimate(), ps.traces.copy(), ps.parents.copy()))
+    O.L.mo_set_threads(1)
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
