@@ -551,8 +551,10 @@ __global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<
         if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
         const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile + warp * kWarpTile) - 1;
         // n[][] counts from 0 at the warp tile's first slot
-        for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kNestedWarpSlots)
-            remote |= warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
+        if (total <= (unsigned int)kNestedWarpSlots) remote = warp_expand_chunk<Real, kNestedWarpSlots, true>(a, head[warp], n, 0u, total, 0u, (unsigned long long)ws, src0);
+        else
+            for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kNestedWarpSlots)
+                remote |= warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
     }
     if (signal_here) nested_signal_done(a.peer, st, epoch, remote);
 }

@@ -78,7 +78,8 @@ __device__ __forceinline__ void warp_tile_counts(unsigned long long wp, const un
 
 // One warp expands slots [chunk_lo, chunk_lo + CAP) of its own range [0, total) (relative to ws).  CAP = 32 * (slots per
 // lane), a multiple of 256: `head` holds CAP 16-bit entries.
-template <typename Real, int CAP = kWarpChunk>
+// SINGLE: the caller guarantees chunk_lo == 0 and total <= CAP (the whole range in one pass): the window tests drop out.
+template <typename Real, int CAP = kWarpChunk, bool SINGLE = false>
 __device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsigned short* head, const unsigned int (&n)[4][4], unsigned int ws,
                                                   unsigned int total, unsigned int chunk_lo, unsigned long long slot_base /* global slot of ws */,
                                                   int32_t src0 /* value for local element 0, minus 1 */) {
@@ -98,8 +99,12 @@ __device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsi
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const unsigned int start = prev - ws, end = n[r][j] - ws;
-            if (end > start && start < chunk_lo + CAP && end > chunk_lo)
-                head[max(start, chunk_lo) - chunk_lo] = (unsigned short)(r * 128 + lane * 4 + j + 1);
+            if constexpr (SINGLE) {
+                if (end > start) head[start] = (unsigned short)(r * 128 + lane * 4 + j + 1);
+            } else {
+                if (end > start && start < chunk_lo + CAP && end > chunk_lo)
+                    head[max(start, chunk_lo) - chunk_lo] = (unsigned short)(r * 128 + lane * 4 + j + 1);
+            }
             prev = n[r][j];
         }
     }
