@@ -655,3 +655,18 @@ def test_nested_device_loop_fp64_equals_call_per_step():
     assert a.log_marginal_likelihood_estimate() == b.log_marginal_likelihood_estimate()
     assert np.array_equal(a.parents, b.parents) and np.array_equal(a.traces, b.traces)
     assert a.num_resamples() == T
+
+
+def test_nested_more_sections_than_one_top_level_pass():
+    # 1026 sections (> 1024): the top level runs in several passes and reads its prefixes back; checked through the
+    # properties that do not need the (slow) oracle: sorted ancestors, every particle within 3 of N w_i / sum w
+    n = (1 << 27) + (1 << 17) + 77
+    rng = np.random.default_rng(12)
+    lw = (rng.standard_normal(n, dtype=np.float32) * np.float32(1.5) - np.float32(40.0))
+    anc, lse, W = m.parity.fixed_resample(lw, scheme=4, seed=5, t=2)
+    assert anc[0] >= 0 and anc[-1] < n and np.all(anc[1:] >= anc[:-1])
+    w = np.exp(lw.astype(np.float64) - float(lw.max()))
+    counts = np.bincount(anc, minlength=n)
+    assert counts.sum() == n
+    assert np.max(np.abs(counts - n * w / w.sum())) < 3.0 + 1e-3
+    assert abs(lse - (float(lw.max()) + math.log(w.sum()))) < 2e-5
