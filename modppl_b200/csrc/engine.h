@@ -59,6 +59,8 @@ struct mpl_ps {
     double* sq_partials;   // per-tile sums of squared weights (ESS in the integer resampler)
     int* host_flags;       // pinned + mapped: [0] = a heavy tile was seen (launch the overflow pass from now on)
     int* host_flags_dev;
+    unsigned int host_seq;  // tag of the last nested resample whose log total weight is posted to host_flags (bytes 16..39)
+    bool host_lse_posted;   // the last resample posts its result there (nested scheme, not ESS-triggered)
     // trajectory reconstruction (reference keeps traces[i].retv as a Vec<State>, dynunfold.rs:91-92): optional log of the
     // per-step states and ancestors, back-traced on demand
     int* rec_e; unsigned int* rec_S; float* rec_sq;   // chunk records of the nested scheme (ld / 128 entries), lazily allocated

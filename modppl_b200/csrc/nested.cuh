@@ -228,11 +228,30 @@ __device__ __forceinline__ void collect_section_records(const PeerTable& p, long
 }
 
 // scalar bookkeeping of resample(): particle_filter.rs:104-105,114 (one thread of the expansion kernel)
+// The log total weight goes straight to the host as well: three self-validating words in mapped pinned memory, so the caller
+// of resample() has its return value as soon as it exists -- before the expansion has even started -- and can queue the next
+// step behind it without ever draining the stream.
+template <typename Real>
+__device__ __forceinline__ void nested_post_to_host(const FixedArgs<Real>& a, double lse, int degenerate) {
+    if (!a.overflow_seen_host) return;
+    volatile unsigned long long* hm = reinterpret_cast<volatile unsigned long long*>(a.overflow_seen_host) + 2;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(lse), tag = (unsigned long long)a.host_seq << 32;
+    hm[0] = (bits & 0xffffffffull) | tag;
+    hm[1] = (bits >> 32) | tag;
+    hm[2] = (unsigned long long)(unsigned int)degenerate | tag;
+}
+
+// scalar bookkeeping of resample(): particle_filter.rs:104-105,114 (one thread of the level-1 pass)
 template <typename Real>
 __device__ __forceinline__ void nested_bookkeeping(const FixedArgs<Real>& a, DeviceStats* st, long long epoch) {
     const unsigned long long W = st->W;
-    if (W == 0ull) { st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1; return; }
+    if (W == 0ull) {
+        st->degenerate = 1; st->lse = -INFINITY; st->resampled = 1; st->resampled_flag[epoch & 1] = 1;
+        nested_post_to_host(a, -INFINITY, 1);
+        return;
+    }
     const double lse = (double)st->nest_E * 0.6931471805599453 + log((double)W) - (double)kNestedBits * 0.6931471805599453;
+    nested_post_to_host(a, lse, 0);
     st->lse = lse;
     st->ess_stale = st->ess;
     if (a.accumulate_lml) st->lml_acc += lse - a.log_n_global;

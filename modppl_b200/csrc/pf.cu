@@ -273,6 +273,7 @@ static FixedArgs<Real> fixed_args(mpl_ps* ps, bool dynamic, bool dev_t) {
     a.max_slot = (ps->world > 1 || ps->stats_valid) ? -1 : (int)((ps->t - 1) & 1);
     a.overflow_follows = (ps->world > 1 || ps->host_flags[0] != 0) ? 1 : 0;
     a.overflow_seen_host = ps->host_flags_dev;
+    a.host_seq = 0;
     a.sq_partials = ps->sq_partials;
     a.ess_threshold = ps->ess_threshold_abs;
     a.desc = ps->desc;
@@ -355,6 +356,8 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     if (n_sec_global > (size_t)kMaxSections) return fail(MPL_ERR_UNSUPPORTED, "nested scheme: at most 2^28 particles");
     FixedArgs<Real> a = fixed_args<Real>(ps, dynamic, false);
     a.overflow_follows = ps->host_flags[0] != 0 ? 1 : 0;   // the heavy-tile pass runs only once a heavy warp tile has been seen
+    if (phases & 2) { ps->host_seq += 1; if (ps->host_seq == 0) ps->host_seq = 1; }
+    a.host_seq = ps->host_seq;
     ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
     unsigned long long* sec = ps->nest_sec;
     NestedPrefixes nb{ps->nest_tile_pre, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
@@ -389,6 +392,7 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (phases & 1) ps->prequantised = 0;
+    if (phases & 2) ps->host_lse_posted = !dynamic;
     return MPL_OK;
 }
 
@@ -594,7 +598,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->D = model->state_dim;
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
     ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
-    ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = 0;
+    ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = 0; ps->host_seq = 0; ps->host_lse_posted = false;
     ps->nest_tile_pre = nullptr; ps->nest_sec = nullptr; ps->nest_slots = nullptr;
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
@@ -729,12 +733,44 @@ extern "C" int mpl_ps_effective_sample_size(mpl_ps* ps, int stale_like_reference
     return MPL_OK;
 }
 
+// The nested resampler posts its log total weight into mapped host memory as soon as the level-1 pass knows it (tagged
+// words, nested.cuh: nested_post_to_host): poll that instead of draining the stream, so that the caller can queue the next
+// step while the expansion kernel is still running.  Returns false if the words never showed up (then: synchronise).
+static bool poll_host_lse(mpl_ps* ps, double* lse, int* degenerate, int* rc) {
+    volatile unsigned long long* hm = reinterpret_cast<volatile unsigned long long*>(ps->host_flags) + 2;
+    const unsigned long long seq = ps->host_seq;
+    *rc = MPL_OK;
+    for (unsigned long spins = 1;; ++spins) {
+        const unsigned long long w0 = hm[0], w1 = hm[1], w2 = hm[2];
+        if ((w0 >> 32) == seq && (w1 >> 32) == seq && (w2 >> 32) == seq) {
+            const unsigned long long bits = (w0 & 0xffffffffull) | (w1 << 32);
+            std::memcpy(lse, &bits, sizeof bits);
+            *degenerate = (int)(w2 & 0xffffffffull);
+            return true;
+        }
+        if ((spins & 0xfff) == 0) {   // every few microseconds: has the stream finished (or failed) without posting?
+            const cudaError_t e = cudaStreamQuery(ps->stream);
+            if (e == cudaSuccess) return false;
+            if (e != cudaErrorNotReady) { *rc = fail(MPL_ERR_CUDA, std::string("resample: ") + cudaGetErrorString(e)); return false; }
+        }
+    }
+}
+
 extern "C" int mpl_ps_resample(mpl_ps* ps, int scheme, double* log_total_weight) {
     if (!ps) return fail(MPL_ERR_INVALID, "null handle");
     MPL_CUDA_OK(cudaSetDevice(ps->device));
+    ps->host_lse_posted = false;
     int rc = do_resample(ps, scheme);
     if (rc) return rc;
     if (log_total_weight) {
+        double lse = 0.;
+        int degenerate = 0;
+        if (ps->host_lse_posted && !ps->profile && poll_host_lse(ps, &lse, &degenerate, &rc)) {
+            *log_total_weight = lse;
+            if (degenerate) return fail(MPL_ERR_DEGENERATE, "all particle weights are -inf");
+            return MPL_OK;
+        }
+        if (rc) return rc;
         if ((rc = fetch_stats(ps))) return rc;
         *log_total_weight = ps->stats_host->lse;
         if (ps->stats_host->degenerate) return fail(MPL_ERR_DEGENERATE, "all particle weights are -inf");

@@ -430,7 +430,9 @@ struct FixedArgs {
     long long epoch;          // step number the mailbox flags must have reached; < 0: stats->t
     int max_slot;             // >= 0: the max lives in stats->max_bits[max_slot] (left by the extend); < 0: in stats->max
     int overflow_follows;     // 1: a fixed_overflow_kernel launch follows the scan (heavy tiles are queued for it)
-    int* overflow_seen_host;  // mapped host word, raised when any tile exceeds the heavy cap
+    int* overflow_seen_host;  // mapped host word, raised when any tile exceeds the heavy cap; the three 8-byte words at byte 16 of the
+                              // same buffer carry the log total weight of this resample to the host (tagged with host_seq)
+    unsigned int host_seq;    // tag of this resample call (nested scheme: the host polls the mapped words instead of synchronising)
     double* sq_partials;      // per tile: sum of (q * 2^-k)^2, for ESS = W^2 / sum q^2
 };
 template <typename Real>
