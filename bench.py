@@ -194,7 +194,7 @@ def run_ours(args):
         "config": {"workload": "lgssm4 (4-D linear-Gaussian SSM) bootstrap particle filter, resample every step", "particles": f"2^{args.log2_particles}",
                    "T_timed": K, "resampling": args.scheme + " on integer weights", "l2": "inputs exceed L2 (2 x 256 MiB state buffers stream every step)",
                    "log_ml": lml},
-        "e2e": {"value": n_global * K / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 128,
+        "e2e": {"value": n_global * K / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 24,
                 "note": "mpl_ps_step_resample(host obs -> host log total weight) per step: the observation travels as a kernel argument, the log total weight is written by the level-1 kernel into mapped pinned host memory (tagged words) and polled there, so the call returns as soon as the value exists and the next step queues behind the running expansion; particles stay in HBM by design"},
         "gpu_launches": int(launches),
         "clocks": clocks,

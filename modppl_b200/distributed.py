@@ -154,7 +154,7 @@ def bench_multi(args, ys, scheme, rank, world, local_rank):
             "config": {"workload": "lgssm4 (4-D linear-Gaussian SSM) bootstrap particle filter, resample every step", "particles": f"2^{args.log2_particles} in total, sharded",
                        "T_timed": K, "resampling": f"global {args.scheme} resampling on integer weights; NVLink peer loads/stores inside the kernels, no NCCL on the data path",
                        "l2": "per-GPU state buffers stream every step", "log_ml": lml, "peer_wait_timeouts": err},
-            "e2e": {"value": n_global * K / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 128},
+            "e2e": {"value": n_global * K / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 24},
             "gpu_launches": int(launches) * world, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": step_gbs, "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "traffic": None,
                          "peak_source": peak_src + f" x {world} GPUs", "kernel_ms_rank0": kernel_ms},
