@@ -274,20 +274,30 @@ static int importance_impl(const mpl_model* m, const double* obs, size_t n_obs, 
     StaticData d;
     if ((rc = build_static(m, obs, n_obs, d))) return rc;
     const int L = m->num_latents;
-    double *dlat = nullptr, *dw = nullptr, *dlnw = nullptr, *dprobs = nullptr, *dcum = nullptr; long long* didx = nullptr;
-    DeviceStats* st = nullptr; Lse3<double>* part = nullptr;
     const int grid = (int)std::min<size_t>(((size_t)n + 255) / 256, (size_t)kNumSMs * 8);
-    MPL_CUDA_OK(cudaMalloc(&dlat, (size_t)L * n * 8));
-    MPL_CUDA_OK(cudaMalloc(&dw, (size_t)n * 8));
-    MPL_CUDA_OK(cudaMalloc(&dlnw, (size_t)n * 8));
-    MPL_CUDA_OK(cudaMalloc(&st, sizeof(DeviceStats)));
-    MPL_CUDA_OK(cudaMalloc(&part, grid * sizeof(Lse3<double>)));
-    MPL_CUDA_OK(cudaMemset(st, 0, sizeof(DeviceStats)));
-    if (n_ret) {
-        MPL_CUDA_OK(cudaMalloc(&dprobs, (size_t)n * 8));
-        MPL_CUDA_OK(cudaMalloc(&dcum, (size_t)n * 8));
-        MPL_CUDA_OK(cudaMalloc(&didx, (size_t)n_ret * 8));
+    // device workspace, kept per host thread and device and only ever grown: a batch of 2^20 proposals runs in tens of
+    // microseconds, several cudaMalloc/cudaFree pairs per call would cost more than the kernels
+    struct Workspace { int device = -1; size_t cap_n = 0, cap_lat = 0, cap_ret = 0, cap_grid = 0;
+                       double *lat = nullptr, *w = nullptr, *lnw = nullptr, *probs = nullptr, *cum = nullptr; long long* idx = nullptr;
+                       DeviceStats* st = nullptr; Lse3<double>* part = nullptr; };
+    static thread_local Workspace ws;
+    int dev = 0;
+    MPL_CUDA_OK(cudaGetDevice(&dev));
+    if (ws.device != dev) { ws = Workspace(); ws.device = dev; }   // (buffers of another device are left to the driver's teardown)
+    if ((size_t)L * n > ws.cap_lat) { cudaFree(ws.lat); ws.lat = nullptr; ws.cap_lat = 0; MPL_CUDA_OK(cudaMalloc(&ws.lat, (size_t)L * n * 8)); ws.cap_lat = (size_t)L * n; }
+    if ((size_t)n > ws.cap_n) {
+        cudaFree(ws.w); cudaFree(ws.lnw); cudaFree(ws.probs); cudaFree(ws.cum); ws.w = ws.lnw = ws.probs = ws.cum = nullptr; ws.cap_n = 0;
+        MPL_CUDA_OK(cudaMalloc(&ws.w, (size_t)n * 8)); MPL_CUDA_OK(cudaMalloc(&ws.lnw, (size_t)n * 8));
+        MPL_CUDA_OK(cudaMalloc(&ws.probs, (size_t)n * 8)); MPL_CUDA_OK(cudaMalloc(&ws.cum, (size_t)n * 8));
+        ws.cap_n = n;
     }
+    if ((size_t)n_ret > ws.cap_ret) { cudaFree(ws.idx); ws.idx = nullptr; ws.cap_ret = 0; MPL_CUDA_OK(cudaMalloc(&ws.idx, (size_t)n_ret * 8)); ws.cap_ret = n_ret; }
+    if (!ws.st) MPL_CUDA_OK(cudaMalloc(&ws.st, sizeof(DeviceStats)));
+    if ((size_t)grid > ws.cap_grid) { cudaFree(ws.part); ws.part = nullptr; ws.cap_grid = 0; MPL_CUDA_OK(cudaMalloc(&ws.part, (size_t)grid * sizeof(Lse3<double>))); ws.cap_grid = grid; }
+    double *dlat = ws.lat, *dw = ws.w, *dlnw = ws.lnw, *dprobs = n_ret ? ws.probs : nullptr, *dcum = ws.cum;
+    long long* didx = ws.idx;
+    DeviceStats* st = ws.st; Lse3<double>* part = ws.part;
+    MPL_CUDA_OK(cudaMemsetAsync(st, 0, sizeof(DeviceStats)));
     is_kernel<<<grid, 256>>>(d, n, seed, (uint32_t)batch, dlat, dw);
     weight_reduce_kernel<double><<<grid, 256>>>(dw, n, st, part);
     is_normalize_kernel<<<grid, 256>>>(dw, n, st, dlnw, dprobs);
@@ -301,7 +311,6 @@ static int importance_impl(const mpl_model* m, const double* obs, size_t n_obs, 
     if (e == cudaSuccess && latents) e = cudaMemcpy(latents, dlat, (size_t)L * n * 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && lnw_out) e = cudaMemcpy(lnw_out, dlnw, (size_t)n * 8, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && idx_out && n_ret) e = cudaMemcpy(idx_out, didx, (size_t)n_ret * 8, cudaMemcpyDeviceToHost);
-    cudaFree(dlat); cudaFree(dw); cudaFree(dlnw); cudaFree(st); cudaFree(part); cudaFree(dprobs); cudaFree(dcum); cudaFree(didx);
     if (e != cudaSuccess) return fail(MPL_ERR_CUDA, cudaGetErrorString(e));
     if (lml) *lml = ((h.max == -INFINITY) ? -INFINITY : h.max + std::log(h.sumexp)) - std::log((double)n);   // importance.rs:21-22
     return MPL_OK;

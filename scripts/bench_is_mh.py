@@ -17,7 +17,12 @@ for name, model, ys in (("line", m.line_model(xs), ys_line), ("hierarchical", m.
     t0 = time.perf_counter()
     lmls = [m.importance_sampling(model, ys, n, seed=0, batch=b)[2] for b in range(16)]
     dt = time.perf_counter() - t0
-    out[f"is_{name}"] = {"proposals_per_s_e2e_incl_d2h": 16 * n / dt, "lml_mean": float(np.mean(lmls)), "lml_std": float(np.std(lmls))}
+    t0 = time.perf_counter()
+    lmls2 = [m.importance_sampling(model, ys, n, seed=0, batch=b, return_traces=False)[2] for b in range(64)]
+    dt2 = time.perf_counter() - t0
+    assert lmls2[:16] == lmls
+    out[f"is_{name}"] = {"proposals_per_s_e2e_incl_d2h_of_all_traces": 16 * n / dt, "proposals_per_s_lml_only": 64 * n / dt2,
+                         "lml_mean": float(np.mean(lmls2)), "lml_std": float(np.std(lmls2))}
 ch = m.Chains(m.hierarchical_model(xs), ys_hier, n, seed=2)
 m.hierarchical_sweeps(ch, 2)
 acc, ms = m.hierarchical_sweeps(ch, 100, timed=True)      # 1400 moves per chain
