@@ -163,6 +163,8 @@ def run_ours(args):
     ms = ps.run(1 + W, K, scheme)                              # timed: K steps, CUDA events on the launching stream
     launches = ps.launch_count() - l0
     value = n_global * K / (ms * 1e-3)
+    tr = ps.device_trace()                                     # %globaltimer stamps of the last timed step (scripts/step_timeline.py)
+    ext_in_loop_ms = (tr[14] - tr[13]) * 1e-6 if tr[14] > tr[13] > 0 else None
 
     # e2e: the reference-facing calls, one host round trip per step (observation in, log total weight out)
     t_first = 1 + W + K
@@ -202,7 +204,12 @@ def run_ours(args):
                      "traffic": EXTEND_DRAM_BYTES_NCU if (args.log2_particles == 24 and args.scheme == "nested") else None, "peak_source": peak_src, "algorithmic_bytes_per_particle": EXTEND_BYTES_PER_PARTICLE,
                      "algorithmic_bytes_per_launch": EXTEND_BYTES_PER_PARTICLE * n_global, "traffic_source": "profiles/r1_ncu_summary_nested.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch; nested scheme)",
                      "whole_step": {"bytes_per_particle": BYTES_PER_PARTICLE_STEP, "achieved": step_gbs, "frac": step_gbs / peak, "frac_of_nominal_8TBs": step_gbs / 8000.0},
-                     "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()}},
+                     "kernel_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in prof.items()},
+                     "in_loop": None if not ext_in_loop_ms else {
+                         "extend_ms": ext_in_loop_ms, "achieved": EXTEND_BYTES_PER_PARTICLE * n_global / (ext_in_loop_ms * 1e-3) / 1e9,
+                         "frac": EXTEND_BYTES_PER_PARTICLE * n_global / (ext_in_loop_ms * 1e-3) / 1e9 / peak,
+                         "source": "device %globaltimer stamps inside the timed loop (extend block 0 past its dependency wait -> last block done); "
+                                   "the CUDA-event figure above times the kernel between its own pair of events, outside the loop's programmatic dependent launch"}},
         "cpu_baseline": base,
     }
     print(json.dumps(line))
