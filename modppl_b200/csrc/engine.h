@@ -60,6 +60,7 @@ struct mpl_ps {
     int* host_flags;       // pinned + mapped: [0] = a heavy tile was seen (launch the overflow pass from now on)
     int* host_flags_dev;
     unsigned int host_seq;  // tag of the last nested resample whose log total weight is posted to host_flags (bytes 16..39)
+    bool in_device_loop;    // inside mpl_ps_run: results are not posted to the host per step
     bool host_lse_posted;   // the last resample posts its result there (nested scheme, not ESS-triggered)
     // trajectory reconstruction (reference keeps traces[i].retv as a Vec<State>, dynunfold.rs:91-92): optional log of the
     // per-step states and ancestors, back-traced on demand

@@ -233,7 +233,7 @@ __device__ __forceinline__ void collect_section_records(const PeerTable& p, long
 // step behind it without ever draining the stream.
 template <typename Real>
 __device__ __forceinline__ void nested_post_to_host(const FixedArgs<Real>& a, double lse, int degenerate) {
-    if (!a.overflow_seen_host) return;
+    if (!a.overflow_seen_host || a.host_seq == 0u) return;   // (nobody polls inside the device-resident loop: no store to host memory there)
     volatile unsigned long long* hm = reinterpret_cast<volatile unsigned long long*>(a.overflow_seen_host) + 2;
     const unsigned long long bits = (unsigned long long)__double_as_longlong(lse), tag = (unsigned long long)a.host_seq << 32;
     hm[0] = (bits & 0xffffffffull) | tag;

@@ -356,8 +356,9 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     if (n_sec_global > (size_t)kMaxSections) return fail(MPL_ERR_UNSUPPORTED, "nested scheme: at most 2^28 particles");
     FixedArgs<Real> a = fixed_args<Real>(ps, dynamic, false);
     a.overflow_follows = ps->host_flags[0] != 0 ? 1 : 0;   // the heavy-tile pass runs only once a heavy warp tile has been seen
-    if (phases & 2) { ps->host_seq += 1; if (ps->host_seq == 0) ps->host_seq = 1; }
-    a.host_seq = ps->host_seq;
+    const bool post = (phases & 2) && !dynamic && !ps->in_device_loop;   // the call-per-step API polls the result in mapped host memory
+    if (post) { ps->host_seq += 1; if (ps->host_seq == 0) ps->host_seq = 1; }
+    a.host_seq = post ? ps->host_seq : 0u;
     ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
     unsigned long long* sec = ps->nest_sec;
     NestedPrefixes nb{ps->nest_tile_pre, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
@@ -392,7 +393,7 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (phases & 1) ps->prequantised = 0;
-    if (phases & 2) ps->host_lse_posted = !dynamic;
+    if (phases & 2) ps->host_lse_posted = post;
     return MPL_OK;
 }
 
@@ -598,7 +599,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->D = model->state_dim;
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
     ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
-    ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = 0; ps->host_seq = 0; ps->host_lse_posted = false;
+    ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = 0; ps->host_seq = 0; ps->host_lse_posted = false; ps->in_device_loop = false;
     ps->nest_tile_pre = nullptr; ps->nest_sec = nullptr; ps->nest_slots = nullptr;
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
@@ -951,6 +952,7 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
     if (elapsed_ms) { MPL_CUDA_OK(cudaEventCreate(&e0)); MPL_CUDA_OK(cudaEventCreate(&e1)); MPL_CUDA_OK(cudaEventRecord(e0, ps->stream)); }
     Obs dummy; std::memset(&dummy, 0, sizeof dummy);
     int rc = MPL_OK;
+    struct LoopFlag { mpl_ps* p; explicit LoopFlag(mpl_ps* q) : p(q) { p->in_device_loop = true; } ~LoopFlag() { p->in_device_loop = false; } } loop_flag(ps);
     for (size_t k = 0; k < n_steps && rc == MPL_OK; ++k) {
         size_t tt = first_step + k;
         if (tt == 0) {
