@@ -47,7 +47,8 @@ extern "C" {
 #define MPL_RESAMPLE_SYSTEMATIC 1
 #define MPL_RESAMPLE_SYSTEMATIC_FIXED 2
 #define MPL_RESAMPLE_MULTINOMIAL_FIXED 3
-#define MPL_RESAMPLE_SYSTEMATIC_NESTED 4   /* integer weights quantised per 128-particle chunk; chunks, then particles, resampled systematically */
+#define MPL_RESAMPLE_SYSTEMATIC_NESTED 4   /* integer weights quantised per 128-particle chunk; sections (2^17 particles), chunks, then particles
+                                            * resampled systematically, each level exactly; the throughput scheme */
 
 #define MPL_READ_STATE 0          /* double[D * N], SoA: state[d * N + i]  (`traces[i].retv.last()`, dynunfold.rs:76) */
 #define MPL_READ_LOG_WEIGHTS 1    /* double[N]                              (`log_weights`, particle_filter.rs:15)      */
