@@ -215,3 +215,22 @@ def test_oracle_particle_filter_is_independent_of_host_threads():
         out.append((ps.log_marginal_likelihood_estimate(), ps.traces.copy(), ps.parents.copy()))
     O.L.mo_set_threads(1)
     assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1]) and np.array_equal(out[0][2], out[1][2])
+
+
+@pytest.mark.parametrize("n,reps", [(1000, 3000), (2 * (1 << 17) + 5000, 250)])
+def test_nested_systematic_is_unbiased(n, reps):
+    # three nested exact systematic levels: E[#offspring of i] = N w_i / sum w (up to the 2^-22 quantisation), checked by
+    # averaging the oracle over many random offset words (the larger case spans three sections on different scales)
+    rng = np.random.default_rng(7)
+    lw = (rng.normal(size=n) * 2.0).astype(np.float32)
+    lw[::7] -= 30.0                                   # a few particles far below their chunk's maximum
+    lw -= (np.arange(n) // (1 << 17)).astype(np.float32) * np.float32(3.3)
+    w = np.exp(lw.astype(np.float64)); expect = n * w / w.sum()
+    mean = np.zeros(n)
+    for r in range(reps):
+        anc, _, _ = O.nested_systematic(lw, int(rng.integers(0, 2**63)) * 2 + int(rng.integers(0, 2)))
+        mean += np.bincount(anc, minlength=n)
+    mean /= reps
+    # systematic counts differ from their mean by less than 1 per level: variance of the average <= 3 / reps
+    assert np.max(np.abs(mean - expect)) < 6.0 * math.sqrt(3.0 / reps)
+    assert abs(mean.sum() - n) < 1e-9
