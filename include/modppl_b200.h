@@ -154,7 +154,9 @@ int mpl_logsumexp_stats(const void* lw, uint64_t n, int dtype, double* lse, doub
  * words come from Philox(seed, t) exactly as inside a particle system resampling the weights of step t. */
 int mpl_fixed_resample(const float* lw, uint64_t n, int scheme, uint64_t seed, uint32_t t, int32_t* anc,
                        double* lse, uint64_t* total_weight);
-/* built-in log-densities evaluated on the device (tests/dists.rs known answers) */
+/* built-in log-densities evaluated on the device (tests/dists.rs known answers): "normal" (mu, std), "bernoulli" (p),
+ * "uniform" (a, b), "uniform_2d" (bounds), "mvnormal2" (mu[2], cov[4]), "uniform_discrete" (a, b), "geometric" (p),
+ * "poisson" (rate), "beta" (a, b), "gamma" (shape, scale), "categorical" (the probabilities, at most 8) */
 int mpl_logpdf(const char* dist, const double* x, const double* params, size_t n_params, double* out);
 
 /* ---- multi-GPU (one process per GPU) ---------------------------------------------------------------- */

@@ -180,6 +180,23 @@ __host__ __device__ __forceinline__ Real normal_logpdf(Real x, Real mu, Real sd)
     Real z = (x - mu) / sd;
     return -(z * z + (Real)1.8378770664093453) / 2 - log(sd);
 }
+// ---- the remaining built-in distributions (reference src/modeling/dists/*.rs; known answers tests/dists.rs:60-69,186-212) ----
+__host__ __device__ __forceinline__ double uniform_discrete_logpdf(long long x, long long a, long long b) {           // uniform.rs:43-47
+    return (a <= x && x <= b) ? -log((double)(b - a + 1)) : -INFINITY;
+}
+__host__ __device__ __forceinline__ double geometric_logpdf(long long k, double p) { return log(pow(1. - p, (double)k) * p); }   // geometric.rs:16-19, literally
+__host__ __device__ __forceinline__ double poisson_logpdf(long long k, double rate) {                                  // poisson.rs:16-18
+    double s = 0.;
+    for (long long v = 1; v <= k; ++v) s += log((double)v);
+    return (double)k * log(rate) - rate - s;
+}
+__host__ __device__ __forceinline__ double beta_logpdf(double x, double a, double b) {                                 // beta.rs:17-21, literally
+    const double beta_f = tgamma(a + b) / (tgamma(a) * tgamma(b));
+    return log(beta_f * pow(x, a - 1.) * pow(1. - x, b - 1.));
+}
+__host__ __device__ __forceinline__ double gamma_logpdf(double x, double a, double b) {                                // gamma.rs:17-20 (shape a, scale b)
+    return (a - 1.) * log(x) - x / b - log(tgamma(a)) - a * log(b);
+}
 __host__ __device__ __forceinline__ double bernoulli_logpdf(bool a, double p) { return log(a ? p : 1. - p); }   // bernoulli.rs:12-14
 __host__ __device__ __forceinline__ double uniform_logpdf(double x, double a, double b) {                        // uniform.rs:22-26
     return (a <= x && x <= b) ? -log(b - a) : -INFINITY;

@@ -435,13 +435,26 @@ __global__ void logpdf_kernel(int which, const double* x, const double* p, doubl
         double prec[4] = {p[5] / det, -p[3] / det, -p[4] / det, p[2] / det};
         *out = mvnormal2_logpdf(x[0], x[1], p[0], p[1], prec, 2. * 1.8378770664093453 + log(det));
     }
+    else if (which == 5) *out = (p[0] > p[1]) ? NAN : uniform_discrete_logpdf((long long)x[0], (long long)p[0], (long long)p[1]);
+    else if (which == 6) *out = geometric_logpdf((long long)x[0], p[0]);
+    else if (which == 7) *out = poisson_logpdf((long long)x[0], p[0]);
+    else if (which == 8) *out = beta_logpdf(x[0], p[0], p[1]);
+    else if (which == 9) *out = gamma_logpdf(x[0], p[0], p[1]);
+    else if (which >= 16) {   // categorical.rs:13-20 with K = which - 16 probabilities
+        const long long k = (long long)x[0];
+        *out = k < 0 ? NAN : (k < (long long)(which - 16) ? log(p[k]) : -INFINITY);
+    }
 }
 extern "C" int mpl_logpdf(const char* dist, const double* x, const double* params, size_t n_params, double* out) {
     if (!dist || !x || !params || !out) return fail(MPL_ERR_INVALID, "null argument");
     std::string s(dist);
-    int which = s == "normal" ? 0 : s == "bernoulli" ? 1 : s == "uniform" ? 2 : s == "uniform_2d" ? 3 : s == "mvnormal2" ? 4 : -1;
-    size_t need = which == 0 ? 2 : which == 1 ? 1 : which == 2 ? 2 : which == 3 ? 4 : 6;
-    if (which < 0 || n_params != need) return fail(MPL_ERR_INVALID, "unknown distribution or wrong parameter count");
+    int which = s == "normal" ? 0 : s == "bernoulli" ? 1 : s == "uniform" ? 2 : s == "uniform_2d" ? 3 : s == "mvnormal2" ? 4
+              : s == "uniform_discrete" ? 5 : s == "geometric" ? 6 : s == "poisson" ? 7 : s == "beta" ? 8 : s == "gamma" ? 9 : s == "categorical" ? 16 : -1;
+    static const size_t kNeed[10] = {2, 1, 2, 4, 6, 2, 1, 1, 2, 2};
+    if (which == 16) {   // the probability vector is the parameter list (at most 8 categories)
+        if (n_params < 1 || n_params > 8) return fail(MPL_ERR_INVALID, "categorical: 1..8 probabilities");
+        which = 16 + (int)n_params;
+    } else if (which < 0 || n_params != kNeed[which]) return fail(MPL_ERR_INVALID, "unknown distribution or wrong parameter count");
     int rc = require_device();
     if (rc) return rc;
     double* d = nullptr;

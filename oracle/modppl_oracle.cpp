@@ -73,6 +73,38 @@ extern "C" double mo_uniform_logpdf(double x, double a, double b) {
     return (a <= x && x <= b) ? -std::log(b - a) : kNegInf;
 }
 
+extern "C" double mo_uniform_discrete_logpdf(int64_t x, int64_t a, int64_t b) {
+    // uniform.rs:43-47 ; check_bounds panics when a > b -> NaN here
+    if (a > b) return std::numeric_limits<double>::quiet_NaN();
+    return (a <= x && x <= b) ? -std::log((double)(b - a + 1)) : kNegInf;
+}
+
+extern "C" double mo_geometric_logpdf(int64_t k, double p) {
+    // geometric.rs:16-19, literally: ((1-p)^k * p).ln()  (underflows to -inf for very large k, like the reference)
+    return std::log(std::pow(1. - p, (double)k) * p);
+}
+
+extern "C" double mo_poisson_logpdf(int64_t k, double rate) {
+    // poisson.rs:16-18: k ln(rate) - rate - sum_{v=1..k} ln v   (the sum in the iterator's order)
+    double s = 0.;
+    for (int64_t v = 1; v <= k; ++v) s += std::log((double)v);
+    return (double)k * std::log(rate) - rate - s;
+}
+
+// beta.rs / gamma.rs call `compute::functions::gamma` (crate compute 0.2.3, not vendored in the reference tree): the
+// Gamma function.  std::tgamma stands in for it; parity is anchored on the reference's known answers
+// (tests/dists.rs:200-212, epsilon = f32::EPSILON), which both satisfy.
+extern "C" double mo_beta_logpdf(double x, double a, double b) {
+    // beta.rs:17-21, literally: ln( Gamma(a+b)/(Gamma(a)Gamma(b)) * x^(a-1) * (1-x)^(b-1) )
+    const double beta_f = std::tgamma(a + b) / (std::tgamma(a) * std::tgamma(b));
+    return std::log(beta_f * std::pow(x, a - 1.) * std::pow(1. - x, b - 1.));
+}
+
+extern "C" double mo_gamma_logpdf(double x, double a, double b) {
+    // gamma.rs:17-20 (shape a, scale b): (a-1) ln x - x/b - ln Gamma(a) - a ln b
+    return (a - 1.) * std::log(x) - x / b - std::log(std::tgamma(a)) - a * std::log(b);
+}
+
 extern "C" double mo_uniform2d_logpdf(double x, double y, const double bd[4]) {
     // tests/pointed_model/types_2d.rs:15-21
     if (bd[0] <= x && x <= bd[1] && bd[2] <= y && y <= bd[3])

@@ -33,6 +33,11 @@ double mo_logsumexp(const double* xs, size_t n);
 double mo_normal_logpdf(double x, double mu, double std);                 /* normal.rs:13-17   */
 double mo_bernoulli_logpdf(int a, double p);                              /* bernoulli.rs:12-14 */
 double mo_uniform_logpdf(double x, double a, double b);                   /* uniform.rs:22-26 (NaN where the reference panics) */
+double mo_uniform_discrete_logpdf(int64_t x, int64_t a, int64_t b);       /* uniform.rs:43-47 (NaN where the reference panics) */
+double mo_geometric_logpdf(int64_t k, double p);                          /* geometric.rs:16-19 */
+double mo_poisson_logpdf(int64_t k, double rate);                         /* poisson.rs:16-18 */
+double mo_beta_logpdf(double x, double a, double b);                      /* beta.rs:17-21 (Gamma function: crate compute 0.2.3 -> std::tgamma) */
+double mo_gamma_logpdf(double x, double shape, double scale);             /* gamma.rs:17-20 */
 double mo_uniform2d_logpdf(double x, double y, const double bounds[4]);   /* tests/pointed_model/types_2d.rs:15-21; bounds = xmin,xmax,ymin,ymax */
 double mo_mvnormal_logpdf(const double* x, const double* mu, const double* cov, int k); /* mvnormal.rs:14-22, nalgebra 0.32 det/inverse, k<=4, cov row-major */
 int64_t mo_categorical_random(const double* probs, size_t n, double u);   /* categorical.rs:22-32 with injected u; literal (may return -1 or run past n: returns n) */

@@ -38,6 +38,11 @@ _f("mo_logsumexp", C.c_double, dp, C.c_size_t)
 _f("mo_normal_logpdf", C.c_double, C.c_double, C.c_double, C.c_double)
 _f("mo_bernoulli_logpdf", C.c_double, C.c_int, C.c_double)
 _f("mo_uniform_logpdf", C.c_double, C.c_double, C.c_double, C.c_double)
+_f("mo_uniform_discrete_logpdf", C.c_double, C.c_int64, C.c_int64, C.c_int64)
+_f("mo_geometric_logpdf", C.c_double, C.c_int64, C.c_double)
+_f("mo_poisson_logpdf", C.c_double, C.c_int64, C.c_double)
+_f("mo_beta_logpdf", C.c_double, C.c_double, C.c_double, C.c_double)
+_f("mo_gamma_logpdf", C.c_double, C.c_double, C.c_double, C.c_double)
 _f("mo_uniform2d_logpdf", C.c_double, C.c_double, C.c_double, dp)
 _f("mo_mvnormal_logpdf", C.c_double, dp, dp, dp, C.c_int)
 _f("mo_categorical_random", C.c_int64, dp, C.c_size_t, C.c_double)
@@ -99,6 +104,24 @@ def logsumexp(xs):
 
 def normal_logpdf(x, mu, sd):
     return L.mo_normal_logpdf(x, mu, sd)
+
+
+def logpdf(dist, x, params):
+    """The remaining built-in distributions by name (same names as modppl_b200.parity.logpdf)."""
+    if dist == "uniform_discrete":
+        return L.mo_uniform_discrete_logpdf(int(x), int(params[0]), int(params[1]))
+    if dist == "geometric":
+        return L.mo_geometric_logpdf(int(x), float(params[0]))
+    if dist == "poisson":
+        return L.mo_poisson_logpdf(int(x), float(params[0]))
+    if dist == "beta":
+        return L.mo_beta_logpdf(float(x), float(params[0]), float(params[1]))
+    if dist == "gamma":
+        return L.mo_gamma_logpdf(float(x), float(params[0]), float(params[1]))
+    if dist == "categorical":
+        pr = np.ascontiguousarray(params, dtype=np.float64)
+        return L.mo_categorical_logpdf(int(x), pr.ctypes.data_as(dp), pr.size)
+    raise ValueError(dist)
 
 
 def mvnormal_logpdf(x, mu, cov):

@@ -121,3 +121,26 @@ def test_particle_filter_end_to_end(scheme):      # tests/particle_filter.rs:35-
         ps.effective_sample_size()
         ps.resample(scheme)
     assert abs(ps.log_marginal_likelihood_estimate() - expected) <= 0.03
+
+
+# ---- the remaining built-in distributions: tests/dists.rs:60-69, 186-212 --------------------------------
+def test_uniform_discrete_logpdf_known_answers():
+    assert abs(O.logpdf("uniform_discrete", 9, (8, 130)) - math.log(1.0 / 123)) <= 1e-15
+    assert abs(O.logpdf("uniform_discrete", 130, (8, 130)) - math.log(1.0 / 123)) <= 1e-15
+    assert O.logpdf("uniform_discrete", 140, (8, 130)) == -math.inf
+
+
+def test_geometric_poisson_beta_gamma_logpdf_known_answers():
+    known = [("geometric", 1, (0.5,), -1.3862943611198906), ("geometric", 5, (0.98,), -19.580317734458244), ("geometric", 101, (0.01,), -5.6202541071917365),
+             ("poisson", 3, (4.0,), -1.6328763858683835), ("poisson", 5, (1.5,), -4.2601662022412240), ("poisson", 52, (36.11,), -5.969204868031767),
+             ("beta", 0.3, (0.5, 0.5), -0.364406011717066), ("beta", 0.7, (1.5, 2.0), -0.06055443631298263),
+             ("gamma", 1.7, (1.23, 1.46), -1.414334369005868), ("gamma", 8.4, (4.5, 1.0), -3.4049256003700052), ("gamma", 0.03, (50.0, 70.0), -528.8122715889206)]
+    for dist, x, params, want in known:
+        assert abs(O.logpdf(dist, x, params) - want) <= F32_EPS, (dist, x, params)
+
+
+def test_categorical_logpdf():                   # categorical.rs:13-20 with the probabilities of tests/dists.rs:89
+    probs = [0.1, 0.3, 0.2, 0.1, 0.05, 0.25]
+    for i, pr in enumerate(probs):
+        assert O.logpdf("categorical", i, probs) == math.log(pr)
+    assert O.logpdf("categorical", 6, probs) == -math.inf

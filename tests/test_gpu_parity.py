@@ -670,3 +670,23 @@ def test_nested_more_sections_than_one_top_level_pass():
     assert counts.sum() == n
     assert np.max(np.abs(counts - n * w / w.sum())) < 3.0 + 1e-3
     assert abs(lse - (float(lw.max()) + math.log(w.sum()))) < 2e-5
+
+
+def test_logpdf_remaining_distributions_on_device():    # SURVEY 8f.4; tests/dists.rs:60-69, 186-212
+    P = m.parity
+    eps = 1.1920929e-07                                   # LOGPDF_EPSILON = f32::EPSILON, the reference's own bar
+    known = [("geometric", 1, (0.5,), -1.3862943611198906), ("geometric", 5, (0.98,), -19.580317734458244), ("geometric", 101, (0.01,), -5.6202541071917365),
+             ("poisson", 3, (4.0,), -1.6328763858683835), ("poisson", 5, (1.5,), -4.2601662022412240), ("poisson", 52, (36.11,), -5.969204868031767),
+             ("beta", 0.3, (0.5, 0.5), -0.364406011717066), ("beta", 0.7, (1.5, 2.0), -0.06055443631298263),
+             ("gamma", 1.7, (1.23, 1.46), -1.414334369005868), ("gamma", 8.4, (4.5, 1.0), -3.4049256003700052), ("gamma", 0.03, (50.0, 70.0), -528.8122715889206),
+             ("uniform_discrete", 9, (8, 130), math.log(1.0 / 123)), ("uniform_discrete", 130, (8, 130), math.log(1.0 / 123))]
+    for dist, x, params, want in known:
+        got = P.logpdf(dist, float(x), [float(v) for v in params])
+        assert abs(got - want) <= eps, (dist, x, params, got)
+        ref = O.logpdf(dist, x, params)
+        assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref)), (dist, x, params, got, ref)
+    assert P.logpdf("uniform_discrete", 140.0, [8.0, 130.0]) == -math.inf
+    probs = [0.1, 0.3, 0.2, 0.1, 0.05, 0.25]
+    for i, pr in enumerate(probs):
+        assert abs(P.logpdf("categorical", float(i), probs) - math.log(pr)) <= 1e-15
+    assert P.logpdf("categorical", 6.0, probs) == -math.inf
