@@ -93,6 +93,11 @@ int mpl_ps_resample(mpl_ps*, int scheme, double* log_total_weight);             
  * the two calls; with MPL_RESAMPLE_SYSTEMATIC_NESTED on fp32 the extend kernel quantises the weights in its epilogue */
 int mpl_ps_step_resample(mpl_ps*, const double* obs, size_t n_obs, int scheme, double* log_total_weight);
 int mpl_ps_log_marginal_likelihood_estimate(mpl_ps*, double* out);                                  /* lml         :119-121 */
+/* checkpoint / resume (single GPU): the filter's resumable state in its native precision.  A restored filter continues
+ * exactly as the original would have (same seed required); the trajectory log is not part of a checkpoint. */
+int mpl_ps_checkpoint_size(mpl_ps*, uint64_t* bytes);
+int mpl_ps_checkpoint(mpl_ps*, void* dst, uint64_t bytes);
+int mpl_ps_restore(mpl_ps*, const void* src, uint64_t bytes);
 int mpl_ps_read(mpl_ps*, int what, void* host_dst, size_t bytes);                                   /* `pub traces` :13     */
 int mpl_ps_write(mpl_ps*, int what, const void* host_src, size_t bytes);                            /* parity hook: inject state / log-weights */
 int mpl_ps_num_particles(const mpl_ps*, uint64_t* out);

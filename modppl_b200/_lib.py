@@ -64,6 +64,9 @@ SYMBOLS = {
     "mpl_ps_step": (C.c_int, C.c_void_p, c_double_p, C.c_size_t),
     "mpl_ps_effective_sample_size": (C.c_int, C.c_void_p, C.c_int, c_double_p),
     "mpl_ps_resample": (C.c_int, C.c_void_p, C.c_int, c_double_p),
+    "mpl_ps_checkpoint_size": (C.c_int, C.c_void_p, C.POINTER(C.c_uint64)),
+    "mpl_ps_checkpoint": (C.c_int, C.c_void_p, C.c_void_p, C.c_uint64),
+    "mpl_ps_restore": (C.c_int, C.c_void_p, C.c_void_p, C.c_uint64),
     "mpl_ps_step_resample": (C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_int, c_double_p),
     "mpl_ps_log_marginal_likelihood_estimate": (C.c_int, C.c_void_p, c_double_p),
     "mpl_ps_read": (C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t),

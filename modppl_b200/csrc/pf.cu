@@ -858,6 +858,80 @@ extern "C" int mpl_ps_write(mpl_ps* ps, int what, const void* host_src, size_t b
     return MPL_OK;
 }
 
+// ---- checkpoint / resume ----------------------------------------------------------------------------------
+// A checkpoint is the filter's whole resumable state in its native precision: header, live state (D x ld), log-weights (ld).
+// A pending resample is applied first (the gather it stands for gives the same particles as the fused gather of the next
+// step would), so no ancestors need to be kept.  Single GPU; the trajectory log is not part of it.
+namespace {
+struct CkptHeader {
+    uint64_t magic, n, ld, n_global, seed, gid_offset;
+    int32_t D, dtype, model_kind, pad;
+    int64_t t;
+    double lml_acc, ess, ess_stale, lse;
+    uint64_t n_resamples;
+};
+constexpr uint64_t kCkptMagic = 0x314b434c504d6f6dull;   // "moMPLCK1"
+size_t ckpt_bytes(const mpl_ps* ps) { return sizeof(CkptHeader) + ((size_t)ps->D + 1) * ps->ld * (ps->dtype == MPL_F32 ? 4 : 8); }
+}  // namespace
+
+extern "C" int mpl_ps_checkpoint_size(mpl_ps* ps, uint64_t* bytes) {
+    if (!ps || !bytes) return fail(MPL_ERR_INVALID, "null argument");
+    *bytes = ckpt_bytes(ps);
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_checkpoint(mpl_ps* ps, void* dst, uint64_t bytes) {
+    if (!ps || !dst) return fail(MPL_ERR_INVALID, "null argument");
+    if (!ps->initialised) return fail(MPL_ERR_INVALID, "checkpoint before init_step");
+    if (ps->world > 1) return fail(MPL_ERR_UNSUPPORTED, "checkpoint: single GPU only");
+    if (bytes != ckpt_bytes(ps)) return fail(MPL_ERR_INVALID, "checkpoint buffer size (see mpl_ps_checkpoint_size)");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    int rc;
+    if ((rc = materialise(ps))) return rc;
+    if ((rc = fetch_stats(ps))) return rc;
+    CkptHeader h;
+    std::memset(&h, 0, sizeof h);
+    h.magic = kCkptMagic; h.n = ps->n; h.ld = ps->ld; h.n_global = ps->n_global; h.seed = ps->seed; h.gid_offset = ps->gid_offset;
+    h.D = ps->D; h.dtype = ps->dtype; h.model_kind = (int32_t)ps->model.kind; h.t = ps->t;
+    h.lml_acc = ps->stats_host->lml_acc; h.ess = ps->stats_host->ess; h.ess_stale = ps->stats_host->ess_stale; h.lse = ps->stats_host->lse;
+    h.n_resamples = ps->stats_host->n_resamples;
+    std::memcpy(dst, &h, sizeof h);
+    const size_t es = elem_size(ps);
+    char* out = (char*)dst + sizeof h;
+    MPL_CUDA_OK(cudaMemcpyAsync(out, ps->state[ps->cur], (size_t)ps->D * ps->ld * es, cudaMemcpyDeviceToHost, ps->stream));
+    MPL_CUDA_OK(cudaMemcpyAsync(out + (size_t)ps->D * ps->ld * es, ps->lw, ps->ld * es, cudaMemcpyDeviceToHost, ps->stream));
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_restore(mpl_ps* ps, const void* src, uint64_t bytes) {
+    if (!ps || !src) return fail(MPL_ERR_INVALID, "null argument");
+    if (ps->world > 1) return fail(MPL_ERR_UNSUPPORTED, "restore: single GPU only");
+    if (bytes != ckpt_bytes(ps)) return fail(MPL_ERR_INVALID, "checkpoint does not fit this particle system (size)");
+    CkptHeader h;
+    std::memcpy(&h, src, sizeof h);
+    if (h.magic != kCkptMagic || h.n != ps->n || h.ld != ps->ld || h.n_global != ps->n_global || h.D != ps->D || h.dtype != ps->dtype ||
+        h.model_kind != (int32_t)ps->model.kind || h.gid_offset != ps->gid_offset)
+        return fail(MPL_ERR_INVALID, "checkpoint does not fit this particle system (model, particle count, precision or shard differ)");
+    if (h.seed != ps->seed) return fail(MPL_ERR_INVALID, "checkpoint was taken with another seed: the continuation would not reproduce the original run");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    int rc;
+    if ((rc = fetch_stats(ps))) return rc;   // (also drains the stream)
+    const size_t es = elem_size(ps);
+    const char* in = (const char*)src + sizeof h;
+    MPL_CUDA_OK(cudaMemcpyAsync(ps->state[ps->cur], in, (size_t)ps->D * ps->ld * es, cudaMemcpyHostToDevice, ps->stream));
+    MPL_CUDA_OK(cudaMemcpyAsync(ps->lw, in + (size_t)ps->D * ps->ld * es, ps->ld * es, cudaMemcpyHostToDevice, ps->stream));
+    DeviceStats& st = *ps->stats_host;
+    st.lml_acc = h.lml_acc; st.ess = h.ess; st.ess_stale = h.ess_stale; st.lse = h.lse; st.n_resamples = h.n_resamples; st.t = h.t;
+    st.resampled = 0; st.resampled_flag[0] = st.resampled_flag[1] = 0; st.degenerate = 0; st.do_resample = 0;
+    st.max_bits[0] = st.max_bits[1] = 0ull; st.blocks_done = 0; st.ticket = 0; st.overflow_count = 0;
+    MPL_CUDA_OK(cudaMemcpyAsync(ps->stats, ps->stats_host, sizeof(DeviceStats), cudaMemcpyHostToDevice, ps->stream));
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    ps->t = h.t; ps->initialised = true; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
+    ps->prequantised = 0; ps->dynamic_state_known = true;
+    return MPL_OK;
+}
+
 extern "C" int mpl_ps_history_enable(mpl_ps* ps, uint64_t max_steps) {
     if (!ps || max_steps == 0) return fail(MPL_ERR_INVALID, "bad argument");
     if (ps->world > 1) return fail(MPL_ERR_UNSUPPORTED, "trajectory log: single GPU only");

@@ -57,6 +57,20 @@ class ParticleSystem:
         self._steps_done = getattr(self, "_steps_done", 0) + 1
         return out.value if sync else None
 
+    def checkpoint(self):
+        """-> bytes: the filter's resumable state (native precision); see `restore`."""
+        n = C.c_uint64()
+        check(lib.mpl_ps_checkpoint_size(self._h, C.byref(n)))
+        buf = np.empty(n.value, dtype=np.uint8)
+        check(lib.mpl_ps_checkpoint(self._h, buf.ctypes.data_as(C.c_void_p), n.value))
+        return buf.tobytes()
+
+    def restore(self, blob):
+        """Continue from a checkpoint taken from a filter with the same model, particle count, precision and seed."""
+        buf = np.frombuffer(blob, dtype=np.uint8)
+        check(lib.mpl_ps_restore(self._h, buf.ctypes.data_as(C.c_void_p), buf.size))
+        return self
+
     def device_trace(self):
         """%globaltimer stamps (ns) left by the kernels of the last step (diagnostics; include/modppl_b200.h: mpl_ps_trace)."""
         buf = (C.c_longlong * 16)()

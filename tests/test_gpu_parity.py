@@ -690,3 +690,25 @@ def test_logpdf_remaining_distributions_on_device():    # SURVEY 8f.4; tests/dis
     for i, pr in enumerate(probs):
         assert abs(P.logpdf("categorical", float(i), probs) - math.log(pr)) <= 1e-15
     assert P.logpdf("categorical", 6.0, probs) == -math.inf
+
+
+@pytest.mark.parametrize("dtype,scheme", [("f32", m.SYSTEMATIC_NESTED), ("f64", m.MULTINOMIAL)])
+def test_checkpoint_restore_continues_bit_for_bit(dtype, scheme):
+    T, n = 10, 30000
+    ys = lgssm_data(T)
+    a = m.ParticleSystem(m.lgssm4(), n, seed=11, dtype=dtype)
+    a.init_step(ys[0]); a.resample(scheme)
+    for y in ys[1:5]:
+        a.step(y); a.resample(scheme)
+    a.step(ys[5])                                    # checkpoint between a step and its resample: weights are live
+    blob = a.checkpoint()
+    b = m.ParticleSystem(m.lgssm4(), n, seed=11, dtype=dtype).restore(blob)
+    for f in (a, b):
+        f.resample(scheme)
+        for y in ys[6:]:
+            f.step(y); f.resample(scheme)
+    assert a.log_marginal_likelihood_estimate() == b.log_marginal_likelihood_estimate()
+    assert np.array_equal(a.traces, b.traces) and np.array_equal(a.parents, b.parents)
+    assert a.num_resamples() == b.num_resamples()
+    with pytest.raises(m.MplError):
+        m.ParticleSystem(m.lgssm4(), n, seed=12, dtype=dtype).restore(blob)      # another seed would not reproduce the run
