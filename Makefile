@@ -8,9 +8,16 @@ LIB := modppl_b200/lib/libmodppl_b200.so
 
 all: $(LIB) oracle
 
-$(LIB): $(SRCS) $(HDRS)
-	mkdir -p modppl_b200/lib
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(SRCS) 2> modppl_b200/lib/ptxas.log || (cat modppl_b200/lib/ptxas.log; false)
+OBJS := $(patsubst $(CSRC)/%.cu,modppl_b200/lib/%.o,$(SRCS))
+
+# one object per translation unit so that `make -j` compiles them side by side; ptxas -v output is kept per unit
+modppl_b200/lib/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p modppl_b200/lib
+	$(NVCC) $(NVCCFLAGS) -c -o $@ $< 2> modppl_b200/lib/$*.ptxas.log || (cat modppl_b200/lib/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	$(NVCC) -shared -o $@ $(OBJS)
+	@cat modppl_b200/lib/*.ptxas.log > modppl_b200/lib/ptxas.log
 
 oracle:
 	$(MAKE) -C oracle

@@ -131,18 +131,34 @@ int mpl_importance_resampling(const mpl_model*, const double* obs, size_t n_obs,
                               int64_t* resampled_indices, double* lml);
 int mpl_model_num_latents(const mpl_model*);
 
-/* ---- Metropolis-Hastings over many independent chains (src/inference/mh.rs:9-76) ----------------------------- */
-#define MPL_MOVE_HIER_DRIFT 0        /* mh(model, trace, hierarchical_drift_proposal, std)   hierarchical.rs:63-71 */
-#define MPL_MOVE_HIER_ADD_REMOVE 1   /* mh(model, trace, add_or_remove_param_proposal, ())   hierarchical.rs:48-61 */
-#define MPL_MOVE_HIER_REGEN 2        /* regen_mh(model, trace, mask): bits 1=coeffs/a 2=coeffs/b 4=coeffs/c 8=is_linear (extension) */
-#define MPL_MOVE_POINTED_DRIFT 3     /* mh(pointed model, trace, drift proposal, s): cov = s^2 I   pointed_model/proposal.rs */
+/* ---- Metropolis-Hastings over many independent chains (src/inference/mh.rs:9-76) -----------------------------
+ * `mh(model, trace, proposal, proposal_args)` is generic over the proposal GenFn (mh.rs:9-14).  Here a static model registers
+ * its proposals as device functors under the names of the reference's fixtures and `mpl_mh` selects one BY NAME:
+ *   "hierarchical": "hierarchical_drift_proposal" (std; hierarchical.rs:63-71), "add_or_remove_param_proposal" (std; :48-61)
+ *   "pointed":      "pointed_2d_drift_proposal"   (s: covariance s^2 I; tests/pointed_model/proposal.rs)
+ * A new proposal is a struct with make / propose / assess next to its model in csrc/is_mh.cu, listed in Model::Proposals. */
+int mpl_model_num_proposals(const mpl_model*);
+const char* mpl_model_proposal_name(const mpl_model*, int index);       /* NULL when out of range */
+int mpl_model_proposal_index(const mpl_model*, const char* name);       /* >= 0, or MPL_ERR_INVALID */
 mpl_chains* mpl_chains_new(const mpl_model*, const double* obs, size_t n_obs, uint64_t n_chains, uint64_t seed,
                            uint64_t chain_offset, int device);                     /* trace = model.generate(args, obs).0 per chain */
 void mpl_chains_destroy(mpl_chains*);
-int mpl_mh(mpl_chains*, int move, double proposal_arg, uint32_t n_steps, uint64_t* n_accepted);     /* mh       :9-50  */
-int mpl_regen_mh(mpl_chains*, uint32_t mask_bits, uint32_t n_steps, uint64_t* n_accepted);           /* regen_mh :54-76 */
-/* n_sweeps x (1 add/remove(.025) + 3 drift(.1) + 10 drift(.01)), the schedule of tests/mh.rs:93-106, in one launch */
-int mpl_mh_hier_sweeps(mpl_chains*, uint32_t n_sweeps, uint64_t* n_accepted, float* elapsed_ms);
+int mpl_mh(mpl_chains*, const char* proposal, double proposal_arg, uint32_t n_steps, uint64_t* n_accepted);   /* mh       :9-50  */
+/* regen_mh(model, trace, mask): mask bits over the model's latent slots; "hierarchical": 1 coeffs/a, 2 coeffs/b, 4 coeffs/c,
+ * 8 is_linear; 0 = everything (dyngenfn.rs:571) */
+int mpl_regen_mh(mpl_chains*, uint32_t mask_bits, uint32_t n_steps, uint64_t* n_accepted);                      /* regen_mh :54-76 */
+/* A sweep as ONE launch: `moves` is the body of the caller's loop (e.g. tests/mh.rs:93-106: 1 add/remove(.025), 3 drift(.1),
+ * 10 drift(.01)), run n_sweeps times per chain with the chain's state in registers throughout. */
+#define MPL_MOVE_MH 0
+#define MPL_MOVE_REGEN 1
+typedef struct mpl_move {
+    int32_t kind;        /* MPL_MOVE_MH | MPL_MOVE_REGEN                                   */
+    int32_t proposal;    /* MPL_MOVE_MH: mpl_model_proposal_index(model, name)             */
+    double arg;          /* MPL_MOVE_MH: proposal_args                                     */
+    uint32_t mask;       /* MPL_MOVE_REGEN: mask bits                                      */
+    uint32_t repeat;     /* how many times in a row                                        */
+} mpl_move;
+int mpl_mh_schedule(mpl_chains*, const mpl_move* moves, uint32_t n_moves, uint32_t n_sweeps, uint64_t* n_accepted, float* elapsed_ms);
 int mpl_chains_num_slots(const mpl_chains*);
 int mpl_chains_read(mpl_chains*, double* host_dst, size_t bytes);    /* double[slots * n] SoA */
 int mpl_chains_write(mpl_chains*, const double* host_src, size_t bytes);
@@ -160,8 +176,9 @@ int mpl_logsumexp_stats(const void* lw, uint64_t n, int dtype, double* lse, doub
 int mpl_fixed_resample(const float* lw, uint64_t n, int scheme, uint64_t seed, uint32_t t, int32_t* anc,
                        double* lse, uint64_t* total_weight);
 /* built-in log-densities evaluated on the device (tests/dists.rs known answers): "normal" (mu, std), "bernoulli" (p),
- * "uniform" (a, b), "uniform_2d" (bounds), "mvnormal2" (mu[2], cov[4]), "uniform_discrete" (a, b), "geometric" (p),
- * "poisson" (rate), "beta" (a, b), "gamma" (shape, scale), "categorical" (the probabilities, at most 8) */
+ * "uniform" (a, b), "uniform_2d" (bounds), "mvnormal2" (mu[2], cov[4]; determinant and inverse hoisted, as the models use
+ * it), "mvnormal" (x[k]; mu[k], cov[k*k] row-major, 1 <= k <= 8: mvnormal.rs:14-22 literally), "uniform_discrete" (a, b),
+ * "geometric" (p), "poisson" (rate), "beta" (a, b), "gamma" (shape, scale), "categorical" (the probabilities, at most 8) */
 int mpl_logpdf(const char* dist, const double* x, const double* params, size_t n_params, double* out);
 
 /* ---- multi-GPU (one process per GPU) ---------------------------------------------------------------- */

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("MODPPL_B200_LIB") or os.path.join(_HERE, "lib", "libmodppl_b200.so")   # env override: A/B experiments only
+LIB_PATH = os.path.join(_HERE, "lib", "libmodppl_b200.so")
 
 
 class MplError(RuntimeError):
@@ -16,7 +16,7 @@ class MplError(RuntimeError):
         self.code = code
 
 
-if not os.path.exists(LIB_PATH) and not os.environ.get("MODPPL_B200_LIB"):
+if not os.path.exists(LIB_PATH):
     # a fresh checkout: compile the CUDA library in-tree (nvcc cross-compiles sm_100a without a GPU)
     import subprocess
     try:
@@ -35,6 +35,10 @@ c_float_p = C.POINTER(C.c_float)
 c_i64_p = C.POINTER(C.c_int64)
 c_i32_p = C.POINTER(C.c_int32)
 c_u64_p = C.POINTER(C.c_uint64)
+
+
+class Move(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("proposal", C.c_int32), ("arg", C.c_double), ("mask", C.c_uint32), ("repeat", C.c_uint32)]
 
 
 class PfConfig(C.Structure):
@@ -85,9 +89,12 @@ SYMBOLS = {
     "mpl_importance_resampling": (C.c_int, C.c_void_p, c_double_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, c_double_p, c_i64_p, c_double_p),
     "mpl_chains_new": (C.c_void_p, C.c_void_p, c_double_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int),
     "mpl_chains_destroy": (None, C.c_void_p),
-    "mpl_mh": (C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_uint32, c_u64_p),
+    "mpl_model_num_proposals": (C.c_int, C.c_void_p),
+    "mpl_model_proposal_name": (C.c_char_p, C.c_void_p, C.c_int),
+    "mpl_model_proposal_index": (C.c_int, C.c_void_p, C.c_char_p),
+    "mpl_mh": (C.c_int, C.c_void_p, C.c_char_p, C.c_double, C.c_uint32, c_u64_p),
     "mpl_regen_mh": (C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, c_u64_p),
-    "mpl_mh_hier_sweeps": (C.c_int, C.c_void_p, C.c_uint32, c_u64_p, c_float_p),
+    "mpl_mh_schedule": (C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, c_u64_p, c_float_p),
     "mpl_chains_num_slots": (C.c_int, C.c_void_p),
     "mpl_chains_read": (C.c_int, C.c_void_p, c_double_p, C.c_size_t),
     "mpl_chains_write": (C.c_int, C.c_void_p, c_double_p, C.c_size_t),

@@ -212,6 +212,68 @@ __host__ __device__ __forceinline__ double mvnormal2_logpdf(double x0, double x1
     return -(log_norm + (t0 * c0 + t1 * c1)) / 2.;
 }
 
+// mvnormal.rs:14-22 for any k <= 8, literally: determinant and inverse of the covariance recomputed per call (row-major cov).
+// nalgebra 0.32.2 (modppl/Cargo.toml:17; not vendored) special-cases k <= 3 with cofactor closed forms -- restated here so that
+// the reference's known answers (tests/dists.rs:164-183, k = 2 and k = 3) are reproduced to the last bits -- and uses LU beyond.
+constexpr int kMvnMaxK = 8;
+__host__ __device__ inline double mvnormal_logpdf_k(const double* x, const double* mu, const double* cov, int k) {
+    if (k < 1 || k > kMvnMaxK) return NAN;
+    double inv[kMvnMaxK * kMvnMaxK], det;
+    if (k == 1) { det = cov[0]; inv[0] = 1. / cov[0]; }
+    else if (k == 2) {
+        const double m11 = cov[0], m12 = cov[1], m21 = cov[2], m22 = cov[3];
+        det = m11 * m22 - m21 * m12;
+        inv[0] = m22 / det; inv[1] = -m12 / det; inv[2] = -m21 / det; inv[3] = m11 / det;
+    } else if (k == 3) {
+        const double m11 = cov[0], m12 = cov[1], m13 = cov[2], m21 = cov[3], m22 = cov[4], m23 = cov[5], m31 = cov[6], m32 = cov[7], m33 = cov[8];
+        const double minor_m12_m23 = m22 * m33 - m32 * m23, minor_m11_m23 = m21 * m33 - m31 * m23, minor_m11_m22 = m21 * m32 - m31 * m22;
+        det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22;
+        inv[0] = minor_m12_m23 / det; inv[1] = (m13 * m32 - m33 * m12) / det; inv[2] = (m12 * m23 - m22 * m13) / det;
+        inv[3] = -minor_m11_m23 / det; inv[4] = (m11 * m33 - m31 * m13) / det; inv[5] = (m13 * m21 - m23 * m11) / det;
+        inv[6] = minor_m11_m22 / det; inv[7] = (m12 * m31 - m32 * m11) / det; inv[8] = (m11 * m22 - m21 * m12) / det;
+    } else {
+        // LU with partial pivoting for the determinant, Gauss-Jordan for the inverse
+        double a[kMvnMaxK * kMvnMaxK];
+        for (int i = 0; i < k * k; ++i) a[i] = cov[i];
+        det = 1.;
+        for (int c = 0; c < k; ++c) {
+            int p = c;
+            for (int r = c + 1; r < k; ++r) if (fabs(a[r * k + c]) > fabs(a[p * k + c])) p = r;
+            if (a[p * k + c] == 0.) { det = 0.; break; }
+            if (p != c) { for (int j = 0; j < k; ++j) { double t = a[p * k + j]; a[p * k + j] = a[c * k + j]; a[c * k + j] = t; } det = -det; }
+            det *= a[c * k + c];
+            for (int r = c + 1; r < k; ++r) {
+                const double f = a[r * k + c] / a[c * k + c];
+                for (int j = c; j < k; ++j) a[r * k + j] -= f * a[c * k + j];
+            }
+        }
+        double g[kMvnMaxK * 2 * kMvnMaxK];
+        for (int r = 0; r < k; ++r) for (int c = 0; c < 2 * k; ++c) g[r * 2 * k + c] = c < k ? cov[r * k + c] : (c - k == r ? 1. : 0.);
+        for (int c = 0; c < k; ++c) {
+            int p = c;
+            for (int r = c + 1; r < k; ++r) if (fabs(g[r * 2 * k + c]) > fabs(g[p * 2 * k + c])) p = r;
+            if (g[p * 2 * k + c] == 0.) return NAN;
+            if (p != c) for (int j = 0; j < 2 * k; ++j) { double t = g[p * 2 * k + j]; g[p * 2 * k + j] = g[c * 2 * k + j]; g[c * 2 * k + j] = t; }
+            const double d = g[c * 2 * k + c];
+            for (int j = 0; j < 2 * k; ++j) g[c * 2 * k + j] /= d;
+            for (int r = 0; r < k; ++r) if (r != c) {
+                const double f = g[r * 2 * k + c];
+                for (int j = 0; j < 2 * k; ++j) g[r * 2 * k + j] -= f * g[c * 2 * k + j];
+            }
+        }
+        for (int r = 0; r < k; ++r) for (int c = 0; c < k; ++c) inv[r * k + c] = g[r * 2 * k + k + c];
+    }
+    if (det == 0.) return NAN;
+    double c[kMvnMaxK], mahal = 0.;
+    for (int i = 0; i < k; ++i) c[i] = x[i] - mu[i];
+    for (int j = 0; j < k; ++j) {   // (centered^T * cov_inv) * centered
+        double t = 0.;
+        for (int i = 0; i < k; ++i) t += c[i] * inv[i * k + j];
+        mahal += t * c[j];
+    }
+    return -((double)k * 1.8378770664093453 + log(det) + mahal) / 2.;
+}
+
 // ------------------------------------------------------------------------------------------------
 // online log-sum-exp triple: (m, s, s2) represents sum exp(x) = s*exp(m), sum exp(2x) = s2*exp(2m)
 // ------------------------------------------------------------------------------------------------

@@ -73,6 +73,7 @@ struct mpl_ps {
     std::vector<int> hist_resampled;   // [t]: a resample followed step t
     double ess_threshold_abs;   // ESS-triggered device loop: threshold in particles
     bool dynamic_state_known;
+    bool hist_broken;            // the trajectory log no longer describes the population (ESS-triggered device loop ran, or a restore)
     bool profile;
     std::map<std::string, mpl::KernelTimer> timers;
     uint64_t launch_count;
@@ -90,4 +91,6 @@ int ps_phase_extend(mpl_ps* ps, bool init, bool fuse_nested = false);
 int ps_phase_nested(mpl_ps* ps, int phase);
 int ps_phase_reduce(mpl_ps* ps);
 int ps_phase_scan(mpl_ps* ps);
+// categorical.rs:25-30: the sequential f64 running sum of `probs`, bit for bit (parallel emulation for long inputs); ps may be null
+int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream);
 }

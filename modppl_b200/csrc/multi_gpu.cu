@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 #include "engine.h"
 
@@ -51,6 +52,10 @@ extern "C" int mpl_ps_peer_export(mpl_ps* ps, void* blob) {
     MPL_CUDA_OK(cudaSetDevice(ps->device));
     int rc = ensure_mailbox(ps);
     if (rc) return rc;
+    // an export precedes the all-gather of the blobs, hence every peer's first store: a (re-)attach starts from a clean
+    // mailbox (its words are validated by step number only)
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    MPL_CUDA_OK(cudaMemset(ps->mailbox, 0, sizeof(Mailbox)));
     PeerBlob b;
     std::memset(&b, 0, sizeof b);
     MPL_CUDA_OK(cudaIpcGetMemHandle(&b.state0, ps->state[0]));
@@ -70,24 +75,35 @@ extern "C" int mpl_ps_peer_attach(mpl_ps* ps, int rank, int world, const void* b
     MPL_CUDA_OK(cudaSetDevice(ps->device));
     if ((rc = ensure_mailbox(ps))) return rc;
     MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
-    fill_table_header(ps, rank, world);
+    // open every handle first (recording each as it is opened); only a complete table is committed
+    PeerTable table = ps->peer;
+    auto rollback = [&](cudaError_t e) {
+        for (int k = 0; k < 4; ++k)
+            for (int h = 0; h < kMaxPeers; ++h)
+                if (ps->ipc_opened[k][h]) { cudaIpcCloseMemHandle(ps->ipc_opened[k][h]); ps->ipc_opened[k][h] = nullptr; }
+        cudaGetLastError();
+        return fail(MPL_ERR_CUDA, std::string("peer attach: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    };
     for (int h = 0; h < world; ++h) {
         if (h == rank) {
-            ps->peer.state[0][h] = ps->state[0]; ps->peer.state[1][h] = ps->state[1];
-            ps->peer.anc[h] = ps->anc; ps->peer.mail[h] = ps->mailbox;
+            table.state[0][h] = ps->state[0]; table.state[1][h] = ps->state[1];
+            table.anc[h] = ps->anc; table.mail[h] = ps->mailbox;
             continue;
         }
         PeerBlob b;
         std::memcpy(&b, (const char*)blobs + (size_t)h * MPL_PEER_BLOB_BYTES, sizeof b);
-        void* p[4] = {nullptr, nullptr, nullptr, nullptr};
-        MPL_CUDA_OK(cudaIpcOpenMemHandle(&p[0], b.state0, cudaIpcMemLazyEnablePeerAccess));
-        MPL_CUDA_OK(cudaIpcOpenMemHandle(&p[1], b.state1, cudaIpcMemLazyEnablePeerAccess));
-        MPL_CUDA_OK(cudaIpcOpenMemHandle(&p[2], b.anc, cudaIpcMemLazyEnablePeerAccess));
-        MPL_CUDA_OK(cudaIpcOpenMemHandle(&p[3], b.mail, cudaIpcMemLazyEnablePeerAccess));
-        for (int k = 0; k < 4; ++k) ps->ipc_opened[k][h] = p[k];
-        ps->peer.state[0][h] = p[0]; ps->peer.state[1][h] = p[1];
-        ps->peer.anc[h] = (int32_t*)p[2]; ps->peer.mail[h] = (Mailbox*)p[3];
+        const cudaIpcMemHandle_t* hs[4] = {&b.state0, &b.state1, &b.anc, &b.mail};
+        for (int k = 0; k < 4; ++k) {
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, *hs[k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return rollback(e);
+            ps->ipc_opened[k][h] = p;
+        }
+        table.state[0][h] = ps->ipc_opened[0][h]; table.state[1][h] = ps->ipc_opened[1][h];
+        table.anc[h] = (int32_t*)ps->ipc_opened[2][h]; table.mail[h] = (Mailbox*)ps->ipc_opened[3][h];
     }
+    ps->peer = table;
+    fill_table_header(ps, rank, world);
     ps->peer_virtual = false;
     return MPL_OK;
 }

@@ -1,6 +1,7 @@
 // pf.cu -- ParticleSystem host driver + C ABI (reference modppl/src/inference/particle_filter.rs:8-121).
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -249,6 +250,10 @@ static int materialise(mpl_ps* ps) {
     }
     ps->launch_count++;
     MPL_CUDA_OK(cudaGetLastError());
+    // the gather is applied: the device-side "ancestors pending" flags must not make a later ESS-triggered extend
+    // (EXT_DYNAMIC reads stats->resampled_flag[t & 1]) gather a second time through the stale ancestors
+    MPL_CUDA_OK(cudaMemsetAsync((char*)ps->stats + offsetof(DeviceStats, resampled_flag), 0, sizeof(int) * 2, ps->stream));
+    MPL_CUDA_OK(cudaMemsetAsync((char*)ps->stats + offsetof(DeviceStats, resampled), 0, sizeof(int), ps->stream));
     ps->cur ^= 1;
     ps->pending_gather = false;
     ps->stats_valid = false; ps->max_valid = false;
@@ -277,7 +282,6 @@ static FixedArgs<Real> fixed_args(mpl_ps* ps, bool dynamic, bool dev_t) {
     a.sq_partials = ps->sq_partials;
     a.ess_threshold = ps->ess_threshold_abs;
     a.desc = ps->desc;
-    a.overflow_unused = nullptr;
     a.stats = ps->stats;
     a.partials = ps->ipartials;
     a.seed = ps->seed;
@@ -327,7 +331,6 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
     return MPL_OK;
 }
 
-static int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream);
 
 static int ensure_chunk_records(mpl_ps* ps) {
     if (ps->rec_e) return MPL_OK;
@@ -424,7 +427,7 @@ static int resample_exact(mpl_ps* ps, int scheme) {
     return MPL_OK;
 }
 
-static int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream) {
+int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream) {
     // categorical.rs:25-30: S_k = fl(S_{k-1} + p_k) in index order.  Short inputs: one thread adds in order.  Long inputs:
     // the parallel exact emulation of cumsum_exact.cuh (same bits).
     if (n < (size_t)4 * kCxTile) {
@@ -601,7 +604,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
     ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = 0; ps->host_seq = 0; ps->host_lse_posted = false; ps->in_device_loop = false;
     ps->nest_tile_pre = nullptr; ps->nest_sec = nullptr; ps->nest_slots = nullptr;
-    ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false;
+    ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false; ps->hist_broken = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
     ps->probs = nullptr; ps->cums = nullptr; ps->icum = nullptr; ps->obs_dev = nullptr; ps->obs_steps = 0; ps->staging = nullptr;
@@ -667,8 +670,7 @@ static int pack_obs(const mpl_ps* ps, const double* obs, size_t n_obs, Obs& o) {
     if (!obs || n_obs < (size_t)ps->model.obs_dim) return fail(MPL_ERR_INVALID, "observation vector too short for this model");
     for (int k = 0; k < 4; ++k) o.v[k] = (k < ps->model.obs_dim) ? obs[k] : 0.;
     if (ps->model.kind == M_HMM) {
-        int sym = (int)obs[0];
-        if (sym < 0 || sym >= (int)ps->model.params[1]) return fail(MPL_ERR_INVALID, "hmm observation symbol out of range");
+        if (!(obs[0] >= 0. && obs[0] < ps->model.params[1]) || obs[0] != std::floor(obs[0])) return fail(MPL_ERR_INVALID, "hmm observation symbol out of range");
     }
     return MPL_OK;
 }
@@ -869,8 +871,18 @@ struct CkptHeader {
     int64_t t;
     double lml_acc, ess, ess_stale, lse;
     uint64_t n_resamples;
+    uint64_t param_hash;   // FNV-1a over the model's parameter vector: a checkpoint continues the SAME filter only
 };
-constexpr uint64_t kCkptMagic = 0x314b434c504d6f6dull;   // "moMPLCK1"
+constexpr uint64_t kCkptMagic = 0x324b434c504d6f6dull;   // "moMPLCK2"
+uint64_t model_param_hash(const mpl_model& m) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (double v : m.params) {
+        unsigned char b[8];
+        std::memcpy(b, &v, 8);
+        for (int i = 0; i < 8; ++i) { h ^= b[i]; h *= 0x100000001b3ull; }
+    }
+    return h;
+}
 size_t ckpt_bytes(const mpl_ps* ps) { return sizeof(CkptHeader) + ((size_t)ps->D + 1) * ps->ld * (ps->dtype == MPL_F32 ? 4 : 8); }
 }  // namespace
 
@@ -895,6 +907,7 @@ extern "C" int mpl_ps_checkpoint(mpl_ps* ps, void* dst, uint64_t bytes) {
     h.D = ps->D; h.dtype = ps->dtype; h.model_kind = (int32_t)ps->model.kind; h.t = ps->t;
     h.lml_acc = ps->stats_host->lml_acc; h.ess = ps->stats_host->ess; h.ess_stale = ps->stats_host->ess_stale; h.lse = ps->stats_host->lse;
     h.n_resamples = ps->stats_host->n_resamples;
+    h.param_hash = model_param_hash(ps->model);
     std::memcpy(dst, &h, sizeof h);
     const size_t es = elem_size(ps);
     char* out = (char*)dst + sizeof h;
@@ -913,6 +926,8 @@ extern "C" int mpl_ps_restore(mpl_ps* ps, const void* src, uint64_t bytes) {
     if (h.magic != kCkptMagic || h.n != ps->n || h.ld != ps->ld || h.n_global != ps->n_global || h.D != ps->D || h.dtype != ps->dtype ||
         h.model_kind != (int32_t)ps->model.kind || h.gid_offset != ps->gid_offset)
         return fail(MPL_ERR_INVALID, "checkpoint does not fit this particle system (model, particle count, precision or shard differ)");
+    if (h.param_hash != model_param_hash(ps->model)) return fail(MPL_ERR_INVALID, "checkpoint was taken with other model parameters: the continuation would be a different filter");
+    if (h.t <= 0) return fail(MPL_ERR_INVALID, "checkpoint header: time index must be positive");
     if (h.seed != ps->seed) return fail(MPL_ERR_INVALID, "checkpoint was taken with another seed: the continuation would not reproduce the original run");
     MPL_CUDA_OK(cudaSetDevice(ps->device));
     int rc;
@@ -928,7 +943,8 @@ extern "C" int mpl_ps_restore(mpl_ps* ps, const void* src, uint64_t bytes) {
     MPL_CUDA_OK(cudaMemcpyAsync(ps->stats, ps->stats_host, sizeof(DeviceStats), cudaMemcpyHostToDevice, ps->stream));
     MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
     ps->t = h.t; ps->initialised = true; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
-    ps->prequantised = 0; ps->dynamic_state_known = true;
+    ps->prequantised = 0; ps->dynamic_state_known = true;   // (an ESS-triggered run may continue from here: nothing is pending)
+    ps->hist_broken = ps->hist_cap != 0;                    // the trajectory log does not describe the restored population
     return MPL_OK;
 }
 
@@ -952,7 +968,7 @@ extern "C" int mpl_ps_trajectories(mpl_ps* ps, const int64_t* ids, uint64_t n_id
     // out[k][t][d]: the state at step t of the lineage of particle ids[k] (`traces[ids[k]].retv`, dynunfold.rs:91)
     if (!ps || !ids || !out) return fail(MPL_ERR_INVALID, "null argument");
     if (!ps->hist_cap) return fail(MPL_ERR_INVALID, "trajectory log not enabled");
-    if (ps->dynamic_state_known) return fail(MPL_ERR_UNSUPPORTED, "trajectory log: not with the ESS-triggered device loop");
+    if (ps->hist_broken) return fail(MPL_ERR_UNSUPPORTED, "trajectory log: not after an ESS-triggered device loop or a restore (the log does not cover those steps)");
     const size_t T = (size_t)ps->t;
     if (T == 0 || T > ps->hist_cap) return fail(MPL_ERR_INVALID, "no logged steps, or more steps than the log holds");
     if (bytes != n_ids * T * ps->D * sizeof(double)) return fail(MPL_ERR_INVALID, "trajectory buffer must be double[n_ids * T * D]");
@@ -966,7 +982,9 @@ extern "C" int mpl_ps_trajectories(mpl_ps* ps, const int64_t* ids, uint64_t n_id
     MPL_CUDA_OK(cudaMalloc(&dout, bytes));
     MPL_CUDA_OK(cudaMemcpyAsync(dids, ids, n_ids * 8, cudaMemcpyHostToDevice, ps->stream));
     MPL_CUDA_OK(cudaMemcpyAsync(dres, res.data(), T * sizeof(int), cudaMemcpyHostToDevice, ps->stream));
-    const int after = (ps->pending_gather && res[T - 1]) ? 1 : 0;
+    // ids name the particles as they are NOW: after a resample that followed the last step they are post-resample particles,
+    // whether or not the gather has been applied yet (the next extend resets the entry)
+    const int after = res[T - 1] ? 1 : 0;
     const int grid = grid_for(n_ids, 128, kNumSMs * 8);
     if (ps->dtype == MPL_F32) backtrace_kernel<float><<<grid, 128, 0, ps->stream>>>((const float*)ps->hist_state, ps->hist_anc, dres, ps->ld, ps->D, (int)T, after, dids, n_ids, dout);
     else backtrace_kernel<double><<<grid, 128, 0, ps->stream>>>((const double*)ps->hist_state, ps->hist_anc, dres, ps->ld, ps->D, (int)T, after, dids, n_ids, dout);
@@ -994,6 +1012,11 @@ extern "C" int mpl_ps_sync(mpl_ps* ps) {
 extern "C" int mpl_ps_upload_observations(mpl_ps* ps, const double* obs, size_t n_steps, size_t n_obs) {
     if (!ps || !obs) return fail(MPL_ERR_INVALID, "null argument");
     if (n_obs != (size_t)ps->model.obs_dim) return fail(MPL_ERR_INVALID, "n_obs must equal the model's observation dimension");
+    if (ps->model.kind == M_HMM) {   // the kernel indexes its emission table with the symbol (models.cuh): same check as pack_obs
+        const double M = ps->model.params[1];
+        for (size_t i = 0; i < n_steps * n_obs; ++i)
+            if (!(obs[i] >= 0. && obs[i] < M) || obs[i] != std::floor(obs[i])) return fail(MPL_ERR_INVALID, "hmm observation symbol out of range (step " + std::to_string(i) + ")");
+    }
     MPL_CUDA_OK(cudaSetDevice(ps->device));
     MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
     cudaFree(ps->obs_dev); ps->obs_dev = nullptr;
@@ -1010,6 +1033,8 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
     if (!ps->obs_dev) return fail(MPL_ERR_INVALID, "mpl_ps_upload_observations first");
     if (first_step + n_steps > ps->obs_steps) return fail(MPL_ERR_INVALID, "run exceeds the uploaded observations");
     if (first_step > 0 && (long long)first_step != ps->t) return fail(MPL_ERR_INVALID, "first_step must equal the filter's current time index");
+    if (first_step == 0 && ps->world > 1 && ps->initialised)
+        return fail(MPL_ERR_UNSUPPORTED, "sharded particle system: one run from step 0 per attach (mailbox words are validated by step number and would look current)");
     const bool dynamic = ess_threshold > 0.;
     int rc0 = MPL_OK;
     if (dynamic && scheme != MPL_RESAMPLE_SYSTEMATIC_FIXED && scheme != MPL_RESAMPLE_SYSTEMATIC_NESTED)
@@ -1060,6 +1085,7 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
         ps->pending_gather = ps->stats_host->resampled_flag[ps->t & 1] != 0;
         ps->stats_valid = false; ps->max_valid = !ps->pending_gather && !dyn_nested;
         ps->dynamic_state_known = true;
+        ps->hist_broken = ps->hist_cap != 0;   // which steps resampled is only known on the device
     }
     return rc;
 }

@@ -32,14 +32,12 @@ struct DeviceStats {
     unsigned long long W;          // total integer weight (fixed schemes)
     unsigned long long rand_word;  // systematic offset word of this resample
     long long t;                   // next kernel time index (device copy, for mpl_ps_run)
-    unsigned int max_ordered;      // (unused)
     unsigned int blocks_done;      // last-block-done counter of the extend epilogue
-    unsigned int ticket;           // (unused)
+    unsigned int ticket;           // last-block-done counter of the expansion's "ancestors written" signal
     unsigned int overflow_count;
     int degenerate;                // all weights -inf seen
     int resampled;                 // 1: ancestors pending (next extend gathers, weights are zero)
     int do_resample;               // ESS trigger decision for the dynamic path
-    int pad;
     // sharded runs: block 0 of a kernel waits for the peers (system scope), publishes the global values into this
     // struct and then raises the matching ready word; the kernel's other blocks only watch that local word
     unsigned long long c_offset;   // integer weight of all lower-ranked shards
@@ -409,16 +407,12 @@ struct FixedArgs {
     int kbits;
     unsigned long long n_out; // global number of offspring (N_global)
     unsigned long long c_offset;   // integer weight of all lower-ranked shards
-    int resampled_flag[2];         // [t & 1]: the extend of step t must gather through the ancestors (set by the scan of step t-1)
-    unsigned long long n_resamples;   // resamples performed so far
-    unsigned long long max_bits[2];   // exact max of the log-weights written by the extend of step t, slot t & 1 (order-preserving bits)
     unsigned long long out_base;   // global index of this shard's first output slot
     unsigned long long n_out_local;
     double log_n_global;
     int32_t* anc;             // local output slots [out_base, out_base + n_out_local)
     int32_t src_base;         // value written for local particle 0 (global id of it, or 0)
     unsigned long long* desc;
-    void* overflow_unused;
     DeviceStats* stats;
     unsigned long long* partials;   // gridDim.x of the reduce kernel
     uint64_t seed;

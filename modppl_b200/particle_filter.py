@@ -69,6 +69,7 @@ class ParticleSystem:
         """Continue from a checkpoint taken from a filter with the same model, particle count, precision and seed."""
         buf = np.frombuffer(blob, dtype=np.uint8)
         check(lib.mpl_ps_restore(self._h, buf.ctypes.data_as(C.c_void_p), buf.size))
+        self._steps_done = int(np.frombuffer(blob, dtype=np.int64, count=1, offset=64)[0])   # CkptHeader.t
         return self
 
     def device_trace(self):

@@ -12,6 +12,8 @@ pytestmark = pytest.mark.gpu
 m = pytest.importorskip("modppl_b200")
 
 XS = np.arange(-5.0, 6.0)
+# the oracle numbers its moves; the engine selects a proposal by the reference fixture's name (mh.rs:9-14 is generic over it)
+PROPOSAL = {0: m.HIER_DRIFT, 1: m.HIER_ADD_REMOVE, 3: m.POINTED_DRIFT}
 
 
 def line_data(seed=6):
@@ -91,10 +93,10 @@ def test_hierarchical_mh_matches_oracle(move, parg, mask):
     assert rel(ch.read(), ref.read()) <= 1e-9                       # chains start from generate(args, observations)
     # warm up with a few accepted moves so that both linear and quadratic states occur
     for mv, pa in [(1, 0.025), (0, 0.1), (1, 0.025)]:
-        a = m.mh(ch, mv, pa, 3); b = ref.move(mv, pa, n_steps=3)
+        a = m.mh(ch, PROPOSAL[mv], pa, 3); b = ref.move(mv, pa, n_steps=3)
         assert a == b
     ch.write(ref.read())                                            # identical inputs for the move under test
-    acc = m.regen_mh(ch, mask, steps) if move == 2 else m.mh(ch, move, parg, steps)
+    acc = m.regen_mh(ch, mask, steps) if move == 2 else m.mh(ch, PROPOSAL[move], parg, steps)
     racc = ref.move(move, parg, mask, steps)
     st, rst = ch.read(), ref.read()
     same = np.all(np.abs(st - rst) <= 1e-9 * np.maximum(1.0, np.abs(rst)), axis=0)
@@ -114,7 +116,7 @@ def test_regen_mask_c_on_linear_trace_is_noop():                  # SURVEY 3.4: 
     for i in range(n):
         st[4, i] = O.hier_logjp(XS, ys, st[:4, i])
     ch.write(st)
-    acc = m.regen_mh(ch, m.mh.__globals__["MASK_C"], 5)
+    acc = m.regen_mh(ch, m.MASK_C, 5)
     assert acc == 5 * n
     got = ch.read()
     assert np.array_equal(got[:4], st[:4])                          # choices untouched
@@ -127,7 +129,7 @@ def test_pointed_mh_matches_oracle_and_rejects_out_of_bounds():   # tests/mh.rs:
     ch = m.Chains(m.pointed_model(bounds, cov), [0.0, 0.0], n, seed=2)
     ref = O.OracleChains("pointed", bounds + cov, [0.0, 0.0], n, seed=2)
     assert rel(ch.read(), ref.read()) <= 1e-9
-    acc = m.mh(ch, 3, 0.5, 40)                                      # drift cov 0.25 I (tests/mh.rs:28)
+    acc = m.mh(ch, m.POINTED_DRIFT, 0.5, 40)                                      # drift cov 0.25 I (tests/mh.rs:28)
     racc = ref.move(3, 0.5, n_steps=40)
     st, rst = ch.read(), ref.read()
     same = np.all(np.abs(st - rst) <= 1e-9 * np.maximum(1.0, np.abs(rst)), axis=0)
@@ -135,7 +137,7 @@ def test_pointed_mh_matches_oracle_and_rejects_out_of_bounds():   # tests/mh.rs:
     assert np.all(np.abs(st[:2]) <= 5.0)                            # uniform_2d = -inf outside => always rejected
     # posterior of latent | obs = (0, 0) is N(0, cov) truncated to the box
     many = m.Chains(m.pointed_model(bounds, cov), [0.0, 0.0], 1 << 16, seed=3)
-    m.mh(many, 3, 0.5, 400)
+    m.mh(many, m.POINTED_DRIFT, 0.5, 400)
     s = many.read()
     assert abs(np.mean(s[0])) < 0.03 and abs(np.mean(s[1])) < 0.04
     assert abs(np.var(s[0]) - 1.0) < 0.05 and abs(np.var(s[1]) - 2.0) < 0.08 and abs(np.mean(s[0] * s[1]) + 0.6) < 0.05
@@ -154,7 +156,7 @@ def test_hierarchical_sweeps_posterior():                          # config 3 sh
     a2 = m.hierarchical_sweeps(ch2, 3)
     a3 = 0
     for _ in range(3):
-        a3 += m.mh(ch3, 1, 0.025, 1) + m.mh(ch3, 0, 0.1, 3) + m.mh(ch3, 0, 0.01, 10)
+        a3 += m.mh(ch3, m.HIER_ADD_REMOVE, 0.025, 1) + m.mh(ch3, m.HIER_DRIFT, 0.1, 3) + m.mh(ch3, m.HIER_DRIFT, 0.01, 10)
     assert a2 == a3 and np.array_equal(ch2.read(), ch3.read())
     # chains that reached the quadratic mode sit at the least-squares coefficients
     quad = st[0] == 0.0
@@ -163,3 +165,42 @@ def test_hierarchical_sweeps_posterior():                          # config 3 sh
     ls = np.linalg.lstsq(A, ys, rcond=None)[0]
     good = quad & (st[4] > np.percentile(st[4], 60))
     assert np.all(np.abs(np.median(st[1:4, good], axis=1) - ls) < 0.1)
+
+
+def test_proposals_are_registered_by_name_and_unknown_names_fail():
+    hm = m.hierarchical_model(XS)
+    assert m.proposals(hm) == ["hierarchical_drift_proposal", "add_or_remove_param_proposal"]       # tests/dyngenfns/hierarchical.rs:48-71
+    assert m.proposals(m.pointed_model([-5.0, 5.0, -5.0, 5.0], [1.0, -0.6, -0.6, 2.0])) == ["pointed_2d_drift_proposal"]
+    assert m.proposals(m.line_model(XS)) == []
+    ch = m.Chains(hm, hier_data(), 64, seed=1)
+    with pytest.raises(m.MplError):
+        m.mh(ch, "pointed_2d_drift_proposal", 0.5, 1)                # registered for another model
+    with pytest.raises(m.MplError):
+        m.mh(ch, m.HIER_DRIFT, -1.0, 1)
+    pc = m.Chains(m.pointed_model([-5.0, 5.0, -5.0, 5.0], [1.0, -0.6, -0.6, 2.0]), [0.0, 0.0], 64, seed=1)
+    with pytest.raises(m.MplError):
+        m.regen_mh(pc, 1, 1)                                         # no regenerate() registered for this model
+
+
+def test_full_sweep_schedule_equals_the_moves_issued_one_by_one():  # config 3: 14 proposal moves + 4 regen_mh per sweep, one launch
+    ys = hier_data()
+    a = m.Chains(m.hierarchical_model(XS), ys, 512, seed=4)
+    b = m.Chains(m.hierarchical_model(XS), ys, 512, seed=4)
+    acc_a = m.hierarchical_full_sweeps(a, 4)
+    acc_b = 0
+    for _ in range(4):
+        acc_b += m.mh(b, m.HIER_ADD_REMOVE, 0.025, 1) + m.mh(b, m.HIER_DRIFT, 0.1, 3) + m.mh(b, m.HIER_DRIFT, 0.01, 10)
+        for mask in (m.MASK_IS_LINEAR, m.MASK_A, m.MASK_B, m.MASK_C):
+            acc_b += m.regen_mh(b, mask, 1)
+    assert acc_a == acc_b and np.array_equal(a.read(), b.read())
+
+
+def test_importance_resampling_long_input_uses_the_parallel_exact_cumsum():
+    # 2^20 proposals: the running sum goes through the parallel emulation of the sequential f64 sum (bit-exact, cumsum_exact.cuh)
+    n, n_ret = 1 << 20, 1 << 10
+    obs = line_data()
+    lat, idx, lml = m.importance_resampling(m.line_model(XS), obs, n, n_ret, seed=4, batch=3)
+    _, lnw, lml2 = m.importance_sampling(m.line_model(XS), obs, n, seed=4, batch=3)
+    assert lml == lml2
+    ridx = O.importance_resampling_indices(lnw, n_ret, seed=4, batch=3)     # the device's own weights through the oracle's sequential sum
+    assert np.sum(idx != ridx) <= 1          # (device exp vs glibc exp differ in the last bit of some weights: a draw within 1e-13 of a boundary may flip)

@@ -27,6 +27,17 @@ def test_logpdf_known_answers_on_device():           # tests/dists.rs:120-176, t
     assert abs(P.logpdf("normal", -3.14, [8.0, 20.0]) - -4.069795306758664) <= 1e-9
     assert abs(P.logpdf("mvnormal2", [1.1, 5.8], [1.3, 5.6, 1.0, -0.81, -0.81, 2.5]) - -2.1642100746383357) <= 1e-9
     assert abs(P.logpdf("mvnormal2", [30.1, -46.8], [0.0, 6.0, 496.0, 0.13, 0.13, 500.0]) - -11.750458919763666) <= 1e-9
+    # mvnormal.rs:14-22 literally (determinant + inverse per call), any k: the reference's three known answers incl. the 3-D one
+    assert abs(P.logpdf("mvnormal", [1.1, 5.8], [1.3, 5.6, 1.0, -0.81, -0.81, 2.5]) - -2.1642100746383357) <= 1e-9
+    assert abs(P.logpdf("mvnormal", [30.1, -46.8], [0.0, 6.0, 496.0, 0.13, 0.13, 500.0]) - -11.750458919763666) <= 1e-9
+    cov3 = [1.0, 0.1, 0.9, 0.1, 1.3, 0.4, 0.9, 0.4, 1.75]
+    assert abs(P.logpdf("mvnormal", [1.2, 5.1, -7.8], [1.4, 5.0, -7.4] + cov3) - -2.873267436425841) <= 1e-9      # tests/dists.rs:178-183
+    rng = np.random.default_rng(7)
+    for k in (1, 4, 5, 8):                                   # beyond the closed forms: LU / Gauss-Jordan, against the oracle
+        a = rng.normal(size=(k, k)); cov = a @ a.T + k * np.eye(k)
+        x, mu = rng.normal(size=k), rng.normal(size=k)
+        got, ref = P.logpdf("mvnormal", x, list(mu) + list(cov.ravel())), O.mvnormal_logpdf(x, mu, cov)
+        assert abs(got - ref) <= 1e-9 * max(1.0, abs(ref)), k
     assert abs(P.logpdf("bernoulli", 1.0, [0.11]) - math.log(0.11)) <= 1e-15
     assert abs(P.logpdf("bernoulli", 0.0, [0.11]) - math.log(0.89)) <= 1e-15
     assert abs(P.logpdf("uniform", 0.9, [0.5, 3.14]) - math.log(1 / 2.64)) <= 1e-15
@@ -196,8 +207,9 @@ def test_init_and_step_match_oracle(name, dtype):
     ps.write_state(ref.traces); ps.write_log_weights(ref.log_weights)
     ps.step(ys[1]); ref.step(ys[1])
     assert rel(ps.traces, ref.traces) <= tol
-    assert rel(ps.log_weights, ref.log_weights) <= tol * 10
-    assert abs(ps.log_marginal_likelihood_estimate() - ref.log_marginal_likelihood_estimate()) <= tol * 10
+    assert rel(ps.log_weights, ref.log_weights) <= tol                     # north_star: 1e-9 (fp64) / 1e-4 (fp32) relative
+    lml_ref = ref.log_marginal_likelihood_estimate()
+    assert abs(ps.log_marginal_likelihood_estimate() - lml_ref) <= tol * max(1.0, abs(lml_ref))
     assert abs(ps.effective_sample_size(False) - ref.effective_sample_size(False)) <= 1e-3 * ref.effective_sample_size(False) if dtype == "f32" else 1e-8 * n
 
 
@@ -257,6 +269,14 @@ def test_spiral_filter_config1_tracks_oracle():       # config 1: spiral model, 
     T, n = 100, 1000
     th = 2 * math.pi * np.arange(T) / T + 0.7
     ys = np.stack([0.4 * np.cos(th), 0.4 * np.sin(th)], 1)
+
+    def oracle_run(seed):
+        r = O.OraclePS("spiral", [0.1, 0.4, 0.2, 0.001], n, dtype="f64", seed=seed)
+        r.init_step(ys[0]); r.resample(0)
+        for t in range(1, T):
+            r.step(ys[t]); r.resample(0)
+        return r.log_marginal_likelihood_estimate()
+
     f = m.ParticleSystem(m.spiral_model(), n, seed=1, dtype="f64")
     r = O.OraclePS("spiral", [0.1, 0.4, 0.2, 0.001], n, dtype="f64", seed=1)
     f.init_step(ys[0]); r.init_step(ys[0])
@@ -271,7 +291,12 @@ def test_spiral_filter_config1_tracks_oracle():       # config 1: spiral model, 
         else:
             same = False     # a 1-ulp exp/sincos difference flipped one ancestor: the runs are now different samples
     assert t == T - 1
-    assert abs(f.log_marginal_likelihood_estimate() - r.log_marginal_likelihood_estimate()) < (1e-6 if same else 25.0)
+    if same:
+        assert abs(f.log_marginal_likelihood_estimate() - r.log_marginal_likelihood_estimate()) < 1e-6
+    else:   # different samples of the same estimator: within Monte Carlo error, measured on the oracle over 8 other seeds
+        lmls = np.array([oracle_run(100 + k) for k in range(8)])
+        sigma = lmls.std(ddof=1)
+        assert abs(f.log_marginal_likelihood_estimate() - lmls.mean()) <= 4.0 * sigma * math.sqrt(1 + 1 / 8)
 
 
 def test_lgssm_filter_vs_kalman_large():              # config 4 shape at 2^20 particles, T = 30: log-ML within MC error of Kalman
@@ -574,8 +599,7 @@ def test_nested_fused_epilogue_equals_standalone_quantisation():
     assert a.log_marginal_likelihood_estimate() == b.log_marginal_likelihood_estimate()
     assert np.array_equal(a.parents, b.parents)
     assert np.array_equal(a.traces, b.traces)
-    truth = O.kalman_lml_lgssm4(0.1, 0.5, 1.0, ys)
-    assert abs(a.log_marginal_likelihood_estimate() - truth) < 1.0
+    # (truth check of this scheme at benchmark-like sizes: test_benchmarked_schemes_vs_kalman_within_mc_error)
 
 
 @pytest.mark.parametrize("world,dtype", [(2, "f32"), (4, "f32"), (8, "f32"), (2, "f64"), (4, "f64")])
@@ -712,3 +736,100 @@ def test_checkpoint_restore_continues_bit_for_bit(dtype, scheme):
     assert a.num_resamples() == b.num_resamples()
     with pytest.raises(m.MplError):
         m.ParticleSystem(m.lgssm4(), n, seed=12, dtype=dtype).restore(blob)      # another seed would not reproduce the run
+
+
+# ------------------------------------------------------------------------------------------------- truth at benchmark-like sizes
+@pytest.mark.parametrize("scheme", [m.SYSTEMATIC_FIXED, m.SYSTEMATIC_NESTED])
+def test_benchmarked_schemes_vs_kalman_within_mc_error(scheme):
+    # config 4 as bench.py runs it (fp32, device-resident loop, resample every step), N = 2^22, T = 200: the log-ML estimate of
+    # seed 0 lies within 4 sigma of the Kalman filter's exact value, sigma estimated from 8 further seeds
+    T, n = 200, 1 << 22
+    ys = lgssm_data(T)
+    truth = O.kalman_lml_lgssm4(0.1, 0.5, 1.0, ys)
+    est = []
+    for seed in range(9):
+        f = m.ParticleSystem(m.lgssm4(), n, seed=seed, dtype="f32")
+        f.upload_observations(ys)
+        f.run(0, T, scheme)
+        est.append(f.log_marginal_likelihood_estimate())
+        f.close()
+    est = np.array(est)
+    sigma = est[1:].std(ddof=1)
+    assert sigma < 0.5                                     # (N = 2^22: the estimator is tight; a broken resampler is not)
+    assert abs(est[0] - truth) <= 4.0 * sigma, (est, truth, sigma)
+    # the mean over the 9 seeds: 4 sigma of a mean of 9, plus the estimator's own Jensen bias sigma^2 / 2, plus 0.01 absolute for
+    # 200 steps of fp32 arithmetic and the resampler's 2^-22 floors
+    assert abs(est.mean() - truth) <= 4.0 * sigma / 3.0 + sigma * sigma / 2 + 0.01, (est.mean(), truth, sigma)
+    print(f"scheme {scheme}: truth {truth:.4f} est {est[0]:.4f} mean {est.mean():.4f} sigma {sigma:.4f}")
+
+
+# ------------------------------------------------------------------------------------------------- regressions (round-1 review)
+@pytest.mark.parametrize("scheme", [m.SYSTEMATIC_FIXED, m.SYSTEMATIC_NESTED])
+def test_ess_triggered_run_survives_checkpoint_and_reads(scheme):
+    # an ESS-triggered run that ends on a resample leaves the gather pending; reading the traces or taking a checkpoint
+    # applies it, and the continuation must not gather a second time through the stale ancestors
+    T, n = 40, 1 << 17
+    ys = np.random.default_rng(5).normal(size=(T, 1)) * 0.6
+    sv = lambda: m.ParticleSystem(m.Model("sv", [-1.024, 0.9702, 0.178]), n, seed=9, dtype="f32")
+    whole = sv(); whole.upload_observations(ys); whole.run(0, T, scheme, ess_threshold=0.5)
+    assert whole.num_resamples() >= 2
+    for cut in range(2, T - 1):                           # find a cut right after a resampling step
+        probe = sv(); probe.upload_observations(ys); probe.run(0, cut, scheme, ess_threshold=0.5)
+        before = probe.num_resamples()
+        probe.run(cut, 1, scheme, ess_threshold=0.5)
+        if probe.num_resamples() > before:
+            cut += 1
+            break
+    else:
+        pytest.skip("no resampling step found")
+    a = sv(); a.upload_observations(ys); a.run(0, cut, scheme, ess_threshold=0.5)
+    _ = a.traces                                          # materialises the pending gather
+    blob = a.checkpoint()
+    a.run(cut, T - cut, scheme, ess_threshold=0.5)
+    b = sv().restore(blob); b.upload_observations(ys); b.run(cut, T - cut, scheme, ess_threshold=0.5)
+    for f in (a, b):
+        assert f.log_marginal_likelihood_estimate() == whole.log_marginal_likelihood_estimate()
+        assert np.array_equal(f.traces, whole.traces)
+        assert f.num_resamples() == whole.num_resamples()
+
+
+def test_checkpoint_right_after_resample_and_parameter_guard():
+    T, n = 6, 20000
+    ys = lgssm_data(T)
+    a = m.ParticleSystem(m.lgssm4(), n, seed=2, dtype="f32")
+    a.init_step(ys[0]); a.resample(m.SYSTEMATIC_NESTED)
+    a.step(ys[1]); a.resample(m.SYSTEMATIC_NESTED)
+    blob = a.checkpoint()                                 # gather pending at the time of the call
+    b = m.ParticleSystem(m.lgssm4(), n, seed=2, dtype="f32").restore(blob)
+    for f in (a, b):
+        for y in ys[2:]:
+            f.step(y); f.resample(m.SYSTEMATIC_NESTED)
+    assert a.log_marginal_likelihood_estimate() == b.log_marginal_likelihood_estimate()
+    assert np.array_equal(a.traces, b.traces)
+    with pytest.raises(m.MplError):                       # same model kind, other parameters: a different filter
+        m.ParticleSystem(m.lgssm4(0.2, 0.5, 1.0), n, seed=2, dtype="f32").restore(blob)
+
+
+def test_trajectories_after_reading_state_post_resample():
+    T, n = 5, 3000
+    ys = lgssm_data(T)
+    f = m.ParticleSystem(m.lgssm4(), n, seed=3, dtype="f64")
+    f.enable_history(T)
+    f.init_step(ys[0]); f.resample(m.SYSTEMATIC_FIXED)
+    for y in ys[1:]:
+        f.step(y); f.resample(m.SYSTEMATIC_FIXED)
+    ids = [0, 17, n - 1]
+    before = f.trajectories(ids)
+    live = f.traces                                       # applies the pending gather; the ids still name post-resample particles
+    after = f.trajectories(ids)
+    assert np.array_equal(before, after)
+    assert np.array_equal(after[:, -1, :], live[:, ids].T)
+
+
+def test_hmm_uploaded_observations_are_validated():
+    model = m.hmm(HMM3["prior"], HMM3["emission"], HMM3["transition"])
+    f = m.ParticleSystem(model, 1000, seed=1, dtype="f64")
+    for bad in ([[0.0], [3.0]], [[-1.0]], [[0.5]], [[float("nan")]]):
+        with pytest.raises(m.MplError):
+            f.upload_observations(np.array(bad))
+    f.upload_observations(np.array(HMM3["obs"], float)[:, None])
