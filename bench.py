@@ -335,7 +335,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------------ config 4, one GPU
 PROFILE_KERNELS = ("extend", "fixed_reduce", "fixed_scan", "fixed_overflow", "fixed_cumsum", "fixed_search", "nested_quantise", "nested_sections", "nested_level1",
-                   "nested_scan", "nested_top", "weight_reduce", "normalize", "cumsum_exact", "search")
+                   "nested_plan", "nested_expand", "nested_heavy", "weight_reduce", "normalize", "cumsum_exact", "search")
 
 
 def time_scheme(ps, m, ys, t_first, scheme, steps, warm=3):

@@ -184,7 +184,7 @@ int mpl_logpdf(const char* dist, const double* x, const double* params, size_t n
 /* ---- multi-GPU (one process per GPU) ---------------------------------------------------------------- */
 /* Peer (NVLink) exchange without a host round trip.  Each rank exports a handle blob, the caller all-gathers the
  * blobs with whatever transport it has (torch.distributed in bench.py) and attaches them. */
-#define MPL_PEER_BLOB_BYTES 256
+#define MPL_PEER_BLOB_BYTES 1024
 int mpl_ps_peer_export(mpl_ps*, void* blob /* MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_attach(mpl_ps*, int rank, int world, const void* blobs /* world * MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_detach(mpl_ps*);

@@ -36,7 +36,10 @@ struct mpl_ps {
     cudaStream_t stream;
     void* state[2];   // D x ld Real
     int cur;          // index of the live state buffer
-    void* lw;         // ld Real
+    void* lw;         // ld Real: the log-weights in use
+    void* lw_alt;     // sharded runs only: the other buffer of the pair (every extend writes the one the previous step did not, see PeerTable::lw)
+    int par;          // which of the pair `lw` is (index into PeerTable::lw / rec_e / rec_S; 0 on one GPU)
+    bool anc_pushed;  // sharded: the last resample's ancestors were pushed by the peers (single-level scheme) -> the next extend waits for their flags
     int32_t* anc;     // ld
     double* probs;    // ld (exact schemes), lazily allocated
     double* cums;     // ld
@@ -64,8 +67,10 @@ struct mpl_ps {
     bool host_lse_posted;   // the last resample posts its result there (nested scheme, not ESS-triggered)
     // trajectory reconstruction (reference keeps traces[i].retv as a Vec<State>, dynunfold.rs:91-92): optional log of the
     // per-step states and ancestors, back-traced on demand
-    int* rec_e; unsigned int* rec_S; float* rec_sq;   // chunk records of the nested scheme (ld / 128 entries), lazily allocated
-    unsigned long long* nest_tile_pre; unsigned long long* nest_sec; void* nest_slots;   // nested scheme: tile prefixes inside a section; section records + top-level prefixes
+    int* rec_e; unsigned int* rec_S; float* rec_sq;   // chunk records of the nested scheme in use (ld / 128 entries), lazily allocated ...
+    int* rec_e2; unsigned int* rec_S2;               // ... as parity `par` of these pairs
+    unsigned long long* nest_tile_pre; unsigned long long* nest_sec;   // nested scheme: tile prefixes inside a section; section records + top-level prefixes
+    unsigned int* nest_P; unsigned int* nest_F;      // nested scheme: the plan pass' output (first slot of every GLOBAL chunk, first chunk of every output tile)
     int prequantised;            // the last extend's fused epilogue left 1: integer weights + chunk records, 2: chunk records only (log-weights kept)
     void* hist_state;            // [hist_cap][D][ld] Real
     int32_t* hist_anc;           // [hist_cap][ld]
@@ -81,7 +86,7 @@ struct mpl_ps {
     int rank, world;
     mpl::PeerTable peer;
     mpl::Mailbox* mailbox;            // device memory of this rank, written by every rank
-    void* ipc_opened[4][mpl::kMaxPeers];   // pointers obtained from cudaIpcOpenMemHandle (to close on detach)
+    void* ipc_opened[8][mpl::kMaxPeers];   // pointers obtained from cudaIpcOpenMemHandle (to close on detach)
     bool peer_virtual;                // peers live in this process (single-GPU emulation used by the tests)
 };
 
@@ -91,6 +96,7 @@ int ps_phase_extend(mpl_ps* ps, bool init, bool fuse_nested = false);
 int ps_phase_nested(mpl_ps* ps, int phase);
 int ps_phase_reduce(mpl_ps* ps);
 int ps_phase_scan(mpl_ps* ps);
+int ensure_chunk_records(mpl_ps* ps);
 // categorical.rs:25-30: the sequential f64 running sum of `probs`, bit for bit (parallel emulation for long inputs); ps may be null
 int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream);
 }

@@ -17,9 +17,33 @@
 using namespace mpl;
 
 namespace {
+constexpr int kPeerHandles = 8;
 struct PeerBlob {   // must fit MPL_PEER_BLOB_BYTES
-    cudaIpcMemHandle_t state0, state1, anc, mail;   // 4 x 64 bytes
+    cudaIpcMemHandle_t h[kPeerHandles];   // state0, state1, anc, mailbox, lw pair, chunk-record pairs (e, S): 8 x 64 bytes
 };
+void* const* peer_buffers(mpl_ps* ps, void* (&out)[kPeerHandles]) {
+    out[0] = ps->state[0]; out[1] = ps->state[1]; out[2] = ps->anc; out[3] = ps->mailbox;
+    out[4] = ps->par == 0 ? ps->lw : ps->lw_alt; out[5] = ps->par == 0 ? ps->lw_alt : ps->lw; out[6] = ps->rec_e2; out[7] = ps->rec_S2;
+    return out;
+}
+// fills rank h's column of the peer table from its 8 buffers (own pointers or IPC-mapped ones)
+void set_peer_column(mpl_ps* ps, PeerTable& t, int h, void* const* b) {
+    const size_t nch = ps->ld / kChunk;
+    t.state[0][h] = b[0]; t.state[1][h] = b[1]; t.anc[h] = (int32_t*)b[2]; t.mail[h] = (Mailbox*)b[3];
+    t.lw[0][h] = b[4]; t.lw[1][h] = b[5];
+    for (int p = 0; p < 2; ++p) { t.rec_e[p][h] = (const int*)b[6] + (size_t)p * nch; t.rec_S[p][h] = (const unsigned int*)b[7] + (size_t)p * nch; }
+}
+// the second log-weight buffer and the chunk records exist before anything is exported (sharded runs alternate them)
+int ensure_pairs(mpl_ps* ps) {
+    int rc = ensure_chunk_records(ps);
+    if (rc) return rc;
+    if (!ps->lw_alt) {
+        const size_t bytes = ps->ld * (ps->dtype == MPL_F64 ? 8 : 4);
+        MPL_CUDA_OK(cudaMalloc(&ps->lw_alt, bytes));
+        MPL_CUDA_OK(cudaMemset(ps->lw_alt, 0, bytes));
+    }
+    return MPL_OK;
+}
 static_assert(sizeof(PeerBlob) <= MPL_PEER_BLOB_BYTES, "peer blob too large");
 
 int ensure_mailbox(mpl_ps* ps) {
@@ -56,12 +80,12 @@ extern "C" int mpl_ps_peer_export(mpl_ps* ps, void* blob) {
     // mailbox (its words are validated by step number only)
     MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
     MPL_CUDA_OK(cudaMemset(ps->mailbox, 0, sizeof(Mailbox)));
+    if ((rc = ensure_pairs(ps))) return rc;
     PeerBlob b;
     std::memset(&b, 0, sizeof b);
-    MPL_CUDA_OK(cudaIpcGetMemHandle(&b.state0, ps->state[0]));
-    MPL_CUDA_OK(cudaIpcGetMemHandle(&b.state1, ps->state[1]));
-    MPL_CUDA_OK(cudaIpcGetMemHandle(&b.anc, ps->anc));
-    MPL_CUDA_OK(cudaIpcGetMemHandle(&b.mail, ps->mailbox));
+    void* bufs[kPeerHandles];
+    peer_buffers(ps, bufs);
+    for (int k = 0; k < kPeerHandles; ++k) MPL_CUDA_OK(cudaIpcGetMemHandle(&b.h[k], bufs[k]));
     std::memset(blob, 0, MPL_PEER_BLOB_BYTES);
     std::memcpy(blob, &b, sizeof b);
     return MPL_OK;
@@ -78,29 +102,26 @@ extern "C" int mpl_ps_peer_attach(mpl_ps* ps, int rank, int world, const void* b
     // open every handle first (recording each as it is opened); only a complete table is committed
     PeerTable table = ps->peer;
     auto rollback = [&](cudaError_t e) {
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < kPeerHandles; ++k)
             for (int h = 0; h < kMaxPeers; ++h)
                 if (ps->ipc_opened[k][h]) { cudaIpcCloseMemHandle(ps->ipc_opened[k][h]); ps->ipc_opened[k][h] = nullptr; }
         cudaGetLastError();
         return fail(MPL_ERR_CUDA, std::string("peer attach: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
     };
+    if ((rc = ensure_pairs(ps))) return rc;
     for (int h = 0; h < world; ++h) {
-        if (h == rank) {
-            table.state[0][h] = ps->state[0]; table.state[1][h] = ps->state[1];
-            table.anc[h] = ps->anc; table.mail[h] = ps->mailbox;
-            continue;
-        }
+        void* bufs[kPeerHandles];
+        if (h == rank) { set_peer_column(ps, table, h, peer_buffers(ps, bufs)); continue; }
         PeerBlob b;
         std::memcpy(&b, (const char*)blobs + (size_t)h * MPL_PEER_BLOB_BYTES, sizeof b);
-        const cudaIpcMemHandle_t* hs[4] = {&b.state0, &b.state1, &b.anc, &b.mail};
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kPeerHandles; ++k) {
             void* p = nullptr;
-            cudaError_t e = cudaIpcOpenMemHandle(&p, *hs[k], cudaIpcMemLazyEnablePeerAccess);
+            cudaError_t e = cudaIpcOpenMemHandle(&p, b.h[k], cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) return rollback(e);
             ps->ipc_opened[k][h] = p;
+            bufs[k] = p;
         }
-        table.state[0][h] = ps->ipc_opened[0][h]; table.state[1][h] = ps->ipc_opened[1][h];
-        table.anc[h] = (int32_t*)ps->ipc_opened[2][h]; table.mail[h] = (Mailbox*)ps->ipc_opened[3][h];
+        set_peer_column(ps, table, h, bufs);
     }
     ps->peer = table;
     fill_table_header(ps, rank, world);
@@ -113,11 +134,17 @@ extern "C" int mpl_ps_peer_detach(mpl_ps* ps) {
     if (ps->world <= 1) return MPL_OK;
     cudaStreamSynchronize(ps->stream);
     if (!ps->peer_virtual)
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < kPeerHandles; ++k)
             for (int h = 0; h < kMaxPeers; ++h)
                 if (ps->ipc_opened[k][h]) { cudaIpcCloseMemHandle(ps->ipc_opened[k][h]); ps->ipc_opened[k][h] = nullptr; }
     std::memset(&ps->peer, 0, sizeof ps->peer);
-    ps->peer.world = 1; ps->world = 1; ps->rank = 0;
+    ps->peer.world = 1; ps->world = 1; ps->rank = 0; ps->anc_pushed = false;
+    void* bufs[kPeerHandles];
+    PeerTable t = ps->peer;
+    set_peer_column(ps, t, 0, peer_buffers(ps, bufs));   // back to one GPU: the self-table of ensure_chunk_records
+    for (int p = 0; p < 2; ++p) { t.lw[p][0] = ps->lw; t.rec_e[p][0] = ps->rec_e; t.rec_S[p][0] = ps->rec_S; }
+    t.n_loc = (unsigned int)ps->n;
+    ps->peer = t;
     return MPL_OK;
 }
 
@@ -168,14 +195,15 @@ extern "C" int mpl_test_virtual_shards_scheme(const mpl_model* model, uint64_t n
         if (!sh[g]) rc = MPL_ERR_CUDA;
         else rc = mpl_ps_upload_observations(sh[g], obs, n_steps, n_obs);
         if (rc == MPL_OK) rc = ensure_mailbox(sh[g]);
+        if (rc == MPL_OK && world > 1) rc = ensure_pairs(sh[g]);
     }
     if (rc == MPL_OK && world > 1) {
         for (int g = 0; g < world; ++g) {
             fill_table_header(sh[g], g, world);
             sh[g]->peer_virtual = true;
             for (int h = 0; h < world; ++h) {
-                sh[g]->peer.state[0][h] = sh[h]->state[0]; sh[g]->peer.state[1][h] = sh[h]->state[1];
-                sh[g]->peer.anc[h] = sh[h]->anc; sh[g]->peer.mail[h] = sh[h]->mailbox;
+                void* bufs[kPeerHandles];
+                set_peer_column(sh[g], sh[g]->peer, h, peer_buffers(sh[h], bufs));
             }
         }
     }

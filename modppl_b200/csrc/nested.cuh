@@ -15,8 +15,16 @@
 // particles by q_i (l*S_c + U_c); U_s and U_c are hashed from the step's random word and the section / chunk number.
 // All of it is integer arithmetic: unbiased up to the floors (relative 2^-22), independent of thread order and of how
 // the particles are sharded (sections are aligned groups of global ids).
-// Kernels per resample: [quantise, unless the extend kernel's epilogue did it] -> section pass -> level-1 pass -> expansion
-// [-> heavy-tile pass once a heavy warp tile has been seen].
+// Kernels per resample: [quantise, unless the extend kernel's epilogue did it] -> section pass (+ top level) -> plan pass
+// (level 1: first output slot of every chunk) -> expansion (level 2: offspring counts of every particle, expanded into the
+// ancestor slots) [-> heavy-tile pass once a heavy warp tile has been seen].
+//
+// Levels 1 and 2 are organised by the slots a GPU has to FILL, not by the particles it owns: a block of the plan pass takes
+// one section whose slots fall into this GPU's slot range -- wherever that section's particles live -- and the expansion
+// walks the chunks that own those slots.  Across GPUs everything is therefore a remote LOAD (chunk records, integer
+// weights) issued after the step's only gate, the exchange of section records; nothing is ever stored into another GPU's
+// memory (a kernel that has stored into a peer's memory cannot complete before those stores are acknowledged, ~4 us at
+// every kernel boundary), and no rank waits for another's ancestors.
 #pragma once
 
 namespace mpl {
@@ -34,7 +42,8 @@ struct NestedPrefixes {
     unsigned long long* sec_M;      // [GLOBAL section] M_s
     unsigned long long* sec_a;      // [GLOBAL section] first output slot of the section                (top-level pass)
     unsigned long long* sec_n;      // [GLOBAL section] number of output slots of the section
-    uint2* slots;                   // [local chunk] (first global output slot, number of slots)          (level-1 pass)
+    unsigned int* P;                // [GLOBAL chunk, + 1 sentinel] first output slot of the chunk (monotone; chunk c owns [P[c], P[c+1]))  (plan pass)
+    unsigned int* F;                // [GLOBAL output tile] the chunk that owns the tile's first slot
     unsigned int sec0;              // global number of this shard's first section
     unsigned int n_sec;             // sections of this shard
     unsigned int n_sec_global;
@@ -209,7 +218,7 @@ __device__ __forceinline__ void collect_section_records(const PeerTable& p, long
     SpinGuard g(p);
     for (unsigned int sg = threadIdx.x; sg < nb.n_sec_global; sg += kScanThreads) {
         if (sg - nb.sec0 < nb.n_sec) continue;   // own sections: already in place
-        const volatile unsigned long long* src = p.mail[sg / nb.n_sec]->sec_ll[sg];   // (equal shards of whole sections: the owner of global section sg)
+        const volatile unsigned long long* src = p.mail[sg / nb.n_sec]->sec_ll[epoch & 1][sg];   // (equal shards of whole sections: the owner of global section sg)
         unsigned long long w[6];
         for (;;) {   // all six tagged words in flight together: one NVLink round trip per poll
 #pragma unroll
@@ -241,7 +250,7 @@ __device__ __forceinline__ void nested_post_to_host(const FixedArgs<Real>& a, do
     hm[2] = (unsigned long long)(unsigned int)degenerate | tag;
 }
 
-// scalar bookkeeping of resample(): particle_filter.rs:104-105,114 (one thread of the level-1 pass)
+// scalar bookkeeping of resample(): particle_filter.rs:104-105,114 (one thread of the plan pass)
 template <typename Real>
 __device__ __forceinline__ void nested_bookkeeping(const FixedArgs<Real>& a, DeviceStats* st, long long epoch) {
     const unsigned long long W = st->W;
@@ -333,7 +342,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
         if (tile < num_tiles) nb.tile_pre[tile] = incl - v;
         const unsigned long long T_s = __shfl_sync(0xffffffffu, incl, 31);
         if (a.peer.world > 1 && lane == 0) {   // published in this GPU's own mailbox (tagged words); the other ranks read it from there
-            unsigned long long* dst = a.peer.mail[a.peer.rank]->sec_ll[sg];
+            unsigned long long* dst = a.peer.mail[a.peer.rank]->sec_ll[epoch & 1][sg];
             ll_write64(dst, (unsigned long long)(unsigned int)E_s, (unsigned int)epoch);
             ll_write64(dst + 2, T_s, (unsigned int)epoch);
             ll_write64(dst + 4, (unsigned long long)__double_as_longlong(sq), (unsigned int)epoch);
@@ -355,8 +364,118 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     }
 }
 
-// exclusive prefix (over the warp) of each lane's 4 particles inside chunk r, for the 4 chunks of a warp tile
-__device__ __forceinline__ void chunk_exclusive_prefixes(const unsigned int (&q)[4][4], unsigned int (&excl)[4]) {
+// ---- plan pass (level 1): one block per GLOBAL section; only the sections whose slots touch this shard's slot range do
+// anything.  For such a section: chunk masses G_c = S_c >> (E_s - e_c) from the chunk records (read from the GPU that owns the
+// particles), their exclusive prefixes, and from those -- exactly, 128-bit once per thread -- the first output slot of every
+// chunk; then per chunk the level-2 constants, and for every output tile that starts inside the section the chunk owning
+// its first slot.
+constexpr int kChunksPerSection = (int)(kSection / kChunk);   // 1024
+
+template <typename Real>
+__global__ void __launch_bounds__(kScanThreads) nested_plan_kernel(FixedArgs<Real> a, NestedPrefixes nb, int par, unsigned int n_chunks_global) {
+    __shared__ unsigned long long wtot[kScanThreads / 32];
+    __shared__ unsigned int Ps[kChunksPerSection + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DeviceStats* st = a.stats;
+    pdl_wait();
+    pdl_trigger();   // the expansion may become resident
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    if (a.dynamic && !st->do_resample) {   // ESS above the threshold: keep the population, weights keep accumulating
+        if (blockIdx.x == 0 && tid == 0) st->resampled_flag[epoch & 1] = 0;
+        return;
+    }
+    if (blockIdx.x == 0 && tid == 0) { st->trace[10] = global_ns(); nested_bookkeeping(a, st, epoch); }
+    const unsigned long long W = st->W;
+    if (W == 0ull) return;   // degenerate: the expansion writes identity ancestors
+    const unsigned int sg = blockIdx.x;
+    const unsigned long long n_s = nb.sec_n[sg], a_s = nb.sec_a[sg], T_s = nb.sec_T[sg];
+    const int E_s = nb.sec_E[sg];
+    // this shard fills the slots [w0, w_end); the tile after its last one starts at w_end and its first chunk is needed too
+    const unsigned long long w0 = a.out_base, w_end = a.out_base + a.n_out_local, w1 = w_end < a.n_out ? w_end : a.n_out - 1;
+    if (a_s > w_end || a_s + n_s < w0) return;   // (closed comparison: empty sections sitting on an edge of the range are kept: P stays monotone)
+    const unsigned int cg0 = sg * (unsigned int)kChunksPerSection;
+    const unsigned int cnt = min((unsigned int)kChunksPerSection, n_chunks_global - cg0);   // chunks of this section
+    if (n_s == 0ull || T_s == 0ull) {   // no slot: every chunk "starts" at the section's first slot (keeps P monotone)
+        for (unsigned int c = tid; c <= cnt; c += kScanThreads) nb.P[cg0 + c] = (unsigned int)a_s;
+        return;
+    }
+    // the section's chunk records, from the GPU that owns its particles
+    const unsigned int owner = a.peer.world > 1 ? peer_owner(a.peer, cg0 * (unsigned int)kChunk) : 0u;
+    const unsigned int c_loc0 = cg0 - owner * (a.peer.n_loc / (unsigned int)kChunk);
+    const int* rec_e = a.peer.rec_e[par][owner] + c_loc0;
+    const unsigned int* rec_S = a.peer.rec_S[par][owner] + c_loc0;
+    unsigned int S[4];
+    unsigned long long G[4], tot = 0;
+    {
+        int4 ev = make_int4(kChunkEmpty, kChunkEmpty, kChunkEmpty, kChunkEmpty);
+        uint4 sv = make_uint4(0u, 0u, 0u, 0u);
+        if (4u * tid + 3u < cnt) { ev = *reinterpret_cast<const int4*>(rec_e + 4 * tid); sv = *reinterpret_cast<const uint4*>(rec_S + 4 * tid); }
+        else {
+            int e4[4] = {kChunkEmpty, kChunkEmpty, kChunkEmpty, kChunkEmpty};
+            unsigned int s4[4] = {0u, 0u, 0u, 0u};
+            for (int i = 0; i < 4; ++i) if (4u * tid + i < cnt) { e4[i] = rec_e[4 * tid + i]; s4[i] = rec_S[4 * tid + i]; }
+            ev = make_int4(e4[0], e4[1], e4[2], e4[3]); sv = make_uint4(s4[0], s4[1], s4[2], s4[3]);
+        }
+        const int e4[4] = {ev.x, ev.y, ev.z, ev.w};
+        S[0] = sv.x; S[1] = sv.y; S[2] = sv.z; S[3] = sv.w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { G[i] = nested_shift(S[i], e4[i], E_s); tot += G[i]; }
+    }
+    unsigned long long incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    unsigned long long pre = incl - tot;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) if (w < warp) pre += wtot[w];
+    {   // slots below the thread's first chunk (exact), then its next three relative to that
+        const double inv_t = 1. / (double)T_s;
+        const TileBase base = tile_base_exact(pre, T_s, nested_section_offset(st->rand_word, sg, T_s), n_s, inv_t);
+        unsigned long long g = 0;
+        unsigned int below = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (4u * tid + i < cnt) Ps[4 * tid + i] = (unsigned int)(a_s + base.n_start) + below;
+            g += G[i];
+            below = local_count(g, base.rem, (double)base.rem, T_s, (double)n_s, n_s, inv_t);
+        }
+    }
+    if (tid == 0) Ps[cnt] = (unsigned int)(a_s + n_s);   // every slot of the section is owned by one of its chunks
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned int c = 4u * tid + i;
+        if (c >= cnt) break;
+        nb.P[cg0 + c] = Ps[c];
+    }
+    if (tid == 0) nb.P[cg0 + cnt] = Ps[cnt];   // == first slot of the next section (or the sentinel N after the last one)
+    if (a_s + n_s == a.n_out) {   // the section that owns the last slot: F's entry after the last tile names the last chunk that owns a slot
+        const unsigned int j = (unsigned int)(a.n_out - 1);
+        if (tid == 0) {
+            unsigned int c = 0;
+#pragma unroll
+            for (int step = kChunksPerSection / 2; step > 0; step >>= 1) if (c + step < cnt && Ps[c + step] <= j) c += step;
+            nb.F[(a.n_out + kScanTile - 1) / kScanTile] = cg0 + c;
+        }
+    }
+    // output tiles that start inside this section (and belong to this shard, or directly follow its last one)
+    const unsigned long long lo = a_s > w0 ? a_s : w0, hi = a_s + n_s - 1 < w1 ? a_s + n_s - 1 : w1;   // first slots of interest, inclusive
+    if (lo <= hi) {
+        for (unsigned long long T = (lo + kScanTile - 1) / kScanTile + tid; T * kScanTile <= hi; T += kScanThreads) {
+            const unsigned int j = (unsigned int)(T * kScanTile);
+            unsigned int c = 0;   // max{c < cnt : Ps[c] <= j}
+#pragma unroll
+            for (int step = kChunksPerSection / 2; step > 0; step >>= 1) if (c + step < cnt && Ps[c + step] <= j) c += step;
+            nb.F[T] = cg0 + c;
+        }
+    }
+}
+
+// ---- expansion (level 2) ---------------------------------------------------------------------------------------------------
+// exclusive prefix (over the warp) of each lane's 4 particles inside chunk r, for the 4 chunks of a warp tile; lane r < 4 gets
+// the total S_c of chunk r in S_w
+__device__ __forceinline__ void chunk_exclusive_prefixes(const unsigned int (&q)[4][4], unsigned int (&excl)[4], unsigned int& S_w) {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -365,6 +484,8 @@ __device__ __forceinline__ void chunk_exclusive_prefixes(const unsigned int (&q)
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned int up = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += up; }
         excl[r] = inc - own;
+        const unsigned int t = __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == r) S_w = t;
     }
 }
 
@@ -392,112 +513,71 @@ __device__ __forceinline__ unsigned int level2_count(unsigned int C, float Cf, u
     return diff < 0.f ? f - 1u : f;
 }
 
-// ---- level-1 pass: one warp per tile (lane <-> chunk): the tile's first slot inside its section, then the slot range of
-// every chunk.  (Kept out of the expansion kernel: there it would hold up seven warps per tile behind one.)
-template <typename Real>
-__global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
-                                                                     unsigned int num_chunks) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    DeviceStats* st = a.stats;
-    const unsigned int tile = blockIdx.x * (kScanThreads / 32) + warp;
-    const unsigned int c_l = tile * kChunksPerTile + lane;
-    unsigned int S_l = 0;
-    int e_l = kChunkEmpty;
-    if (tile < num_tiles && c_l < num_chunks) { S_l = rec.S[c_l]; e_l = rec.e[c_l]; }   // (written two kernels ago: complete)
-    pdl_wait();
-    pdl_trigger();   // the expansion kernel may become resident and load its weights
-    if (a.dynamic && !st->do_resample) {   // ESS above the threshold: keep the population, weights keep accumulating
-        if (blockIdx.x == 0 && tid == 0) st->resampled_flag[(a.epoch < 0 ? st->t : a.epoch) & 1] = 0;
-        return;
-    }
-    if (blockIdx.x == 0 && tid == 0) { st->trace[10] = global_ns(); nested_bookkeeping(a, st, a.epoch < 0 ? st->t : a.epoch); }
-    const unsigned long long W = st->W;
-    if (tile >= num_tiles || W == 0ull) return;
-    const unsigned int sg = nb.sec0 + tile / kTilesPerSection;
-    const unsigned long long T_s = nb.sec_T[sg], n_s = nb.sec_n[sg], a_s = nb.sec_a[sg], pre_t = nb.tile_pre[tile];
-    const int E_s = nb.sec_E[sg];
-    uint2 out = make_uint2(0u, 0u);
-    if (n_s != 0ull && T_s != 0ull) {
-        const double inv_t = 1. / (double)T_s;
-        const TileBase base = tile_base_exact(pre_t, T_s, nested_section_offset(st->rand_word, sg, T_s), n_s, inv_t);
-        unsigned long long gi = nested_shift(S_l, e_l, E_s);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, gi, o); if (lane >= o) gi += up; }
-        const unsigned int slot_end = local_count(gi, base.rem, (double)base.rem, T_s, (double)n_s, n_s, inv_t);   // slots of the tile up to and including chunk l
-        unsigned int slot_beg = __shfl_up_sync(0xffffffffu, slot_end, 1);
-        if (lane == 0) slot_beg = 0;
-        out = make_uint2((unsigned int)(a_s + base.n_start) + slot_beg, slot_end - slot_beg);
-    }
-    if (c_l < num_chunks) nb.slots[c_l] = out;
-}
-
-// several GPUs, end of the expansion kernel (every thread of every block calls it): once ALL blocks are through, the last
-// one tells every rank that this shard has written every ancestor it owes.  Blocks that stored into another GPU's array
-// make those stores visible system-wide first; the ticket orders everything else.
-__device__ __forceinline__ void nested_signal_done(const PeerTable& peer, DeviceStats* st, long long epoch, bool remote) {
-    const int any_remote = __syncthreads_or(remote ? 1 : 0);
-    if (threadIdx.x == 0) {
-        if (any_remote) __threadfence_system(); else __threadfence();
-        if (atomicAdd(&st->ticket, 1u) == gridDim.x - 1) {
-            st->ticket = 0;
-            __threadfence();
-            st->trace[8] = global_ns();
-            for (int h = 0; h < peer.world; ++h) *(volatile long long*)&peer.mail[h]->flag_done[peer.rank] = epoch;
-        }
-    }
-}
-
-// The lane's 16 integer weights of a warp tile (round r == chunk 4*warp + r of the tile) and their exclusive prefixes.
+// The lane's 16 integer weights of GLOBAL warp tile `wt` (chunks 4 wt .. 4 wt + 3; round r == chunk 4 wt + r), read from the GPU
+// that owns those particles, and their exclusive prefixes / chunk totals.
 // RECOMPUTE: the array still holds the log-weights (ESS-triggered loop); the integer weights are re-derived from them and the
 // chunk's reference e_c exactly as the quantisation did.
-template <typename Real, bool RECOMPUTE>
-__device__ __forceinline__ void nested_load_warp_tile(const FixedArgs<Real>& a, const ChunkRecords& rec, unsigned int num_chunks, size_t wt_base,
-                                                      unsigned int (&q)[4][4], unsigned int (&excl)[4]) {
+template <typename Real, bool RECOMPUTE, bool PULL>
+__device__ __forceinline__ void nested_load_warp_tile(const FixedArgs<Real>& a, const int* rec_e_own, int par, unsigned int wt, unsigned int n_chunks_global, unsigned int (&q)[4][4]) {
     const int lane = threadIdx.x & 31;
+    const unsigned int k0 = 4u * wt;
+    if (k0 >= n_chunks_global) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0u;
+        return;
+    }
+    // (a warp tile never straddles two shards: shards are whole sections)
+    unsigned int k_loc0 = k0;
+    size_t n_own = a.n;
+    const Real* lw = a.lw;
+    const int* rec_e = rec_e_own;
+    if constexpr (PULL) {
+        const unsigned int owner = peer_owner(a.peer, k0 * (unsigned int)kChunk);
+        k_loc0 = k0 - owner * (a.peer.n_loc / (unsigned int)kChunk);
+        n_own = (size_t)a.peer.n_loc;
+        lw = reinterpret_cast<const Real*>(a.peer.lw[par][owner]);
+        rec_e = a.peer.rec_e[par][owner];
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const size_t idx = wt_base + (size_t)r * kChunk + (size_t)lane * 4;
+        const size_t idx = (size_t)(k_loc0 + r) * kChunk + (size_t)lane * 4;
         if constexpr (RECOMPUTE) {
-            const size_t c = wt_base / kChunk + r;
-            const int e_c = c < num_chunks ? rec.e[c] : kChunkEmpty;
+            const int e_c = k0 + r < n_chunks_global ? rec_e[k_loc0 + r] : kChunkEmpty;
             float w[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-            if (idx < a.n) {
-                if constexpr (sizeof(Real) == 4) { const float4 v = *reinterpret_cast<const float4*>(a.lw + idx); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
-                else { const double2 u = *reinterpret_cast<const double2*>(a.lw + idx), v = *reinterpret_cast<const double2*>(a.lw + idx + 2); w[0] = (float)u.x; w[1] = (float)u.y; w[2] = (float)v.x; w[3] = (float)v.y; }
+            if (idx < n_own) {
+                if constexpr (sizeof(Real) == 4) { const float4 v = *reinterpret_cast<const float4*>(lw + idx); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+                else { const double2 u = *reinterpret_cast<const double2*>(lw + idx), v = *reinterpret_cast<const double2*>(lw + idx + 2); w[0] = (float)u.x; w[1] = (float)u.y; w[2] = (float)v.x; w[3] = (float)v.y; }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 float qf;
-                const bool live = e_c != kChunkEmpty && idx + j < a.n;
+                const bool live = e_c != kChunkEmpty && idx + j < n_own;
                 q[r][j] = live ? nested_weight(__fmul_rn(w[j], 1.44269504088896341f), (float)e_c, &qf) : 0u;
             }
             continue;
         }
-        if (idx < a.n) {   // (chunks are quantised whole: entries past n inside the last chunk hold 0)
+        if (idx < n_own) {   // (chunks are quantised whole: entries past n inside the last chunk hold 0)
             if constexpr (sizeof(Real) == 4) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(a.lw + idx));   // last use; the integers' bit patterns
+                const uint4 v = *reinterpret_cast<const uint4*>(lw + idx);   // the integers' bit patterns
                 q[r][0] = v.x; q[r][1] = v.y; q[r][2] = v.z; q[r][3] = v.w;
             } else {
-                const double2 u = *reinterpret_cast<const double2*>(a.lw + idx), v = *reinterpret_cast<const double2*>(a.lw + idx + 2);
+                const double2 u = *reinterpret_cast<const double2*>(lw + idx), v = *reinterpret_cast<const double2*>(lw + idx + 2);
                 q[r][0] = nested_load<double>(u.x); q[r][1] = nested_load<double>(u.y); q[r][2] = nested_load<double>(v.x); q[r][3] = nested_load<double>(v.y);
             }
         } else { q[r][0] = q[r][1] = q[r][2] = q[r][3] = 0u; }
     }
-    chunk_exclusive_prefixes(q, excl);
 }
 
 // Level 2 for one warp tile: inclusive offspring counts n[r][j] of the lane's 16 particles, counted from the warp tile's
-// first output slot `ws` (global); returns the number of slots the warp tile owns.
-template <typename Real>
-__device__ __forceinline__ unsigned int nested_warp_tile_counts(const FixedArgs<Real>& a, unsigned int tile, int warp, uint2 slot_w, unsigned int S_w,
-                                                               unsigned long long word, const unsigned int (&q)[4][4], const unsigned int (&excl)[4],
-                                                               unsigned int (&n)[4][4], unsigned int& ws) {
-    ws = __shfl_sync(0xffffffffu, slot_w.x, 0);
+// first output slot `ws` (global); returns the number of slots the warp tile owns.  P_w: lanes 0..4 hold P[4 wt .. 4 wt + 4].
+__device__ __forceinline__ unsigned int nested_warp_tile_counts(unsigned int wt, unsigned int P_w, unsigned int S_w, unsigned long long word, const unsigned int (&q)[4][4],
+                                                               const unsigned int (&excl)[4], unsigned int (&n)[4][4], unsigned int& ws) {
+    ws = __shfl_sync(0xffffffffu, P_w, 0);
     unsigned int we = ws;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const unsigned int n_c = __shfl_sync(0xffffffffu, slot_w.y, r);
-        const unsigned int cb = we - ws;   // chunks of a tile own consecutive slot ranges
+        const unsigned int n_c = __shfl_sync(0xffffffffu, P_w, r + 1) - __shfl_sync(0xffffffffu, P_w, r);
+        const unsigned int cb = we - ws;   // chunks own consecutive slot ranges
         const unsigned int S_c = __shfl_sync(0xffffffffu, S_w, r);
         if (n_c == 0u || S_c == 0u) {
 #pragma unroll
@@ -506,7 +586,7 @@ __device__ __forceinline__ unsigned int nested_warp_tile_counts(const FixedArgs<
         }
         we += n_c;
         // local slot l sits at l*S_c + U_c; particle with inclusive chunk prefix C owns the slots below C*n_c
-        const unsigned long long chunk_gid = ((unsigned long long)a.out_base / kChunk) + (unsigned long long)tile * kChunksPerTile + 4 * warp + r;
+        const unsigned long long chunk_gid = 4ull * wt + r;
         const unsigned int rem_c = S_c - (unsigned int)nested_chunk_offset(word, chunk_gid, (unsigned long long)S_c) - 1u;
         unsigned int C = excl[r];
         if (n_c <= kLevel2FloatMax) {   // (warp-uniform)
@@ -530,58 +610,95 @@ __device__ __forceinline__ unsigned int nested_warp_tile_counts(const FixedArgs<
     return we - ws;
 }
 
-struct NestedHeavyEntry { unsigned int tile, warp; };
+// first / last GLOBAL tile of chunks (32 chunks each) that own slots of this shard's range
+__device__ __forceinline__ void nested_tile_range(const NestedPrefixes& nb, unsigned long long out_base, unsigned int n_tiles_local, unsigned int n_tiles_global,
+                                                  unsigned int& tg_lo, unsigned int& tg_hi) {
+    const unsigned int T0 = (unsigned int)(out_base / kScanTile), T1 = T0 + n_tiles_local;
+    tg_lo = nb.F[T0] / (unsigned int)kChunksPerTile;
+    tg_hi = (T1 < n_tiles_global ? nb.F[T1] : nb.F[n_tiles_global]) / (unsigned int)kChunksPerTile;
+}
 
-// ---- expansion (level 2): one block per tile, one warp per 4 chunks; warps never meet ---------------------------------------
-template <typename Real, bool RECOMPUTE>
-__global__ void __launch_bounds__(kScanThreads, 4) nested_scan_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_tiles,
-                                                                      unsigned int num_chunks, NestedHeavyEntry* heavy) {
-    __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    DeviceStats* st = a.stats;
-    const unsigned int tile = blockIdx.x;
-    // The integer weights and chunk records come from the kernel before the section pass, and this grid is only released
-    // once every block of the two small passes in between is past its own dependency wait -- so they are complete and
-    // visible already: load them (and do the warp-local scans) before waiting for the level-1 pass' slot ranges.
-    unsigned int q[4][4], excl[4];
-    nested_load_warp_tile<Real, RECOMPUTE>(a, rec, num_chunks, (size_t)tile * kScanTile + (size_t)warp * kWarpTile, q, excl);
-    const unsigned int c_w = tile * kChunksPerTile + 4 * warp + (lane & 3);   // this warp's 4 chunks (lanes 0..3 hold them)
-    const unsigned int S_w = c_w < num_chunks ? rec.S[c_w] : 0u;
-    pdl_wait();
-    pdl_trigger();
-    if (tile == 0 && tid == 0) st->trace[11] = global_ns();
-    if (a.dynamic && !st->do_resample) return;   // ESS above the threshold (the level-1 pass cleared the step's flag)
-    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
-    const bool signal_here = a.peer.world > 1 && !a.overflow_follows;   // else the heavy-tile pass signals
-    if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the level-1 pass)
-        for (size_t i = (size_t)tile * kScanTile + tid; i < min((size_t)(tile + 1) * kScanTile, a.n); i += kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
-        if (signal_here) nested_signal_done(a.peer, st, epoch, false);
+// passes of kNestedWarpSlots slots of a warp tile's range [ws, ws + total) that can touch this shard's slots
+__device__ __forceinline__ void nested_pass_range(unsigned long long out_base, unsigned long long n_out_local, unsigned int ws, unsigned int total, unsigned int& lo, unsigned int& hi) {
+    const unsigned long long b = ws, e = (unsigned long long)ws + total, w0 = out_base, w1 = out_base + n_out_local;
+    if (e <= w0 || b >= w1) { lo = hi = 0u; return; }
+    lo = b >= w0 ? 0u : (unsigned int)((w0 - b) / kNestedWarpSlots) * kNestedWarpSlots;
+    hi = e <= w1 ? total : (unsigned int)(w1 - b);
+}
+
+// One block per tile of 32 chunks, one warp per 4 chunks (512 particles); warps never meet.  The grid walks the tiles of chunks
+// that own slots of THIS shard's slot range -- on one GPU simply all of them -- wherever their particles live (remote loads of the
+// integer weights); every warp computes the offspring counts of its 512 particles and expands them into the ancestor slots
+// that fall into the shard's range.  PULL: several GPUs.
+struct NestedHeavyEntry { unsigned int wt; };
+template <typename Real, bool PULL>
+__device__ __forceinline__ void nested_expand_warp_tile(const FixedArgs<Real>& a, const NestedPrefixes& nb, DeviceStats* st, unsigned short* head, unsigned int wt,
+                                                        unsigned int n_chunks_global, const unsigned int (&q)[4][4], const unsigned int (&excl)[4], unsigned int S_w,
+                                                        NestedHeavyEntry* heavy) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int c_w = 4u * wt + (unsigned int)min(lane, 4);
+    const unsigned int P_w = c_w <= n_chunks_global ? nb.P[c_w] : (unsigned int)a.n_out;   // lanes 0..4: the slot starts of the warp's 4 chunks
+    unsigned int n[4][4], ws;
+    const unsigned int total = nested_warp_tile_counts(wt, P_w, S_w, st->rand_word, q, excl, n, ws);
+    unsigned int lo = 0, hi = total;
+    if constexpr (PULL) nested_pass_range(a.out_base, a.n_out_local, ws, total, lo, hi);
+    if (hi <= lo) return;
+    if (total > kWarpHeavyCap && a.overflow_follows) {   // a few particles own a large share of the offspring: the whole grid expands this warp tile
+        if (lane == 0) heavy[atomicAdd(&st->overflow_count, 1u)] = NestedHeavyEntry{wt};
         return;
     }
-    const uint2 slot_w = c_w < num_chunks ? nb.slots[c_w] : make_uint2(0u, 0u);
-    unsigned int n[4][4], ws;
-    const unsigned int total = nested_warp_tile_counts<Real>(a, tile, warp, slot_w, S_w, st->rand_word, q, excl, n, ws);
-    bool remote = false;
-    if (total > kWarpHeavyCap && a.overflow_follows) {   // a few particles own a large share of the offspring: the whole grid expands this warp tile
-        if (lane == 0) heavy[atomicAdd(&st->overflow_count, 1u)] = NestedHeavyEntry{tile, (unsigned int)warp};
-    } else if (total != 0u) {
-        // no heavy-tile pass was launched for this step (none had been needed so far): the warp expands alone, and the raised
-        // host word makes every later step launch the pass
-        if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
-        const int32_t src0 = a.src_base + (int32_t)(tile * (unsigned int)kScanTile + warp * kWarpTile) - 1;
-        // n[][] counts from 0 at the warp tile's first slot
-        if (total <= (unsigned int)kNestedWarpSlots) remote = warp_expand_chunk<Real, kNestedWarpSlots, true>(a, head[warp], n, 0u, total, 0u, (unsigned long long)ws, src0);
-        else
-            for (unsigned int chunk_lo = 0; chunk_lo < total; chunk_lo += kNestedWarpSlots)
-                remote |= warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
+    // no heavy-tile pass was launched for this step (none had been needed so far): the warp expands alone, and the raised
+    // host word makes every later step launch the pass
+    if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
+    const int32_t src0 = (int32_t)(wt * (unsigned int)kWarpTile) - 1;   // global id of the warp tile's first particle, minus 1
+    // n[][] counts from 0 at the warp tile's first slot
+    if (!PULL && total <= (unsigned int)kNestedWarpSlots) warp_expand_chunk<Real, kNestedWarpSlots, true, false>(a, head, n, 0u, total, 0u, (unsigned long long)ws, src0);
+    else
+        for (unsigned int chunk_lo = lo; chunk_lo < hi; chunk_lo += kNestedWarpSlots)
+            warp_expand_chunk<Real, kNestedWarpSlots, false, PULL>(a, head, n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
+}
+
+template <typename Real, bool RECOMPUTE, bool PULL>
+__global__ void __launch_bounds__(kScanThreads, PULL ? 3 : 4) nested_expand_kernel(FixedArgs<Real> a, NestedPrefixes nb, const int* rec_e_own, int par, unsigned int n_tiles_local,
+                                                                                   unsigned int n_tiles_global, unsigned int n_chunks_global, NestedHeavyEntry* heavy) {
+    __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    DeviceStats* st = a.stats;
+    unsigned int q[4][4], excl[4], S_w = 0u;
+    // One GPU: tile b of chunks belongs to block b, and the integer weights come from the kernel before the section pass -- this
+    // grid is only released once every block of the two small passes in between is past its own dependency wait -- so they are
+    // complete and visible already: load them (and do the warp-local scans) before waiting for the plan pass' slot ranges.
+    if constexpr (!PULL) {
+        nested_load_warp_tile<Real, RECOMPUTE, false>(a, rec_e_own, par, blockIdx.x * (kScanThreads / 32) + warp, n_chunks_global, q);
+        chunk_exclusive_prefixes(q, excl, S_w);
     }
-    if (signal_here) nested_signal_done(a.peer, st, epoch, remote);
+    pdl_wait();
+    pdl_trigger();
+    if (blockIdx.x == 0 && tid == 0) st->trace[11] = global_ns();
+    if (a.dynamic && !st->do_resample) return;   // ESS above the threshold (the plan pass cleared the step's flag)
+    if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the plan pass)
+        for (size_t i = (size_t)blockIdx.x * kScanThreads + tid; i < a.n; i += (size_t)gridDim.x * kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
+        return;
+    }
+    if constexpr (!PULL) {
+        nested_expand_warp_tile<Real, false>(a, nb, st, head[warp], blockIdx.x * (kScanThreads / 32) + warp, n_chunks_global, q, excl, S_w, heavy);
+    } else {
+        unsigned int tg_lo, tg_hi;
+        nested_tile_range(nb, a.out_base, n_tiles_local, n_tiles_global, tg_lo, tg_hi);
+        for (unsigned int tg = tg_lo + blockIdx.x; tg <= tg_hi; tg += gridDim.x) {
+            const unsigned int wt = tg * (kScanThreads / 32) + warp;
+            nested_load_warp_tile<Real, RECOMPUTE, true>(a, rec_e_own, par, wt, n_chunks_global, q);
+            chunk_exclusive_prefixes(q, excl, S_w);
+            nested_expand_warp_tile<Real, true>(a, nb, st, head[warp], wt, n_chunks_global, q, excl, S_w, heavy);
+        }
+    }
+    if (tid == 0 && atomicAdd(&st->ticket, 1u) == gridDim.x - 1) { st->ticket = 0; st->trace[8] = global_ns(); }   // (time stamp of the last block; diagnostics)
 }
 
 // ---- heavy warp tiles: every warp of the grid recomputes the tile's counts (512 particles) and expands its share of the passes.
 // Launched only once a heavy tile has been seen (host-mapped flag), like the single-level scheme's overflow pass.
-template <typename Real, bool RECOMPUTE>
-__global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Real> a, ChunkRecords rec, NestedPrefixes nb, unsigned int num_chunks,
+template <typename Real, bool RECOMPUTE, bool PULL>
+__global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Real> a, NestedPrefixes nb, const int* rec_e_own, int par, unsigned int n_chunks_global,
                                                                     const NestedHeavyEntry* heavy) {
     __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
     DeviceStats* st = a.stats;
@@ -589,25 +706,23 @@ __global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Re
     pdl_trigger();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (a.dynamic && !st->do_resample) return;
-    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
     const unsigned int count = st->overflow_count;
-    bool remote = false;
-    if (count != 0u && st->W != 0ull) {
-        const unsigned int gw = blockIdx.x * (kScanThreads / 32) + warp, nw = gridDim.x * (kScanThreads / 32);
-        for (unsigned int k = 0; k < count; ++k) {
-            const NestedHeavyEntry e = heavy[k];
-            unsigned int q[4][4], excl[4], n[4][4], ws;
-            nested_load_warp_tile<Real, RECOMPUTE>(a, rec, num_chunks, (size_t)e.tile * kScanTile + (size_t)e.warp * kWarpTile, q, excl);
-            const unsigned int c_w = e.tile * kChunksPerTile + 4 * e.warp + (lane & 3);
-            const unsigned int S_w = c_w < num_chunks ? rec.S[c_w] : 0u;
-            const uint2 slot_w = c_w < num_chunks ? nb.slots[c_w] : make_uint2(0u, 0u);
-            const unsigned int total = nested_warp_tile_counts<Real>(a, e.tile, (int)e.warp, slot_w, S_w, st->rand_word, q, excl, n, ws);
-            const int32_t src0 = a.src_base + (int32_t)(e.tile * (unsigned int)kScanTile + e.warp * kWarpTile) - 1;
-            for (unsigned long long chunk_lo = (unsigned long long)gw * kNestedWarpSlots; chunk_lo < total; chunk_lo += (unsigned long long)nw * kNestedWarpSlots)
-                remote |= warp_expand_chunk<Real, kNestedWarpSlots>(a, head[warp], n, 0u, total, (unsigned int)chunk_lo, (unsigned long long)ws, src0);
-        }
+    if (count == 0u || st->W == 0ull) return;
+    const unsigned int gw = blockIdx.x * (kScanThreads / 32) + warp, nw = gridDim.x * (kScanThreads / 32);
+    for (unsigned int k = 0; k < count; ++k) {
+        const unsigned int wt = heavy[k].wt;
+        unsigned int q[4][4], excl[4], S_w = 0u, n[4][4], ws;
+        nested_load_warp_tile<Real, RECOMPUTE, PULL>(a, rec_e_own, par, wt, n_chunks_global, q);
+        chunk_exclusive_prefixes(q, excl, S_w);
+        const unsigned int c_w = 4u * wt + (unsigned int)min(lane, 4);
+        const unsigned int P_w = c_w <= n_chunks_global ? nb.P[c_w] : (unsigned int)a.n_out;
+        const unsigned int total = nested_warp_tile_counts(wt, P_w, S_w, st->rand_word, q, excl, n, ws);
+        unsigned int lo = 0, hi = total;
+        if constexpr (PULL) nested_pass_range(a.out_base, a.n_out_local, ws, total, lo, hi);
+        const int32_t src0 = (int32_t)(wt * (unsigned int)kWarpTile) - 1;
+        for (unsigned long long chunk_lo = (unsigned long long)lo + (unsigned long long)gw * kNestedWarpSlots; chunk_lo < hi; chunk_lo += (unsigned long long)nw * kNestedWarpSlots)
+            warp_expand_chunk<Real, kNestedWarpSlots, false, PULL>(a, head[warp], n, 0u, total, (unsigned int)chunk_lo, (unsigned long long)ws, src0);
     }
-    if (a.peer.world > 1) nested_signal_done(a.peer, st, epoch, remote);
 }
 
 }  // namespace mpl

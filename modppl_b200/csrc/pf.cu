@@ -111,6 +111,7 @@ static int flush_timers(mpl_ps* ps) {
     return MPL_OK;
 }
 
+static void refresh_chunk_records(mpl_ps* ps);
 static size_t elem_size(const mpl_ps* ps) { return ps->dtype == MPL_F64 ? 8 : 4; }
 
 static int grid_for(size_t work_items, int per_block, int max_blocks) {
@@ -126,7 +127,10 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     ExtendArgs<Real> a;
     a.state_in = (const Real*)ps->state[ps->cur];
     a.state_out = (Real*)ps->state[mode == EXT_INIT || mode == EXT_ACCUM ? ps->cur : ps->cur ^ 1];
+    a.lw_in = (const Real*)ps->lw;
+    if (ps->world > 1 && ps->lw_alt) { std::swap(ps->lw, ps->lw_alt); ps->par ^= 1; refresh_chunk_records(ps); }   // sharded: the other buffer of the pair (PeerTable::lw)
     a.lw = (Real*)ps->lw;
+    a.wait_done = ps->anc_pushed ? 1 : 0;
     a.anc = ps->anc;
     a.n = ps->n; a.ld = ps->ld;
     a.seed = ps->seed; a.gid_offset = ps->gid_offset;
@@ -308,6 +312,7 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
             else pdl_launch(fixed_scan2_kernel<Real, true>, (unsigned int)num_tiles, kScanThreads, ps->stream, a, (unsigned int)num_tiles, (OverflowEntry2*)ps->overflow);
         }
         MPL_CUDA_OK(cudaGetLastError());
+        ps->anc_pushed = ps->world > 1;
         if (a.overflow_follows) {
             ScopedLaunch sl(ps, "fixed_overflow");
             if (dynamic) pdl_launch(fixed_overflow2_kernel<Real, false>, kNumSMs * 2, kScanThreads, ps->stream, a, (const OverflowEntry2*)ps->overflow);
@@ -332,18 +337,34 @@ static int resample_fixed_t(mpl_ps* ps, int scheme, bool dynamic, bool dev_t) {
 }
 
 
-static int ensure_chunk_records(mpl_ps* ps) {
-    if (ps->rec_e) return MPL_OK;
+// the chunk records in use: parity ps->par of the pair (only sharded runs alternate)
+static void refresh_chunk_records(mpl_ps* ps) {
+    if (!ps->rec_e2) return;
     const size_t nch = ps->ld / kChunk;
-    MPL_CUDA_OK(cudaMalloc(&ps->rec_e, nch * sizeof(int)));
-    MPL_CUDA_OK(cudaMalloc(&ps->rec_S, nch * sizeof(unsigned int)));
+    ps->rec_e = ps->rec_e2 + (size_t)ps->par * nch;
+    ps->rec_S = ps->rec_S2 + (size_t)ps->par * nch;
+}
+
+int ensure_chunk_records(mpl_ps* ps) {
+    if (ps->rec_e2) return MPL_OK;
+    const size_t nch = ps->ld / kChunk;
+    MPL_CUDA_OK(cudaMalloc(&ps->rec_e2, 2 * nch * sizeof(int)));
+    MPL_CUDA_OK(cudaMalloc(&ps->rec_S2, 2 * nch * sizeof(unsigned int)));
     MPL_CUDA_OK(cudaMalloc(&ps->rec_sq, nch * sizeof(float)));
-    const size_t nsec = (ps->ld + kSection - 1) / kSection;
-    MPL_CUDA_OK(cudaMalloc(&ps->nest_tile_pre, nsec * kTilesPerSection * sizeof(unsigned long long)));
+    refresh_chunk_records(ps);
     // section records and top-level results of EVERY shard: [E int | T u64 | sq f64 | pre u64 | M u64 | a u64 | n u64] x kMaxSections
     MPL_CUDA_OK(cudaMalloc(&ps->nest_sec, (size_t)kMaxSections * 7 * sizeof(unsigned long long)));
     MPL_CUDA_OK(cudaMemset(ps->nest_sec, 0, (size_t)kMaxSections * 7 * sizeof(unsigned long long)));
-    MPL_CUDA_OK(cudaMalloc(&ps->nest_slots, nch * sizeof(uint2)));
+    const size_t nsec = (ps->ld + kSection - 1) / kSection;
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_tile_pre, nsec * kTilesPerSection * sizeof(unsigned long long)));
+    // plan of the WHOLE population (a shard plans the sections whose slots it fills, wherever their particles live)
+    const size_t nch_g = (ps->n_global + kChunk - 1) / kChunk, nt_g = (ps->n_global + kScanTile - 1) / kScanTile;
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_P, (nch_g + 2) * sizeof(unsigned int)));
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_F, (nt_g + 1) * sizeof(unsigned int)));
+    if (ps->world <= 1) {   // one GPU: the "peer" tables point at this system's own arrays (kernels use one code path)
+        for (int p = 0; p < 2; ++p) { ps->peer.lw[p][0] = ps->lw; ps->peer.rec_e[p][0] = ps->rec_e2; ps->peer.rec_S[p][0] = ps->rec_S2; }
+        ps->peer.n_loc = (unsigned int)ps->n;
+    }
     return MPL_OK;
 }
 
@@ -362,12 +383,16 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     const bool post = (phases & 2) && !dynamic && !ps->in_device_loop;   // the call-per-step API polls the result in mapped host memory
     if (post) { ps->host_seq += 1; if (ps->host_seq == 0) ps->host_seq = 1; }
     a.host_seq = post ? ps->host_seq : 0u;
+    if (ps->world <= 1) for (int p = 0; p < 2; ++p) ps->peer.lw[p][0] = ps->lw;   // (the log-weight array may have been reallocated: keep the self-table current)
+    a.peer = ps->peer;
     ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
     unsigned long long* sec = ps->nest_sec;
     NestedPrefixes nb{ps->nest_tile_pre, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
-                      sec + 5 * kMaxSections, sec + 6 * kMaxSections, (uint2*)ps->nest_slots, (unsigned int)(ps->gid_offset / kSection), (unsigned int)((ps->n + kSection - 1) / kSection), (unsigned int)n_sec_global};
+                      sec + 5 * kMaxSections, sec + 6 * kMaxSections, ps->nest_P, ps->nest_F,
+                      (unsigned int)(ps->gid_offset / kSection), (unsigned int)((ps->n + kSection - 1) / kSection), (unsigned int)n_sec_global};
     const unsigned int num_tiles = (unsigned int)((ps->n + kScanTile - 1) / kScanTile);
     const unsigned int num_chunks = (unsigned int)((ps->n + kChunk - 1) / kChunk);
+    const unsigned int n_chunks_global = (unsigned int)((ps->n_global + kChunk - 1) / kChunk), n_tiles_global = (unsigned int)((ps->n_global + kScanTile - 1) / kScanTile);
     if (dynamic && ps->prequantised == 1) return fail(MPL_ERR_INVALID, "ESS-triggered nested resampling after a step that dropped the log-weights");
     if ((phases & 1) && !ps->prequantised) {
         ScopedLaunch sl(ps, "nested_quantise");
@@ -381,22 +406,35 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
         else pdl_launch(nested_sections_kernel<Real, 2>, 1, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
     }
     if (phases & 2) {
-        ScopedLaunch sl(ps, "nested_level1");
-        pdl_launch(nested_level1_kernel<Real>, (num_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32), kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
+        ScopedLaunch sl(ps, "nested_plan");
+        pdl_launch(nested_plan_kernel<Real>, (unsigned int)n_sec_global, kScanThreads, ps->stream, a, nb, ps->par, n_chunks_global);
     }
     if (phases & 2) {
-        ScopedLaunch sl(ps, "nested_scan");
-        if (dynamic) pdl_launch(nested_scan_kernel<Real, true>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks, (NestedHeavyEntry*)ps->overflow);
-        else pdl_launch(nested_scan_kernel<Real, false>, num_tiles, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks, (NestedHeavyEntry*)ps->overflow);
+        ScopedLaunch sl(ps, "nested_expand");
+        NestedHeavyEntry* hv = (NestedHeavyEntry*)ps->overflow;
+        if (ps->world > 1) {   // the chunks that own this shard's slots: about its own tiles, one more at each edge, more when the weights are lopsided (grid-stride)
+            const unsigned int grid = num_tiles + 2;
+            if (dynamic) pdl_launch(nested_expand_kernel<Real, true, true>, grid, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
+            else pdl_launch(nested_expand_kernel<Real, false, true>, grid, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
+        } else {
+            if (dynamic) pdl_launch(nested_expand_kernel<Real, true, false>, num_tiles, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
+            else pdl_launch(nested_expand_kernel<Real, false, false>, num_tiles, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
+        }
     }
     if ((phases & 2) && a.overflow_follows) {
         ScopedLaunch sl(ps, "nested_heavy");
-        if (dynamic) pdl_launch(nested_heavy_kernel<Real, true>, kNumSMs * 2, kScanThreads, ps->stream, a, rec, nb, num_chunks, (const NestedHeavyEntry*)ps->overflow);
-        else pdl_launch(nested_heavy_kernel<Real, false>, kNumSMs * 2, kScanThreads, ps->stream, a, rec, nb, num_chunks, (const NestedHeavyEntry*)ps->overflow);
+        const NestedHeavyEntry* hv = (const NestedHeavyEntry*)ps->overflow;
+        if (ps->world > 1) {
+            if (dynamic) pdl_launch(nested_heavy_kernel<Real, true, true>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, n_chunks_global, hv);
+            else pdl_launch(nested_heavy_kernel<Real, false, true>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, n_chunks_global, hv);
+        } else {
+            if (dynamic) pdl_launch(nested_heavy_kernel<Real, true, false>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, n_chunks_global, hv);
+            else pdl_launch(nested_heavy_kernel<Real, false, false>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, n_chunks_global, hv);
+        }
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (phases & 1) ps->prequantised = 0;
-    if (phases & 2) ps->host_lse_posted = post;
+    if (phases & 2) { ps->host_lse_posted = post; ps->anc_pushed = false; }
     return MPL_OK;
 }
 
@@ -527,6 +565,7 @@ int ps_phase_scan(mpl_ps* ps) {
     }
     MPL_CUDA_OK(cudaGetLastError());
     ps->pending_gather = true; ps->stats_valid = false; ps->max_valid = false;
+    ps->anc_pushed = ps->world > 1;
     return MPL_OK;
 }
 
@@ -603,7 +642,8 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->cur = 0; ps->t = 0; ps->initialised = false; ps->pending_gather = false; ps->stats_valid = false; ps->max_valid = false;
     ps->hist_state = nullptr; ps->hist_anc = nullptr; ps->hist_cap = 0;
     ps->rec_e = nullptr; ps->rec_S = nullptr; ps->rec_sq = nullptr; ps->prequantised = 0; ps->host_seq = 0; ps->host_lse_posted = false; ps->in_device_loop = false;
-    ps->nest_tile_pre = nullptr; ps->nest_sec = nullptr; ps->nest_slots = nullptr;
+    ps->nest_tile_pre = nullptr; ps->nest_sec = nullptr; ps->nest_P = nullptr; ps->nest_F = nullptr;
+    ps->rec_e2 = nullptr; ps->rec_S2 = nullptr; ps->lw_alt = nullptr; ps->par = 0; ps->anc_pushed = false;
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false; ps->hist_broken = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
@@ -658,7 +698,8 @@ extern "C" void mpl_ps_destroy(mpl_ps* ps) {
     cudaFree(ps->stats); cudaFreeHost(ps->stats_host); cudaFree(ps->partials); cudaFree(ps->ipartials);
     cudaFree(ps->sq_partials); if (ps->host_flags) cudaFreeHost(ps->host_flags);
     cudaFree(ps->hist_state); cudaFree(ps->hist_anc);
-    cudaFree(ps->rec_e); cudaFree(ps->rec_S); cudaFree(ps->rec_sq); cudaFree(ps->nest_tile_pre); cudaFree(ps->nest_sec); cudaFree(ps->nest_slots);
+    cudaFree(ps->rec_e2); cudaFree(ps->rec_S2); cudaFree(ps->rec_sq); cudaFree(ps->nest_tile_pre); cudaFree(ps->nest_sec); cudaFree(ps->nest_P); cudaFree(ps->nest_F);
+    cudaFree(ps->lw_alt);
     if (ps->world > 1 && !ps->peer_virtual) mpl_ps_peer_detach(ps);
     cudaFree(ps->mailbox);
     cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
@@ -822,11 +863,10 @@ extern "C" int mpl_ps_read(mpl_ps* ps, int what, void* host_dst, size_t bytes) {
         MPL_CUDA_OK(cudaMemcpyAsync(host_dst, ps->staging, bytes, cudaMemcpyDeviceToHost, ps->stream));
     } else if (what == MPL_READ_STATE) {
         if (bytes != (size_t)ps->D * ps->n * sizeof(double)) return fail(MPL_ERR_INVALID, "state buffer must be double[D*N]");
-        for (int d = 0; d < ps->D; ++d) {
-            if (ps->dtype == MPL_F32) to_f64_kernel<float><<<grid, 256, 0, ps->stream>>>((const float*)ps->state[ps->cur] + (size_t)d * ps->ld, ps->staging + (size_t)d * ps->ld, ps->n);
-            else to_f64_kernel<double><<<grid, 256, 0, ps->stream>>>((const double*)ps->state[ps->cur] + (size_t)d * ps->ld, ps->staging + (size_t)d * ps->ld, ps->n);
+        if (ps->dtype == MPL_F32) state_to_f64_kernel<float><<<grid, 256, 0, ps->stream>>>((const float*)ps->state[ps->cur], ps->staging, ps->n, ps->ld, ps->D);
+        else state_to_f64_kernel<double><<<grid, 256, 0, ps->stream>>>((const double*)ps->state[ps->cur], ps->staging, ps->n, ps->ld, ps->D);
+        for (int d = 0; d < ps->D; ++d)
             MPL_CUDA_OK(cudaMemcpyAsync((double*)host_dst + (size_t)d * ps->n, ps->staging + (size_t)d * ps->ld, ps->n * sizeof(double), cudaMemcpyDeviceToHost, ps->stream));
-        }
         MPL_CUDA_OK(cudaGetLastError());
     } else return fail(MPL_ERR_INVALID, "unknown read selector");
     MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
@@ -848,11 +888,10 @@ extern "C" int mpl_ps_write(mpl_ps* ps, int what, const void* host_src, size_t b
         ps->stats_valid = false; ps->max_valid = false;
     } else if (what == MPL_READ_STATE) {
         if (bytes != (size_t)ps->D * ps->n * sizeof(double)) return fail(MPL_ERR_INVALID, "state buffer must be double[D*N]");
-        for (int d = 0; d < ps->D; ++d) {
+        for (int d = 0; d < ps->D; ++d)
             MPL_CUDA_OK(cudaMemcpyAsync(ps->staging + (size_t)d * ps->ld, (const double*)host_src + (size_t)d * ps->n, ps->n * sizeof(double), cudaMemcpyHostToDevice, ps->stream));
-            if (ps->dtype == MPL_F32) from_f64_kernel<float><<<grid, 256, 0, ps->stream>>>(ps->staging + (size_t)d * ps->ld, (float*)ps->state[ps->cur] + (size_t)d * ps->ld, ps->n);
-            else from_f64_kernel<double><<<grid, 256, 0, ps->stream>>>(ps->staging + (size_t)d * ps->ld, (double*)ps->state[ps->cur] + (size_t)d * ps->ld, ps->n);
-        }
+        if (ps->dtype == MPL_F32) state_from_f64_kernel<float><<<grid, 256, 0, ps->stream>>>(ps->staging, (float*)ps->state[ps->cur], ps->n, ps->ld, ps->D);
+        else state_from_f64_kernel<double><<<grid, 256, 0, ps->stream>>>(ps->staging, (double*)ps->state[ps->cur], ps->n, ps->ld, ps->D);
         if (!ps->initialised) { ps->initialised = true; if (ps->t == 0) ps->t = 1; }
     } else return fail(MPL_ERR_INVALID, "unknown write selector");
     MPL_CUDA_OK(cudaGetLastError());
@@ -873,7 +912,7 @@ struct CkptHeader {
     uint64_t n_resamples;
     uint64_t param_hash;   // FNV-1a over the model's parameter vector: a checkpoint continues the SAME filter only
 };
-constexpr uint64_t kCkptMagic = 0x324b434c504d6f6dull;   // "moMPLCK2"
+constexpr uint64_t kCkptMagic = 0x334b434c504d6f6dull;   // "moMPLCK3" (3: particle-major state)
 uint64_t model_param_hash(const mpl_model& m) {
     uint64_t h = 0xcbf29ce484222325ull;
     for (double v : m.params) {

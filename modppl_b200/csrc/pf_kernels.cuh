@@ -67,8 +67,10 @@ struct Mailbox {
     long long flag_done[kMaxPeers];              // shard h has written every ancestor it owes for this step
     int error;
     int pad;
-    // nested scheme: (E_s, T_s, sum q^2) of every section of every shard, indexed by the GLOBAL section number
-    unsigned long long sec_ll[kMaxSections][6];
+    // nested scheme: (E_s, T_s, sum q^2) of every section of THIS shard, indexed by [step & 1][GLOBAL section number]; published
+    // here by the owner and polled by the peers.  Two parities: a rank may already publish step t + 1 while a slow peer is still
+    // collecting step t (it cannot get to t + 2 before that peer has published t + 1, i.e. is done with t)
+    unsigned long long sec_ll[2][kMaxSections][6];
 };
 __device__ __forceinline__ void ll_write64(unsigned long long* dst2, unsigned long long value, unsigned int epoch) {
     *(volatile unsigned long long*)(dst2 + 0) = (value & 0xffffffffull) | ((unsigned long long)epoch << 32);
@@ -79,8 +81,14 @@ struct PeerTable {
     unsigned int n_loc;   // particles per shard (equal shards)
     int shift;            // log2(n_loc) when it is a power of two, else -1
     const void* state[2][kMaxPeers];   // [buffer][rank]: SoA state of every shard
-    int32_t* anc[kMaxPeers];           // ancestor slots of every shard
+    int32_t* anc[kMaxPeers];           // ancestor slots of every shard (single-level scheme: ancestors are pushed)
     Mailbox* mail[kMaxPeers];
+    // nested scheme: everything is PULLED.  [parity][rank]: the integer weights (in the log-weight array) and the chunk records
+    // the extend of a step left; a sharded run alternates two buffers so that a rank which is already extending step t + 1 does
+    // not overwrite what a slower peer still reads for the resampling of step t
+    const void* lw[2][kMaxPeers];
+    const int* rec_e[2][kMaxPeers];
+    const unsigned int* rec_S[2][kMaxPeers];
 };
 __device__ __forceinline__ unsigned int peer_owner(const PeerTable& p, unsigned int gid) { return p.shift >= 0 ? gid >> p.shift : gid / p.n_loc; }
 
@@ -145,6 +153,68 @@ template <typename Real> __device__ __forceinline__ void vec_store_stream(Real* 
 template <> __device__ __forceinline__ void vec_store_stream<float>(float* p, const float (&v)[4]) { __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3])); }
 template <> __device__ __forceinline__ void vec_store_stream<double>(double* p, const double (&v)[2]) { __stcs(reinterpret_cast<double2*>(p), make_double2(v[0], v[1])); }
 
+// ---- particle-major state: the D components of particle i are contiguous (state[i * D + d]).  A parent is fetched with ONE
+// vector load (16 bytes for D = 4 in fp32) instead of D scalar loads from D arrays -- the ancestor-indirect gather is the
+// latency-critical access of the extend kernel -- and a thread's V consecutive particles are V * D contiguous elements.
+template <typename Real, int D>
+__device__ __forceinline__ void load_particle_ro(const Real* __restrict__ state, size_t i, Real (&x)[D]) {   // read-only path (LDG.CONSTANT)
+    constexpr int BYTES = D * (int)sizeof(Real);
+    const Real* p = state + i * D;
+    if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+        for (int k = 0; k < BYTES / 16; ++k) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + k);
+            memcpy(reinterpret_cast<char*>(x) + 16 * k, &v, 16);
+        }
+    } else if constexpr (BYTES == 8) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+        memcpy(x, &v, 8);
+    } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = __ldg(p + d);
+    }
+}
+template <typename Real, int D>
+__device__ __forceinline__ void load_particle(const Real* state, size_t i, Real (&x)[D]) {   // plain loads (a peer's memory over NVLink)
+    constexpr int BYTES = D * (int)sizeof(Real);
+    const Real* p = state + i * D;
+    if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+        for (int k = 0; k < BYTES / 16; ++k) {
+            const uint4 v = *(reinterpret_cast<const uint4*>(p) + k);
+            memcpy(reinterpret_cast<char*>(x) + 16 * k, &v, 16);
+        }
+    } else if constexpr (BYTES == 8) {
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        memcpy(x, &v, 8);
+    } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = p[d];
+    }
+}
+// a thread's V consecutive particles (V * D contiguous elements, a multiple of 16 bytes): 128-bit accesses
+template <typename Real, int V, int D>
+__device__ __forceinline__ void load_particles(const Real* __restrict__ state, size_t i0, Real (&x)[V][D]) {
+    static_assert((V * D * sizeof(Real)) % 16 == 0, "V consecutive particles are whole 16-byte words");
+    const uint4* p = reinterpret_cast<const uint4*>(state + i0 * D);
+#pragma unroll
+    for (int k = 0; k < (int)(V * D * sizeof(Real)) / 16; ++k) {
+        const uint4 v = p[k];
+        memcpy(reinterpret_cast<char*>(x) + 16 * k, &v, 16);
+    }
+}
+template <typename Real, int V, int D>
+__device__ __forceinline__ void store_particles_stream(Real* __restrict__ state, size_t i0, const Real (&x)[V][D]) {   // st.global.cs: touched once per step
+    static_assert((V * D * sizeof(Real)) % 16 == 0, "V consecutive particles are whole 16-byte words");
+    uint4* p = reinterpret_cast<uint4*>(state + i0 * D);
+#pragma unroll
+    for (int k = 0; k < (int)(V * D * sizeof(Real)) / 16; ++k) {
+        uint4 v;
+        memcpy(&v, reinterpret_cast<const char*>(x) + 16 * k, 16);
+        __stcs(p + k, v);
+    }
+}
+
 // ================================================================================================
 // K1/K2/K6/K3: extend
 // ================================================================================================
@@ -152,10 +222,11 @@ enum ExtendMode : int { EXT_INIT = 0, EXT_ACCUM = 1, EXT_GATHER = 2, EXT_DYNAMIC
 
 template <typename Real>
 struct ExtendArgs {
-    const Real* state_in;    // D x ld
-    Real* state_out;         // D x ld
-    Real* lw;                // ld
-    const int32_t* anc;      // ld (local parent index)
+    const Real* state_in;    // ld x D, particle-major
+    Real* state_out;         // ld x D
+    const Real* lw_in;       // ld: log-weights to accumulate onto (EXT_ACCUM)
+    Real* lw;                // ld: log-weights written (== lw_in on one GPU; the other buffer of the pair when sharded)
+    const int32_t* anc;      // ld (parent: global particle id)
     size_t n, ld;
     uint64_t seed, gid_offset;
     long long t;             // kernel time index; < 0: read stats->t (device-resident loop)
@@ -166,6 +237,7 @@ struct ExtendArgs {
     Lse3<double>* partials;  // gridDim.x
     PeerTable peer;          // world == 1: single GPU
     int cur;                 // which state buffer is the input (index into peer.state)
+    int wait_done;           // sharded: the ancestors were PUSHED by the peers (single-level scheme): wait for their "done" flags
     ChunkRecords rec;        // NESTED: chunk records written by the fused quantisation epilogue
     int kbits;
 };
@@ -197,7 +269,8 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
         accum = !gather;
     }
     constexpr bool sharded = SHARDED;
-    if (sharded && gather) gate_done(a.peer, a.stats, t);   // ancestors written everywhere; old buffer no longer read
+    if (sharded && gather && a.wait_done) gate_done(a.peer, a.stats, t);   // ancestors written everywhere; old buffer no longer read
+    // (nested scheme: nothing is pushed -- this rank computed its own ancestors after the step's only gate, the section records)
 
     Real run_max = (Real)-INFINITY;
     if (blockIdx.x == 0 && tid == 0) { a.stats->max_bits[(t + 1) & 1] = 0ull; a.stats->trace[13] = global_ns(); }   // slot of the next step (its last reader finished before this launch)
@@ -229,30 +302,21 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
                 const unsigned int off = sharded ? (unsigned int)a.gid_offset : 0u;
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    size_t src = (sharded || full || base + v < a.n) ? (size_t)((unsigned int)par[v] - off) : 0;
-#pragma unroll
-                    for (int d = 0; d < D; ++d) x[v][d] = __ldg(a.state_in + (size_t)d * a.ld + src);
+                    const size_t src = (sharded || full || base + v < a.n) ? (size_t)((unsigned int)par[v] - off) : 0;
+                    load_particle_ro<Real, D>(a.state_in, src, x[v]);
                 }
             } else {   // parents are global ids: read them where they live (a peer's HBM over NVLink)
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
-                    unsigned int g = (unsigned int)par[v];
-                    unsigned int r = peer_owner(a.peer, g);
-                    const Real* src = reinterpret_cast<const Real*>(a.peer.state[a.cur][r]) + (g - r * a.peer.n_loc);
-#pragma unroll
-                    for (int d = 0; d < D; ++d) x[v][d] = src[(size_t)d * a.ld];
+                    const unsigned int g = (unsigned int)par[v];
+                    const unsigned int r = peer_owner(a.peer, g);
+                    load_particle<Real, D>(reinterpret_cast<const Real*>(a.peer.state[a.cur][r]), (size_t)(g - r * a.peer.n_loc), x[v]);
                 }
             }
         } else if (MODE != EXT_INIT) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                Real tmp[V];
-                vec_load<Real>(a.state_in + (size_t)d * a.ld + base, tmp);
-#pragma unroll
-                for (int v = 0; v < V; ++v) x[v][d] = tmp[v];
-            }
+            load_particles<Real, V, D>(a.state_in, base, x);
         }
-        if (accum) vec_load<Real>(a.lw + base, w);
+        if (accum) vec_load<Real>(a.lw_in + base, w);
         else {
 #pragma unroll
             for (int v = 0; v < V; ++v) w[v] = 0;
@@ -270,13 +334,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
                 w[v] += model.kernel(t, s, x[v], obs);
             }
         }
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            Real tmp[V];
-#pragma unroll
-            for (int v = 0; v < V; ++v) tmp[v] = x[v][d];
-            vec_store_stream<Real>(a.state_out + (size_t)d * a.ld + base, tmp);
-        }
+        store_particles_stream<Real, V, D>(a.state_out, base, x);
         if constexpr (NESTED) {
             float wm[4], sqc;
             unsigned int qv[4];
@@ -299,8 +357,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
 
         if (gather && base + stride < a.n && (unsigned int)anc_next.x - (unsigned int)a.gid_offset < (unsigned int)a.n) {
             const size_t nsrc = (size_t)((unsigned int)anc_next.x - (unsigned int)a.gid_offset);
-#pragma unroll
-            for (int d = 0; d < D; ++d) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state_in + (size_t)d * a.ld + nsrc));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.state_in + nsrc * D));
         }
 
         // exact running max of the log-weights (NaN and padding lanes count as -inf, quirk Q9).  Sum statistics are not
@@ -907,7 +964,7 @@ template <typename Real>
 __global__ void __launch_bounds__(256) gather_kernel(const Real* __restrict__ in, Real* __restrict__ out, const int32_t* __restrict__ anc, size_t n, size_t ld, int D) {
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
         size_t src = (size_t)anc[i];
-        for (int d = 0; d < D; ++d) out[(size_t)d * ld + i] = __ldg(in + (size_t)d * ld + src);
+        for (int d = 0; d < D; ++d) out[i * D + d] = __ldg(in + src * D + d);
     }
 }
 
@@ -920,7 +977,7 @@ __global__ void __launch_bounds__(128) backtrace_kernel(const Real* __restrict__
         size_t cur = (size_t)ids[k];
         if (start_after_resample) cur = (size_t)hist_anc[(size_t)(T - 1) * ld + cur];   // ids name post-resample particles
         for (int t = T - 1; t >= 0; --t) {
-            for (int d = 0; d < D; ++d) out[(k * T + t) * D + d] = (double)hist_state[((size_t)t * D + d) * ld + cur];
+            for (int d = 0; d < D; ++d) out[(k * T + t) * D + d] = (double)hist_state[((size_t)t * ld + cur) * D + d];
             if (t > 0 && resampled[t - 1]) cur = (size_t)hist_anc[(size_t)(t - 1) * ld + cur];
         }
     }
@@ -938,6 +995,17 @@ __global__ void __launch_bounds__(256) to_f64_kernel(const Real* __restrict__ in
 template <typename Real>
 __global__ void __launch_bounds__(256) from_f64_kernel(const double* __restrict__ in, Real* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (Real)in[i];
+}
+// host-facing reads / writes of the state are double[D][N] (`state[d * N + i]`); on the device it is particle-major in Real
+template <typename Real>
+__global__ void __launch_bounds__(256) state_to_f64_kernel(const Real* __restrict__ in, double* __restrict__ out, size_t n, size_t ld, int D) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        for (int d = 0; d < D; ++d) out[(size_t)d * ld + i] = (double)in[i * D + d];
+}
+template <typename Real>
+__global__ void __launch_bounds__(256) state_from_f64_kernel(const double* __restrict__ in, Real* __restrict__ out, size_t n, size_t ld, int D) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        for (int d = 0; d < D; ++d) out[i * D + d] = (Real)in[(size_t)d * ld + i];
 }
 static __global__ void __launch_bounds__(256) i32_to_i64_kernel(const int32_t* __restrict__ in, long long* __restrict__ out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (long long)in[i];

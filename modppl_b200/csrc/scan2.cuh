@@ -79,7 +79,9 @@ __device__ __forceinline__ void warp_tile_counts(unsigned long long wp, const un
 // One warp expands slots [chunk_lo, chunk_lo + CAP) of its own range [0, total) (relative to ws).  CAP = 32 * (slots per
 // lane), a multiple of 256: `head` holds CAP 16-bit entries.
 // SINGLE: the caller guarantees chunk_lo == 0 and total <= CAP (the whole range in one pass): the window tests drop out.
-template <typename Real, int CAP = kWarpChunk, bool SINGLE = false>
+// CLIP: pull organisation (nested scheme on several GPUs) -- this shard fills only its OWN slot range, wherever the parents live:
+// slots outside [out_base, out_base + n_out_local) are some other GPU's to fill and are dropped here.
+template <typename Real, int CAP = kWarpChunk, bool SINGLE = false, bool CLIP = false>
 __device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsigned short* head, const unsigned int (&n)[4][4], unsigned int ws,
                                                   unsigned int total, unsigned int chunk_lo, unsigned long long slot_base /* global slot of ws */,
                                                   int32_t src0 /* value for local element 0, minus 1 */) {
@@ -132,6 +134,17 @@ __device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsi
     __syncwarp();
     const unsigned int valid = min((unsigned int)CAP, total - chunk_lo);
     const unsigned long long slot0 = slot_base + chunk_lo;
+    if constexpr (CLIP) {
+        const unsigned long long rel0 = slot0 - a.out_base;   // (wraps for slots below the range: then rel0 + o >= n_out_local too, the totals being < 2^32)
+#pragma unroll
+        for (int k = 0; k < CAP / 32; ++k) {
+            const unsigned int o = k * 32 + lane;
+            const unsigned long long rel = rel0 + o;
+            if (o < valid && rel < a.n_out_local) a.anc[rel] = src0 + (int32_t)head[o];
+        }
+        __syncwarp();
+        return false;
+    }
     const bool local = slot0 >= a.out_base && slot0 + valid <= a.out_base + a.n_out_local;   // whole chunk lands in this shard (always, on one GPU)
     if (local) {
         int32_t* dst = a.anc + (slot0 - a.out_base);

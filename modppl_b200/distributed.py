@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import lib, check
 from .particle_filter import ParticleSystem, SYSTEMATIC_FIXED
 
-PEER_BLOB_BYTES = 256
+PEER_BLOB_BYTES = 1024
 
 
 def shard_range(n_global, rank, world):
@@ -77,7 +77,7 @@ class ShardedParticleSystem(ParticleSystem):
         tr = self.trace()
         if tr[9] > 0:   # nested scheme (stamps: scripts/step_timeline.py)
             return {"extend_gate_wait": tr[1] - tr[0], "extend_start_to_last_block": tr[14] - tr[13], "to_section_pass": tr[9] - tr[14], "section_phase_a": tr[5] - tr[9],
-                    "collect_records_and_top_level": tr[7] - tr[6], "to_level1": tr[10] - tr[7], "level1_to_expansion": tr[11] - tr[10], "expansion_to_done_signal": tr[8] - tr[11]}
+                    "collect_records_and_top_level": tr[7] - tr[6], "to_plan_pass": tr[10] - tr[7], "plan_pass_to_expansion": tr[11] - tr[10], "expansion": tr[8] - tr[11]}
         return {"extend_gate_wait": tr[1] - tr[0], "extend_body": tr[2] - tr[1], "to_reduce_gate": tr[3] - tr[2], "reduce_gate_wait": tr[4] - tr[3],
                 "reduce_body": tr[5] - tr[4], "to_scan_gate": tr[6] - tr[5], "scan_gate_wait": tr[7] - tr[6], "scan_to_signal": tr[8] - tr[7]}
 

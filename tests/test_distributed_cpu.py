@@ -5,6 +5,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+D_BLOB = 1024      # MPL_PEER_BLOB_BYTES (include/modppl_b200.h)
 
 
 def _worker(rank, world, port, q):
@@ -50,5 +51,5 @@ def test_blob_exchange_and_reduction_world2():
         assert p.exitcode == 0
     assert res[0][:3] == (0, 0, 512) and res[1][:3] == (1, 512, 512)
     for r in res:
-        assert r[3] == [0, 1] and r[4] == [256, 256]      # blobs arrive in rank order, intact
+        assert r[3] == [0, 1] and r[4] == [D_BLOB, D_BLOB]      # blobs arrive in rank order, intact
         assert r[5] == 1.5                                  # max over ranks
