@@ -462,6 +462,8 @@ def run_config4_multi(args):
     scheme = {"systematic": m.SYSTEMATIC_FIXED, "nested": m.SYSTEMATIC_NESTED}.get(args.scheme)
     if scheme is None:
         raise SystemExit("sharded runs: --scheme nested | systematic")
+    if args.variant == "island":
+        return run_config4_islands(args, m, torch, dist, rank, world, local_rank, ys, scheme)
     ps = ShardedParticleSystem(m.lgssm4(), n_global, rank, world, seed=1, dtype="f32", device=local_rank)
     ps.upload_observations(ys)
     dist.barrier(); torch.cuda.synchronize()
@@ -472,12 +474,15 @@ def run_config4_multi(args):
     if sampler:
         time.sleep(0.5)      # nvidia-smi needs a moment to enumerate 8 GPUs
     l0 = ps.launch_count()
+    nv0 = ps.nvlink_bytes()
     dist.barrier(); torch.cuda.synchronize()
     ms = ps.run(1 + W, K, scheme)
     ps.sync()
     dist.barrier(); torch.cuda.synchronize()
     ms = max_over_ranks(ms)
     launches = ps.launch_count() - l0
+    nv = [None] * world
+    dist.all_gather_object(nv, (ps.nvlink_bytes() - nv0) / K)
     phases = ps.phase_times()
     all_phases = [None] * world
     dist.all_gather_object(all_phases, phases)
@@ -512,7 +517,9 @@ def run_config4_multi(args):
             "config": {"workload": WORKLOADS[4], "particles": f"2^{args.log2_particles} in total, sharded", "T_timed": K,
                        "resampling": f"global {args.scheme} resampling on integer weights (same ancestors as on one GPU); NVLink peer loads/stores inside the kernels, no NCCL on the data path",
                        "l2": "per-GPU state buffers stream every step", "log_ml": lml, "log_ml_truth": lml_truth, "log_ml_abs_err": abs(lml - lml_truth), "log_ml_steps": 1 + W + K,
-                       "peer_wait_timeouts": err},
+                       "peer_wait_timeouts": err, "variant": "global",
+                       "nvlink_payload_bytes_per_step": {"total": float(sum(nv)), "per_rank": [float(v) for v in nv],
+                                                         "what": "parent states gathered across shard edges, integer weights / chunk records of chunks that own another shard's slots, section records"}},
             "e2e": {"value": n_global * K / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 24},
             "gpu_launches": int(launches) * world, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": step_gbs, "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "traffic": None,
@@ -521,6 +528,67 @@ def run_config4_multi(args):
         }
         print(json.dumps(line))
     ps.close()
+    dist.destroy_process_group()
+
+
+def run_config4_islands(args, m, torch, dist, rank, world, local_rank, ys, scheme):
+    """the local-resample variant next to the global scheme (north_star): one island of N / G particles per GPU, local
+    resampling every step, island weights compared every `--exchange-every` steps (island-level resampling when their ESS has
+    dropped).  A different estimator: its log-ML is reported against the same Kalman value."""
+    from modppl_b200.distributed import IslandParticleSystem, max_over_ranks
+    n_global = 1 << args.log2_particles
+    K, W, S = args.steps, args.warmup, args.exchange_every
+    isl = IslandParticleSystem(m.lgssm4(), n_global, rank, world, seed=1, dtype="f32", device=local_rank)
+    isl.upload_observations(ys)
+    dist.barrier(); torch.cuda.synchronize()
+    isl.run(0, 1 + W, scheme, exchange_every=S)
+    isl.sync()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    if sampler:
+        time.sleep(0.5)
+    l0 = isl.launch_count()
+    x0 = isl.bytes_exchanged
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ms_dev = isl.run(1 + W, K, scheme, exchange_every=S)          # device time of the segments; the comparisons in between are host work
+    isl.sync()
+    dist.barrier(); torch.cuda.synchronize()
+    wall = max_over_ranks(time.perf_counter() - t0)               # everything: segments, island comparisons, barriers
+    ms_dev = max_over_ranks(ms_dev)
+    launches = isl.launch_count() - l0
+    lml = isl.log_marginal_likelihood_estimate()
+    lml_truth = kalman_log_ml(ys[:1 + W + K])
+    t_first = 1 + W + K
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(K):
+        isl.step_resample(ys[t_first + k], scheme, exchange_every=S)
+    isl.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    ex = [None] * world
+    dist.all_gather_object(ex, (isl.bytes_exchanged - x0, isl.n_island_resamplings))
+    if rank == 0:
+        value = n_global * K / wall
+        peak, peak_src = measured_peak()
+        step_gbs = BYTES_PER_PARTICLE_STEP * value / 1e9
+        line = {
+            "metric": METRIC4, "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": wall * 1e3 / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOADS[4], "particles": f"2^{args.log2_particles} in total, {world} islands of 2^{args.log2_particles}/{world}", "T_timed": K,
+                       "variant": "island", "resampling": f"LOCAL {args.scheme} resampling on each island every step; island weights compared every {S} steps, islands resampled when "
+                                                          "their ESS < G/2 -- a different estimator from the global scheme (not the same ancestors)",
+                       "l2": "per-GPU state buffers stream every step", "log_ml": lml, "log_ml_truth": lml_truth, "log_ml_abs_err": abs(lml - lml_truth), "log_ml_steps": 1 + W + K,
+                       "island_resamplings": int(ex[0][1]), "device_ms_per_step": ms_dev / K,
+                       "nvlink_payload_bytes_per_step": {"total": float(sum(e[0] for e in ex)) / K, "what": "whole islands copied at island-level resamplings (none when the island weights stay balanced)"},
+                       "host_bytes_per_comparison": 16 * world},
+            "e2e": {"value": n_global * K / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 24},
+            "gpu_launches": int(launches) * world, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole step", "achieved": step_gbs, "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "traffic": None,
+                         "peak_source": peak_src + f" x {world} GPUs"},
+        }
+        print(json.dumps(line))
+    isl.close()
     dist.destroy_process_group()
 
 
@@ -698,6 +766,10 @@ def main():
                     help="config 4/5 resampler: nested systematic on integer weights (default, fastest), single-level systematic, multinomial on integer "
                          "weights, or the reference's own multinomial (bit-exact parity path)")
     ap.add_argument("--log2-particles", type=int, default=LOG2_PARTICLES)
+    ap.add_argument("--variant", default="global", choices=["global", "island"],
+                    help="several GPUs, config 4: global resampling over all shards (default; the same ancestors as on one GPU) or one island per GPU "
+                         "with local resampling and occasional island-level resampling (a different estimator)")
+    ap.add_argument("--exchange-every", type=int, default=50, help="island variant: steps between two comparisons of the island weights")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

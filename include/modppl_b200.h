@@ -189,7 +189,18 @@ int mpl_ps_peer_export(mpl_ps*, void* blob /* MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_attach(mpl_ps*, int rank, int world, const void* blobs /* world * MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_detach(mpl_ps*);
 int mpl_ps_peer_error(mpl_ps*, int* out);   /* 1 if a kernel gave up waiting for a peer (bounded spin) */
+int mpl_ps_nvlink_bytes(mpl_ps*, uint64_t* out);   /* payload bytes requested from the peers' memory so far (remote parents, weights, records) */
 int mpl_ps_trace(mpl_ps*, long long* out16);   /* device time stamps (ns) of the last sharded step's phases; diagnostics */
+/* Islands -- the local-resample-then-rebalance variant: each GPU filters N / G particles of its own and resamples
+ * locally, so no step waits for another GPU.  The islands' weights are their log-ML increments; the host compares them now and
+ * then and, when the island-level ESS has dropped, resamples whole islands: a surviving island is copied over NVLink into the
+ * place of one that died out (orchestration: modppl_b200/distributed.py, IslandParticleSystem).  A different estimator from the
+ * global scheme above (not the same ancestors), unbiased for the likelihood all the same. */
+int mpl_ps_island_export(mpl_ps*, void* blob /* MPL_PEER_BLOB_BYTES */);
+int mpl_ps_island_attach(mpl_ps*, int rank, int n_islands, const void* blobs /* n_islands * MPL_PEER_BLOB_BYTES */);
+int mpl_ps_live_buffer(mpl_ps*, int* out);                 /* which state buffer is live (a pending resample is applied first) */
+int mpl_ps_island_copy_from(mpl_ps*, int src_island, int src_live_buffer);   /* this island := a copy of island src (uniform weights) */
+int mpl_ps_copy_state(mpl_ps* dst, mpl_ps* src);           /* the same between two particle systems of one process */
 /* Test hook: `world` shards emulated on ONE GPU run the multi-GPU kernels phase by phase (remote loads/stores become
  * local).  init + resample, then steps with a resample after each except the last; outputs the final state
  * double[D * n_global] (SoA), log-weights double[n_global] and the log-ML estimate. */

@@ -108,6 +108,12 @@ SYMBOLS = {
     "mpl_ps_peer_detach": (C.c_int, C.c_void_p),
     "mpl_ps_peer_error": (C.c_int, C.c_void_p, C.POINTER(C.c_int)),
     "mpl_ps_trace": (C.c_int, C.c_void_p, C.POINTER(C.c_longlong)),
+    "mpl_ps_nvlink_bytes": (C.c_int, C.c_void_p, c_u64_p),
+    "mpl_ps_island_export": (C.c_int, C.c_void_p, C.c_void_p),
+    "mpl_ps_island_attach": (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p),
+    "mpl_ps_live_buffer": (C.c_int, C.c_void_p, C.POINTER(C.c_int)),
+    "mpl_ps_island_copy_from": (C.c_int, C.c_void_p, C.c_int, C.c_int),
+    "mpl_ps_copy_state": (C.c_int, C.c_void_p, C.c_void_p),
     "mpl_test_virtual_shards": (C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, c_double_p, C.c_size_t, C.c_size_t, c_double_p, c_double_p, c_double_p, c_double_p),
     "mpl_test_virtual_shards_scheme": (C.c_int, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_uint64, C.c_int, c_double_p, C.c_size_t, C.c_size_t, c_double_p, c_double_p, c_double_p, c_double_p),
 }

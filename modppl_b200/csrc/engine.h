@@ -88,6 +88,10 @@ struct mpl_ps {
     mpl::Mailbox* mailbox;            // device memory of this rank, written by every rank
     void* ipc_opened[8][mpl::kMaxPeers];   // pointers obtained from cudaIpcOpenMemHandle (to close on detach)
     bool peer_virtual;                // peers live in this process (single-GPU emulation used by the tests)
+    // islands (local resampling; multi_gpu.cu): the other islands' state buffers, for the occasional island-level resampling
+    int n_islands, island_rank;
+    const void* island_state[2][mpl::kMaxPeers];
+    void* island_opened[2][mpl::kMaxPeers];
 };
 
 namespace mpl {
@@ -97,6 +101,7 @@ int ps_phase_nested(mpl_ps* ps, int phase);
 int ps_phase_reduce(mpl_ps* ps);
 int ps_phase_scan(mpl_ps* ps);
 int ensure_chunk_records(mpl_ps* ps);
+int materialise(mpl_ps* ps);   // apply a pending ancestor gather
 // categorical.rs:25-30: the sequential f64 running sum of `probs`, bit for bit (parallel emulation for long inputs); ps may be null
 int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream);
 }

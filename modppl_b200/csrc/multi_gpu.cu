@@ -148,6 +148,85 @@ extern "C" int mpl_ps_peer_detach(mpl_ps* ps) {
     return MPL_OK;
 }
 
+// ---- islands (the local-resample variant of SURVEY 8e): every GPU runs its own filter on N / G particles and resamples locally;
+// nothing is exchanged per step.  Now and then the host compares the islands' weights (their log-ML increments) and, when the
+// island-level ESS has dropped, resamples whole islands: an island that is selected twice is copied over NVLink into the place of
+// one that was not selected.  These calls are that copy; the orchestration is host code (modppl_b200/distributed.py).
+namespace {
+struct IslandBlob { cudaIpcMemHandle_t state[2]; };
+int island_install(mpl_ps* dst, const void* src_state) {   // src_state: the source island's live state, D x ld elements, same shape
+    int rc = MPL_OK;
+    const size_t bytes = (size_t)dst->D * dst->ld * (dst->dtype == MPL_F64 ? 8 : 4);
+    MPL_CUDA_OK(cudaMemcpyAsync(dst->state[dst->cur ^ 1], src_state, bytes, cudaMemcpyDeviceToDevice, dst->stream));
+    MPL_CUDA_OK(cudaMemsetAsync(dst->lw, 0, dst->ld * (dst->dtype == MPL_F64 ? 8 : 4), dst->stream));
+    MPL_CUDA_OK(cudaMemsetAsync((char*)dst->stats + offsetof(DeviceStats, resampled_flag), 0, sizeof(int) * 2, dst->stream));
+    MPL_CUDA_OK(cudaMemsetAsync((char*)dst->stats + offsetof(DeviceStats, resampled), 0, sizeof(int), dst->stream));
+    MPL_CUDA_OK(cudaStreamSynchronize(dst->stream));
+    dst->cur ^= 1;
+    dst->pending_gather = false; dst->stats_valid = false; dst->max_valid = false; dst->prequantised = 0;
+    return rc;
+}
+}  // namespace
+
+extern "C" int mpl_ps_island_export(mpl_ps* ps, void* blob) {
+    if (!ps || !blob) return fail(MPL_ERR_INVALID, "null argument");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    IslandBlob b;
+    std::memset(&b, 0, sizeof b);
+    MPL_CUDA_OK(cudaIpcGetMemHandle(&b.state[0], ps->state[0]));
+    MPL_CUDA_OK(cudaIpcGetMemHandle(&b.state[1], ps->state[1]));
+    std::memset(blob, 0, MPL_PEER_BLOB_BYTES);
+    std::memcpy(blob, &b, sizeof b);
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_island_attach(mpl_ps* ps, int rank, int n_islands, const void* blobs) {
+    if (!ps || !blobs) return fail(MPL_ERR_INVALID, "null argument");
+    if (n_islands < 1 || n_islands > kMaxPeers || rank < 0 || rank >= n_islands) return fail(MPL_ERR_INVALID, "island attach: 1..8 islands, 0 <= rank < islands");
+    if (ps->world > 1) return fail(MPL_ERR_INVALID, "island attach: this particle system is a shard of a global one");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    for (int h = 0; h < n_islands; ++h) {
+        if (h == rank) { ps->island_state[0][h] = ps->state[0]; ps->island_state[1][h] = ps->state[1]; continue; }
+        IslandBlob b;
+        std::memcpy(&b, (const char*)blobs + (size_t)h * MPL_PEER_BLOB_BYTES, sizeof b);
+        for (int k = 0; k < 2; ++k) {
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, b.state[k], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(MPL_ERR_CUDA, std::string("island attach: cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+            ps->island_state[k][h] = p;
+            ps->island_opened[k][h] = p;
+        }
+    }
+    ps->n_islands = n_islands; ps->island_rank = rank;
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_live_buffer(mpl_ps* ps, int* out) {   // which of the two state buffers is live, with any pending resample applied
+    if (!ps || !out) return fail(MPL_ERR_INVALID, "null argument");
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    int rc = materialise(ps);   // a pending resample is applied (one gather on the device)
+    if (rc) return rc;
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    *out = ps->cur;
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_island_copy_from(mpl_ps* ps, int src_island, int src_live_buffer) {
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    if (src_island < 0 || src_island >= ps->n_islands || (src_live_buffer != 0 && src_live_buffer != 1)) return fail(MPL_ERR_INVALID, "island copy: bad source");
+    if (src_island == ps->island_rank) return MPL_OK;
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    return island_install(ps, ps->island_state[src_live_buffer][src_island]);
+}
+
+extern "C" int mpl_ps_copy_state(mpl_ps* dst, mpl_ps* src) {   // islands living in one process (tests): same device, same shape
+    if (!dst || !src) return fail(MPL_ERR_INVALID, "null handle");
+    if (dst->n != src->n || dst->D != src->D || dst->dtype != src->dtype || dst->ld != src->ld) return fail(MPL_ERR_INVALID, "copy_state: the two particle systems differ in shape");
+    int live = 0, rc = mpl_ps_live_buffer(src, &live);
+    if (rc) return rc;
+    return island_install(dst, src->state[live]);
+}
+
 extern "C" int mpl_ps_trace(mpl_ps* ps, long long* out16) {
     // %globaltimer stamps (ns) of the last step: [0] extend gate entered, [1] passed, [2] extend's last block done,
     // [3] reduce gate entered, [4] passed, [5] reduce's last block done, [6] scan gate entered, [7] passed, [8] done flag sent
@@ -156,6 +235,19 @@ extern "C" int mpl_ps_trace(mpl_ps* ps, long long* out16) {
     DeviceStats h;
     MPL_CUDA_OK(cudaMemcpy(&h, ps->stats, sizeof h, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; ++i) out16[i] = h.trace[i];
+    return MPL_OK;
+}
+
+extern "C" int mpl_ps_nvlink_bytes(mpl_ps* ps, uint64_t* out) {
+    // payload bytes this GPU has requested from its peers' memory so far: parent states gathered across a shard edge, integer
+    // weights and chunk records of chunks that own some of this GPU's slots, the peers' section records
+    if (!ps || !out) return fail(MPL_ERR_INVALID, "null argument");
+    MPL_CUDA_OK(cudaStreamSynchronize(ps->stream));
+    DeviceStats h;
+    MPL_CUDA_OK(cudaMemcpy(&h, ps->stats, sizeof h, cudaMemcpyDeviceToHost));
+    unsigned long long polled = 0;
+    if (ps->mailbox) MPL_CUDA_OK(cudaMemcpy(&polled, (const char*)ps->mailbox + offsetof(Mailbox, nvlink_polled), sizeof polled, cudaMemcpyDeviceToHost));
+    *out = h.nvlink_bytes + polled;
     return MPL_OK;
 }
 

@@ -31,23 +31,8 @@ namespace mpl {
 
 constexpr int kChunksPerTile = kScanTile / kChunk;   // 32
 constexpr int kTilesPerSection = 32;                 // one block of the section pass (one warp scan over its tile sums)
-constexpr size_t kSection = (size_t)kTilesPerSection * kScanTile;   // 2^17 particles
+static_assert(kSection == (size_t)kTilesPerSection * kScanTile, "a section is 32 tiles");
 
-struct NestedPrefixes {
-    unsigned long long* tile_pre;   // [local tile] exclusive prefix of the tile's chunk masses inside its section (scale E_s)
-    int* sec_E;                     // [GLOBAL section] E_s (kChunkEmpty: no finite weight)
-    unsigned long long* sec_T;      // [GLOBAL section] T_s
-    double* sec_sq;                 // [GLOBAL section] sum of squared integer weights at scale E_s (ESS)
-    unsigned long long* sec_pre;    // [GLOBAL section] exclusive prefix of M_s                       (top-level pass)
-    unsigned long long* sec_M;      // [GLOBAL section] M_s
-    unsigned long long* sec_a;      // [GLOBAL section] first output slot of the section                (top-level pass)
-    unsigned long long* sec_n;      // [GLOBAL section] number of output slots of the section
-    unsigned int* P;                // [GLOBAL chunk, + 1 sentinel] first output slot of the chunk (monotone; chunk c owns [P[c], P[c+1]))  (plan pass)
-    unsigned int* F;                // [GLOBAL output tile] the chunk that owns the tile's first slot
-    unsigned int sec0;              // global number of this shard's first section
-    unsigned int n_sec;             // sections of this shard
-    unsigned int n_sec_global;
-};
 
 // warp-wide sum of per-lane values below 2^48: two integer redux instructions instead of ten 32-bit shuffles
 __device__ __forceinline__ unsigned long long warp_sum_u48(unsigned long long v) {
@@ -100,123 +85,73 @@ __device__ __forceinline__ unsigned long long nested_chunk_offset(unsigned long 
 // 2^(-2d), exactly, for 0 <= d < 500 (rescales a sum of squares between two power-of-two references)
 __device__ __forceinline__ double pow2_neg2(int d) { return __longlong_as_double((long long)(1023 - 2 * d) << 52); }
 
-struct NestedTopShared {
-    int wmax[kScanThreads / 32];
-    unsigned long long ws[kScanThreads / 32];
-    double wsq[kScanThreads / 32];
-    unsigned long long carry;
-};
-
-// Top level, by one whole block: E, M_s, W, the ESS, and level 0 of the resampling (slot j sits at j*W + U; section s owns
-// the slots [a_s, a_s + n_s)) from the section records.  Written for latency: with up to 1024 sections (2^27 particles)
-// every thread loads its 4 records once and everything else stays in registers.
-__device__ __forceinline__ void nested_top_level(const NestedPrefixes& nb, DeviceStats* st, NestedTopShared& sh, uint64_t seed, long long rt,
-                                                 unsigned long long n_out, int dynamic, double ess_threshold) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Top level, by ONE WARP (of the section pass' last block): E, M_s, W, the ESS, and level 0 of the resampling (slot j sits at j*W + U; section s owns the slots
+// [a_s, a_s + n_s)) from the section records.  Sections are taken in groups of 128, 4 consecutive ones per lane.
+__device__ __forceinline__ void nested_top_level_warp(const NestedPrefixes& nb, DeviceStats* st, uint64_t seed, long long rt, unsigned long long n_out, int dynamic,
+                                                      double ess_threshold) {
+    const int lane = threadIdx.x & 31;
     const unsigned int n_sec = nb.n_sec_global;
-    if (tid == 0) sh.carry = 0ull;
     int E = kChunkEmpty;
-    if (n_sec > kScanThreads * 4) {   // more sections than one pass holds: the maximum needs its own pass
-        int emax = kChunkEmpty;
-        for (unsigned int i = tid; i < n_sec; i += kScanThreads) emax = max(emax, __ldcg(nb.sec_E + i));
-        emax = __reduce_max_sync(0xffffffffu, emax);
-        if (lane == 0) sh.wmax[warp] = emax;
-        __syncthreads();
-#pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) E = max(E, sh.wmax[w]);
-        __syncthreads();
-    }
-    const unsigned long long word = resample_rand_word(seed, rt, st);   // (independent of the loads below)
+    for (unsigned int i = lane; i < n_sec; i += 32) E = max(E, __ldcg(nb.sec_E + i));
+    E = __reduce_max_sync(0xffffffffu, E);
+    const unsigned long long word = resample_rand_word(seed, rt, st);   // (independent of the loads)
+    unsigned long long carry = 0;
     double sqt = 0.;
-    unsigned long long v[4], pre0 = 0;   // the last pass' values stay in registers for level 0
-    unsigned int first = 0;
-    for (unsigned int base = 0; base < n_sec; base += kScanThreads * 4) {
-        first = base + tid * 4;
-        int e_s[4];
-        unsigned long long T[4];
-        double sq[4];
+    for (unsigned int base = 0; base < n_sec; base += 128) {
+        const unsigned int first = base + 4u * lane;
+        unsigned long long v[4], tot = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const bool ok = first + i < n_sec;
-            e_s[i] = ok ? __ldcg(nb.sec_E + first + i) : kChunkEmpty;
-            T[i] = ok ? __ldcg(nb.sec_T + first + i) : 0ull;
-            sq[i] = ok ? __ldcg(nb.sec_sq + first + i) : 0.;
-        }
-        if (n_sec <= kScanThreads * 4) {   // single pass: the maximum from the values just loaded
-            int emax = max(max(e_s[0], e_s[1]), max(e_s[2], e_s[3]));
-            emax = __reduce_max_sync(0xffffffffu, emax);
-            if (lane == 0) sh.wmax[warp] = emax;
-            __syncthreads();
-#pragma unroll
-            for (int w = 0; w < kScanThreads / 32; ++w) E = max(E, sh.wmax[w]);
-        }
-        unsigned long long tot = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            v[i] = nested_shift(T[i], e_s[i], E);
-            if (e_s[i] != kChunkEmpty && E - e_s[i] < 500) sqt += sq[i] * pow2_neg2(E - e_s[i]);
+            const int e_s = ok ? __ldcg(nb.sec_E + first + i) : kChunkEmpty;
+            const unsigned long long T = ok ? __ldcg(nb.sec_T + first + i) : 0ull;
+            const double sq = ok ? __ldcg(nb.sec_sq + first + i) : 0.;
+            v[i] = nested_shift(T, e_s, E);
+            if (e_s != kChunkEmpty && E - e_s < 500) sqt += sq * pow2_neg2(E - e_s);
             tot += v[i];
         }
         unsigned long long incl = tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
-        if (lane == 31) sh.ws[warp] = incl;
-        __syncthreads();
-        unsigned long long all = 0;
-        pre0 = sh.carry + incl - tot;
+        unsigned long long pre = carry + incl - tot;
 #pragma unroll
-        for (int w = 0; w < kScanThreads / 32; ++w) { unsigned long long x = sh.ws[w]; if (w < warp) pre0 += x; all += x; }
-        if (base + kScanThreads * 4 < n_sec) {   // more passes follow: their level 0 reads the prefixes back
-            unsigned long long pre = pre0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { if (first + i < n_sec) { nb.sec_pre[first + i] = pre; nb.sec_M[first + i] = v[i]; } pre += v[i]; }
-        }
-        __syncthreads();
-        if (tid == 0) sh.carry += all;
-        __syncthreads();
+        for (int i = 0; i < 4; ++i) { if (first + i < n_sec) { nb.sec_pre[first + i] = pre; nb.sec_M[first + i] = v[i]; } pre += v[i]; }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sqt += __shfl_xor_sync(0xffffffffu, sqt, o);
-    if (lane == 0) sh.wsq[warp] = sqt;
-    const unsigned long long W = sh.carry;
+    const unsigned long long W = carry;
     if (W != 0ull) {
         const unsigned long long U = __umul64hi(word, W);
         const double inv_w = 1. / (double)W;
-        for (unsigned int base = 0; base < n_sec; base += kScanThreads * 4) {
-            const bool in_regs = base + kScanThreads * 4 >= n_sec;
-            const unsigned int f = base + tid * 4;
-            unsigned long long pre = in_regs ? pre0 : 0ull;
+        for (unsigned int base = 0; base < n_sec; base += 128) {   // (every lane re-reads what it wrote itself)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                if (f + i >= n_sec) break;
-                const unsigned long long m = in_regs ? v[i] : nb.sec_M[f + i];
-                if (!in_regs) pre = nb.sec_pre[f + i];
-                const TileBase sb = tile_base_exact(pre, W, U, n_out, inv_w);
-                nb.sec_a[f + i] = sb.n_start;
-                nb.sec_n[f + i] = local_count(m, sb.rem, (double)sb.rem, W, (double)n_out, n_out, inv_w);
-                pre += m;
+                const unsigned int sc = base + 4u * lane + i;
+                if (sc >= n_sec) break;
+                const unsigned long long m = nb.sec_M[sc];
+                const TileBase sb = tile_base_exact(nb.sec_pre[sc], W, U, n_out, inv_w);
+                nb.sec_a[sc] = sb.n_start;
+                nb.sec_n[sc] = local_count(m, sb.rem, (double)sb.rem, W, (double)n_out, n_out, inv_w);
             }
         }
     }
-    __syncthreads();
-    if (tid == 0) {
-        double sq = 0.;
-        for (int i = 0; i < kScanThreads / 32; ++i) sq += sh.wsq[i];
+    if (lane == 0) {
         st->W = W; st->c_offset = 0; st->nest_E = E; st->rand_word = word;
-        st->sumexp2 = sq;
-        const double ess = sq > 0. ? ((double)W * (double)W) / sq : 0.;
+        st->sumexp2 = sqt;
+        const double ess = sqt > 0. ? ((double)W * (double)W) / sqt : 0.;
         st->ess = ess;
         if (dynamic) st->do_resample = (ess < ess_threshold) ? 1 : 0;   // ESS trigger, decided where the numbers are
     }
 }
 
-// several GPUs: collect every other shard's section records (the caller then runs the top level).  The records are PULLED:
-// every rank publishes its own in its own mailbox and the readers poll them over NVLink -- a kernel that stores into
+// several GPUs: collect every other shard's section records (the caller then runs the top level), one warp.  The records are
+// PULLED: every rank publishes its own in its own mailbox and the readers poll them over NVLink -- a kernel that stores into
 // another GPU's memory cannot complete before those stores are acknowledged (~4 us at every kernel boundary), a kernel
 // that only loads has nothing to wait for.
-__device__ __forceinline__ void collect_section_records(const PeerTable& p, long long epoch, const NestedPrefixes& nb) {
+__device__ __forceinline__ void collect_section_records_warp(const PeerTable& p, long long epoch, const NestedPrefixes& nb) {
     SpinGuard g(p);
-    for (unsigned int sg = threadIdx.x; sg < nb.n_sec_global; sg += kScanThreads) {
+    for (unsigned int sg = threadIdx.x & 31; sg < nb.n_sec_global; sg += 32) {
         if (sg - nb.sec0 < nb.n_sec) continue;   // own sections: already in place
         const volatile unsigned long long* src = p.mail[sg / nb.n_sec]->sec_ll[epoch & 1][sg];   // (equal shards of whole sections: the owner of global section sg)
         unsigned long long w[6];
@@ -228,12 +163,23 @@ __device__ __forceinline__ void collect_section_records(const PeerTable& p, long
             for (int k = 0; k < 6; ++k) ok = ok && (unsigned int)(w[k] >> 32) == (unsigned int)epoch;
             if (ok || g.give_up()) break;
         }
+        atomicAdd(&p.mail[p.rank]->nvlink_polled, 48ull);
         nb.sec_E[sg] = (int)(unsigned int)w[0];
         nb.sec_T[sg] = (w[2] & 0xffffffffull) | (w[3] << 32);
         nb.sec_sq[sg] = __longlong_as_double((long long)((w[4] & 0xffffffffull) | (w[5] << 32)));
     }
     __threadfence();
-    __syncthreads();
+    __syncwarp();
+}
+
+// the tail of the section level, by the warp that completed this shard's LAST section: (several GPUs: the other shards' records,)
+// the top level
+__device__ __forceinline__ void nested_after_sections_warp(const PeerTable& peer, const NestedPrefixes& nb, DeviceStats* st, long long epoch, uint64_t seed, long long rt,
+                                                           unsigned long long n_out, int dynamic, double ess_threshold) {
+    const int lane = threadIdx.x & 31;
+    if (peer.world > 1) { if (lane == 0) st->trace[6] = global_ns(); collect_section_records_warp(peer, epoch, nb); }
+    nested_top_level_warp(nb, st, seed, rt, n_out, dynamic, ess_threshold);
+    if (lane == 0) st->trace[7] = global_ns();
 }
 
 // scalar bookkeeping of resample(): particle_filter.rs:104-105,114 (one thread of the expansion kernel)
@@ -283,7 +229,6 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     __shared__ unsigned long long ts[kTilesPerSection];
     __shared__ double tsq[kTilesPerSection];
     __shared__ int wmax[kScanThreads / 32];
-    __shared__ NestedTopShared top;
     __shared__ bool is_last;
     DeviceStats* st = a.stats;
     pdl_wait();
@@ -292,9 +237,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     const long long epoch = a.epoch < 0 ? st->t : a.epoch;
     if (blockIdx.x == 0 && tid == 0) st->trace[9] = global_ns();
     if constexpr (PHASES == 2) {
-        if (a.peer.world > 1) { if (tid == 0) st->trace[6] = global_ns(); collect_section_records(a.peer, epoch, nb); }
-        nested_top_level(nb, st, top, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
-        if (tid == 0) st->trace[7] = global_ns();
+        if (warp == 0) nested_after_sections_warp(a.peer, nb, st, epoch, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
         return;
     }
     const unsigned int sec = blockIdx.x;
@@ -358,9 +301,8 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     __threadfence();
     if (tid == 0) { st->overflow_count = 0; st->blocks_done = 0; st->trace[5] = global_ns(); }
     if constexpr (PHASES == 3) {
-        if (a.peer.world > 1) { if (tid == 0) st->trace[6] = global_ns(); collect_section_records(a.peer, epoch, nb); }
-        nested_top_level(nb, st, top, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
-        if (tid == 0) st->trace[7] = global_ns();
+        __syncthreads();
+        if (warp == 0) nested_after_sections_warp(a.peer, nb, st, epoch, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
     }
 }
 
@@ -404,6 +346,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_plan_kernel(FixedArgs<Rea
     const unsigned int c_loc0 = cg0 - owner * (a.peer.n_loc / (unsigned int)kChunk);
     const int* rec_e = a.peer.rec_e[par][owner] + c_loc0;
     const unsigned int* rec_S = a.peer.rec_S[par][owner] + c_loc0;
+    if (tid == 0 && owner != (unsigned int)a.peer.rank) atomicAdd(&st->nvlink_bytes, (unsigned long long)cnt * 8ull);
     unsigned int S[4];
     unsigned long long G[4], tot = 0;
     {
@@ -537,6 +480,7 @@ __device__ __forceinline__ void nested_load_warp_tile(const FixedArgs<Real>& a, 
         n_own = (size_t)a.peer.n_loc;
         lw = reinterpret_cast<const Real*>(a.peer.lw[par][owner]);
         rec_e = a.peer.rec_e[par][owner];
+        if (lane == 0 && owner != (unsigned int)a.peer.rank) atomicAdd(&a.stats->nvlink_bytes, (unsigned long long)(kWarpTile * sizeof(Real)));
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {

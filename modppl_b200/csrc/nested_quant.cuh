@@ -7,6 +7,8 @@ namespace mpl {
 
 constexpr int kChunk = 128;                       // particles per chunk == one warp x 4 particles
 
+constexpr size_t kSection = (size_t)1 << 17;      // particles per section (1024 chunks; one block of the section pass)
+
 constexpr int kNestedBits = 22;                   // a chunk's integer weights: rint(w_i / 2^e_c * 2^22) <= 2^22, so a chunk sum fits 32 bits
 
 struct ChunkRecords {
@@ -15,6 +17,23 @@ struct ChunkRecords {
     float* sq;               // sum of squared integer weights (for the ESS), as a float
 };
 constexpr int kChunkEmpty = -2147483647 - 1;
+
+// arrays of the levels above the chunks (nested.cuh)
+struct NestedPrefixes {
+    unsigned long long* tile_pre;   // [local tile] exclusive prefix of the tile's chunk masses inside its section (scale E_s)
+    int* sec_E;                     // [GLOBAL section] E_s (kChunkEmpty: no finite weight)
+    unsigned long long* sec_T;      // [GLOBAL section] T_s
+    double* sec_sq;                 // [GLOBAL section] sum of squared integer weights at scale E_s (ESS)
+    unsigned long long* sec_pre;    // [GLOBAL section] exclusive prefix of M_s                       (top-level pass)
+    unsigned long long* sec_M;      // [GLOBAL section] M_s
+    unsigned long long* sec_a;      // [GLOBAL section] first output slot of the section                (top-level pass)
+    unsigned long long* sec_n;      // [GLOBAL section] number of output slots of the section
+    unsigned int* P;                // [GLOBAL chunk, + 1 sentinel] first output slot of the chunk (monotone; chunk c owns [P[c], P[c+1]))  (plan pass)
+    unsigned int* F;                // [GLOBAL output tile] the chunk that owns the tile's first slot
+    unsigned int sec0;              // global number of this shard's first section
+    unsigned int n_sec;             // sections of this shard
+    unsigned int n_sec_global;
+};
 
 __device__ __forceinline__ unsigned long long splitmix64_mix(unsigned long long z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -112,6 +112,7 @@ static int flush_timers(mpl_ps* ps) {
 }
 
 static void refresh_chunk_records(mpl_ps* ps);
+static NestedPrefixes make_prefixes(mpl_ps* ps);
 static size_t elem_size(const mpl_ps* ps) { return ps->dtype == MPL_F64 ? 8 : 4; }
 
 static int grid_for(size_t work_items, int per_block, int max_blocks) {
@@ -238,7 +239,7 @@ static int fetch_stats(mpl_ps* ps) {
 }
 
 // materialise a pending ancestor gather (only needed when the host looks at / overwrites state between resample and step)
-static int materialise(mpl_ps* ps) {
+int materialise(mpl_ps* ps) {
     if (!ps->pending_gather) return MPL_OK;
     if (ps->world > 1) return fail(MPL_ERR_UNSUPPORTED, "sharded particle system: read or write state after the next step (ancestors point into other shards)");
     const int grid = grid_for(ps->n, 256, kNumSMs * 8);
@@ -368,6 +369,14 @@ int ensure_chunk_records(mpl_ps* ps) {
     return MPL_OK;
 }
 
+static NestedPrefixes make_prefixes(mpl_ps* ps) {
+    unsigned long long* sec = ps->nest_sec;
+    const size_t n_sec_global = (ps->n_global + kSection - 1) / kSection;
+    return NestedPrefixes{ps->nest_tile_pre, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
+                          sec + 5 * kMaxSections, sec + 6 * kMaxSections, ps->nest_P, ps->nest_F,
+                          (unsigned int)(ps->gid_offset / kSection), (unsigned int)((ps->n + kSection - 1) / kSection), (unsigned int)n_sec_global};
+}
+
 // phases: 1 = quantise (unless the extend did it) + chunk pass, 2 = expansion (+ the peers' "done" flag); 3 = both
 // dynamic: ESS-triggered (decision on the device; the log-weights survive: quantisation keeps them, the expansion re-quantises)
 template <typename Real>
@@ -386,10 +395,7 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     if (ps->world <= 1) for (int p = 0; p < 2; ++p) ps->peer.lw[p][0] = ps->lw;   // (the log-weight array may have been reallocated: keep the self-table current)
     a.peer = ps->peer;
     ChunkRecords rec{ps->rec_e, ps->rec_S, ps->rec_sq};
-    unsigned long long* sec = ps->nest_sec;
-    NestedPrefixes nb{ps->nest_tile_pre, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
-                      sec + 5 * kMaxSections, sec + 6 * kMaxSections, ps->nest_P, ps->nest_F,
-                      (unsigned int)(ps->gid_offset / kSection), (unsigned int)((ps->n + kSection - 1) / kSection), (unsigned int)n_sec_global};
+    NestedPrefixes nb = make_prefixes(ps);
     const unsigned int num_tiles = (unsigned int)((ps->n + kScanTile - 1) / kScanTile);
     const unsigned int num_chunks = (unsigned int)((ps->n + kChunk - 1) / kChunk);
     const unsigned int n_chunks_global = (unsigned int)((ps->n_global + kChunk - 1) / kChunk), n_tiles_global = (unsigned int)((ps->n_global + kScanTile - 1) / kScanTile);
@@ -647,6 +653,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false; ps->hist_broken = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
+    ps->n_islands = 1; ps->island_rank = 0; std::memset(ps->island_state, 0, sizeof ps->island_state); std::memset(ps->island_opened, 0, sizeof ps->island_opened);
     ps->probs = nullptr; ps->cums = nullptr; ps->icum = nullptr; ps->obs_dev = nullptr; ps->obs_steps = 0; ps->staging = nullptr;
     const size_t es = elem_size(ps);
     const size_t num_tiles = ps->ld / kScanTile;
@@ -701,6 +708,7 @@ extern "C" void mpl_ps_destroy(mpl_ps* ps) {
     cudaFree(ps->rec_e2); cudaFree(ps->rec_S2); cudaFree(ps->rec_sq); cudaFree(ps->nest_tile_pre); cudaFree(ps->nest_sec); cudaFree(ps->nest_P); cudaFree(ps->nest_F);
     cudaFree(ps->lw_alt);
     if (ps->world > 1 && !ps->peer_virtual) mpl_ps_peer_detach(ps);
+    for (int k = 0; k < 2; ++k) for (int h = 0; h < kMaxPeers; ++h) if (ps->island_opened[k][h]) cudaIpcCloseMemHandle(ps->island_opened[k][h]);
     cudaFree(ps->mailbox);
     cudaFree(ps->probs); cudaFree(ps->cums); cudaFree(ps->icum); cudaFree(ps->obs_dev); cudaFree(ps->staging);
     if (ps->stream) cudaStreamDestroy(ps->stream);

@@ -48,6 +48,7 @@ struct DeviceStats {
     long long trace[16];           // %globaltimer stamps of the last step's phases (sharded runs; mpl_ps_trace)
     int nest_E;                    // nested scheme: the global power-of-two reference of this resample
     unsigned int pad2;
+    unsigned long long nvlink_bytes;   // sharded runs: payload bytes this GPU has requested from its peers' memory so far (diagnostics: mpl_ps_nvlink_bytes)
 };
 __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
@@ -67,6 +68,7 @@ struct Mailbox {
     long long flag_done[kMaxPeers];              // shard h has written every ancestor it owes for this step
     int error;
     int pad;
+    unsigned long long nvlink_polled;   // bytes of section records fetched from peers (one successful poll each; diagnostics)
     // nested scheme: (E_s, T_s, sum q^2) of every section of THIS shard, indexed by [step & 1][GLOBAL section number]; published
     // here by the owner and polled by the peers.  Two parities: a rank may already publish step t + 1 while a slow peer is still
     // collecting step t (it cannot get to t + 2 before that peer has published t + 1, i.e. is done with t)
@@ -307,11 +309,14 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
                 }
             } else {   // parents are global ids: read them where they live (a peer's HBM over NVLink)
 #pragma unroll
+                unsigned int n_remote = 0;
                 for (int v = 0; v < V; ++v) {
                     const unsigned int g = (unsigned int)par[v];
                     const unsigned int r = peer_owner(a.peer, g);
+                    n_remote += r != (unsigned int)a.peer.rank ? 1u : 0u;
                     load_particle<Real, D>(reinterpret_cast<const Real*>(a.peer.state[a.cur][r]), (size_t)(g - r * a.peer.n_loc), x[v]);
                 }
+                atomicAdd(&a.stats->nvlink_bytes, (unsigned long long)(n_remote * D * sizeof(Real)));   // (rare branch: shard edges only)
             }
         } else if (MODE != EXT_INIT) {
             load_particles<Real, V, D>(a.state_in, base, x);

@@ -833,3 +833,63 @@ def test_hmm_uploaded_observations_are_validated():
         with pytest.raises(m.MplError):
             f.upload_observations(np.array(bad))
     f.upload_observations(np.array(HMM3["obs"], float)[:, None])
+
+
+# ------------------------------------------------------------------------------------------------- islands (local-resample variant)
+def test_virtual_islands_estimate_is_consistent_with_kalman():
+    # G islands that never need an island-level resampling: log mean exp of G independent filters' estimates
+    from modppl_b200.distributed import VirtualIslands, island_seed
+    T, n, G = 60, 1 << 20, 4
+    ys = lgssm_data(T)
+    truth = O.kalman_lml_lgssm4(0.1, 0.5, 1.0, ys)
+    isl = VirtualIslands(m.lgssm4(), n, G, seed=5, dtype="f32")
+    isl.upload_observations(ys)
+    isl.run(0, T, m.SYSTEMATIC_NESTED, exchange_every=20)
+    est = isl.log_marginal_likelihood_estimate()
+    singles = []
+    for g in range(G):                                   # each island is exactly a plain filter with the island's seed
+        f = m.ParticleSystem(m.lgssm4(), n // G, seed=island_seed(5, g), dtype="f32")
+        f.upload_observations(ys); f.run(0, T, m.SYSTEMATIC_NESTED)
+        singles.append(f.log_marginal_likelihood_estimate())
+    if isl.n_island_resamplings == 0:
+        mx = max(singles)
+        assert abs(est - (mx + math.log(np.mean(np.exp(np.array(singles) - mx))))) < 1e-9
+    assert abs(est - truth) < 0.5
+    isl.close()
+
+
+def test_virtual_islands_resample_islands_and_stay_unbiased():
+    # tiny islands degenerate quickly: island-level resamplings happen, copies are exact, and the likelihood estimate stays
+    # unbiased: mean over seeds of exp(estimate - truth) is 1 within 4 standard errors
+    from modppl_b200.distributed import VirtualIslands
+    T, G, n_loc = 12, 8, 128
+    ys = lgssm_data(T)
+    truth = O.kalman_lml_lgssm4(0.1, 0.5, 1.0, ys)
+    ratios, n_ex = [], 0
+    for seed in range(120):
+        isl = VirtualIslands(m.lgssm4(), G * n_loc, G, seed=seed, dtype="f64")
+        isl.upload_observations(ys)
+        isl.run(0, T, m.SYSTEMATIC_FIXED, exchange_every=2)
+        ratios.append(math.exp(isl.log_marginal_likelihood_estimate() - truth))
+        n_ex += isl.n_island_resamplings
+        isl.close()
+    ratios = np.array(ratios)
+    assert n_ex > 0
+    se = ratios.std(ddof=1) / math.sqrt(len(ratios))
+    assert abs(ratios.mean() - 1.0) <= 4.0 * se + 0.02, (ratios.mean(), se, n_ex)
+
+
+def test_island_copy_is_exact():
+    T = 4
+    ys = lgssm_data(T)
+    a = m.ParticleSystem(m.lgssm4(), 5000, seed=1, dtype="f32")
+    b = m.ParticleSystem(m.lgssm4(), 5000, seed=2, dtype="f32")
+    for f in (a, b):
+        f.init_step(ys[0]); f.resample(m.SYSTEMATIC_NESTED); f.step(ys[1]); f.resample(m.SYSTEMATIC_NESTED)
+    from modppl_b200._lib import lib, check
+    check(lib.mpl_ps_copy_state(b._h, a._h))              # b := a (a's pending resample is applied first)
+    assert np.array_equal(a.traces, b.traces) and np.all(b.log_weights == 0.0)
+    lml_b = b.log_marginal_likelihood_estimate()
+    b.step(ys[2]); b.resample(m.SYSTEMATIC_NESTED)        # b continues with its own random numbers and its own running log-ML
+    assert np.isfinite(b.log_marginal_likelihood_estimate()) and b.log_marginal_likelihood_estimate() != lml_b
+    assert not np.array_equal(a.traces, b.traces)
