@@ -201,6 +201,9 @@ int mpl_ps_island_attach(mpl_ps*, int rank, int n_islands, const void* blobs /* 
 int mpl_ps_live_buffer(mpl_ps*, int* out);                 /* which state buffer is live (a pending resample is applied first) */
 int mpl_ps_island_copy_from(mpl_ps*, int src_island, int src_live_buffer);   /* this island := a copy of island src (uniform weights) */
 int mpl_ps_copy_state(mpl_ps* dst, mpl_ps* src);           /* the same between two particle systems of one process */
+/* Test hook: the nested scheme computes level 1 (the first output slot of every chunk) in a plan pass of its own for large shards
+ * and inside the expansion for shards of at most 2^22 particles (-1, the default); 0 / 1 force one or the other.  Same results. */
+int mpl_test_set_inline_level1(int mode);
 /* Test hook: `world` shards emulated on ONE GPU run the multi-GPU kernels phase by phase (remote loads/stores become
  * local).  init + resample, then steps with a resample after each except the last; outputs the final state
  * double[D * n_global] (SoA), log-weights double[n_global] and the log-ML estimate. */

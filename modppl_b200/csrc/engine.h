@@ -86,7 +86,7 @@ struct mpl_ps {
     int rank, world;
     mpl::PeerTable peer;
     mpl::Mailbox* mailbox;            // device memory of this rank, written by every rank
-    void* ipc_opened[8][mpl::kMaxPeers];   // pointers obtained from cudaIpcOpenMemHandle (to close on detach)
+    void* ipc_opened[9][mpl::kMaxPeers];   // pointers obtained from cudaIpcOpenMemHandle (to close on detach)
     bool peer_virtual;                // peers live in this process (single-GPU emulation used by the tests)
     // islands (local resampling; multi_gpu.cu): the other islands' state buffers, for the occasional island-level resampling
     int n_islands, island_rank;

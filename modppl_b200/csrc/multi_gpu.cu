@@ -17,13 +17,13 @@
 using namespace mpl;
 
 namespace {
-constexpr int kPeerHandles = 8;
+constexpr int kPeerHandles = 9;
 struct PeerBlob {   // must fit MPL_PEER_BLOB_BYTES
-    cudaIpcMemHandle_t h[kPeerHandles];   // state0, state1, anc, mailbox, lw pair, chunk-record pairs (e, S): 8 x 64 bytes
+    cudaIpcMemHandle_t h[kPeerHandles];   // state0, state1, anc, mailbox, lw pair, chunk-record pairs (e, S), tile-prefix pair: 9 x 64 bytes
 };
 void* const* peer_buffers(mpl_ps* ps, void* (&out)[kPeerHandles]) {
     out[0] = ps->state[0]; out[1] = ps->state[1]; out[2] = ps->anc; out[3] = ps->mailbox;
-    out[4] = ps->par == 0 ? ps->lw : ps->lw_alt; out[5] = ps->par == 0 ? ps->lw_alt : ps->lw; out[6] = ps->rec_e2; out[7] = ps->rec_S2;
+    out[4] = ps->par == 0 ? ps->lw : ps->lw_alt; out[5] = ps->par == 0 ? ps->lw_alt : ps->lw; out[6] = ps->rec_e2; out[7] = ps->rec_S2; out[8] = ps->nest_tile_pre;
     return out;
 }
 // fills rank h's column of the peer table from its 8 buffers (own pointers or IPC-mapped ones)
@@ -31,7 +31,11 @@ void set_peer_column(mpl_ps* ps, PeerTable& t, int h, void* const* b) {
     const size_t nch = ps->ld / kChunk;
     t.state[0][h] = b[0]; t.state[1][h] = b[1]; t.anc[h] = (int32_t*)b[2]; t.mail[h] = (Mailbox*)b[3];
     t.lw[0][h] = b[4]; t.lw[1][h] = b[5];
-    for (int p = 0; p < 2; ++p) { t.rec_e[p][h] = (const int*)b[6] + (size_t)p * nch; t.rec_S[p][h] = (const unsigned int*)b[7] + (size_t)p * nch; }
+    const size_t n_tp = ((ps->ld + kSection - 1) / kSection) * kTilesPerSection;
+    for (int p = 0; p < 2; ++p) {
+        t.rec_e[p][h] = (const int*)b[6] + (size_t)p * nch; t.rec_S[p][h] = (const unsigned int*)b[7] + (size_t)p * nch;
+        t.tile_pre[p][h] = (const unsigned long long*)b[8] + (size_t)p * n_tp;
+    }
 }
 // the second log-weight buffer and the chunk records exist before anything is exported (sharded runs alternate them)
 int ensure_pairs(mpl_ps* ps) {
@@ -142,7 +146,7 @@ extern "C" int mpl_ps_peer_detach(mpl_ps* ps) {
     void* bufs[kPeerHandles];
     PeerTable t = ps->peer;
     set_peer_column(ps, t, 0, peer_buffers(ps, bufs));   // back to one GPU: the self-table of ensure_chunk_records
-    for (int p = 0; p < 2; ++p) { t.lw[p][0] = ps->lw; t.rec_e[p][0] = ps->rec_e; t.rec_S[p][0] = ps->rec_S; }
+    for (int p = 0; p < 2; ++p) { t.lw[p][0] = ps->lw; t.rec_e[p][0] = ps->rec_e; t.rec_S[p][0] = ps->rec_S; t.tile_pre[p][0] = ps->nest_tile_pre + (size_t)ps->par * (((ps->ld + kSection - 1) / kSection) * kTilesPerSection); }
     t.n_loc = (unsigned int)ps->n;
     ps->peer = t;
     return MPL_OK;

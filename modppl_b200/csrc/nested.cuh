@@ -575,13 +575,60 @@ __device__ __forceinline__ void nested_pass_range(unsigned long long out_base, u
 // integer weights); every warp computes the offspring counts of its 512 particles and expands them into the ancestor slots
 // that fall into the shard's range.  PULL: several GPUs.
 struct NestedHeavyEntry { unsigned int wt; };
+// Level 1 without a plan pass (small shards, where a kernel boundary costs more than the arithmetic): the warp derives the slot
+// starts of its own 4 chunks from the section pass' tile prefix -- lane <-> chunk of the 32-chunk tile, exactly the arithmetic of
+// the plan pass, hence the same numbers.  Lanes 0..4 return P[4 wt .. 4 wt + 4].
 template <typename Real, bool PULL>
-__device__ __forceinline__ void nested_expand_warp_tile(const FixedArgs<Real>& a, const NestedPrefixes& nb, DeviceStats* st, unsigned short* head, unsigned int wt,
-                                                        unsigned int n_chunks_global, const unsigned int (&q)[4][4], const unsigned int (&excl)[4], unsigned int S_w,
-                                                        NestedHeavyEntry* heavy) {
+__device__ __forceinline__ unsigned int nested_inline_level1(const FixedArgs<Real>& a, const NestedPrefixes& nb, const ChunkRecords& rec_own, int par, unsigned int wt,
+                                                            unsigned int n_chunks_global, unsigned long long word) {
     const int lane = threadIdx.x & 31;
-    const unsigned int c_w = 4u * wt + (unsigned int)min(lane, 4);
-    const unsigned int P_w = c_w <= n_chunks_global ? nb.P[c_w] : (unsigned int)a.n_out;   // lanes 0..4: the slot starts of the warp's 4 chunks
+    const unsigned int tile_g = wt / (kScanThreads / 32), sg = tile_g / kTilesPerSection;
+    if (sg >= nb.n_sec_global) return (unsigned int)a.n_out;
+    const unsigned long long n_s = nb.sec_n[sg], a_s = nb.sec_a[sg], T_s = nb.sec_T[sg];
+    if (n_s == 0ull || T_s == 0ull) return (unsigned int)a_s;   // no slot in this section: every chunk "starts" at the section's first slot
+    const int E_s = nb.sec_E[sg];
+    const unsigned int c = tile_g * kChunksPerTile + lane;   // global chunk of this lane
+    unsigned int c_loc = c, t_loc = tile_g;
+    const int* rec_e = rec_own.e;
+    const unsigned int* rec_S = rec_own.S;
+    const unsigned long long* tile_pre = nb.tile_pre;
+    if constexpr (PULL) {
+        const unsigned int owner = peer_owner(a.peer, tile_g * (unsigned int)kScanTile);
+        c_loc = c - owner * (a.peer.n_loc / (unsigned int)kChunk);
+        t_loc = tile_g - owner * (a.peer.n_loc / (unsigned int)kScanTile);
+        rec_e = a.peer.rec_e[par][owner]; rec_S = a.peer.rec_S[par][owner]; tile_pre = a.peer.tile_pre[par][owner];
+        if (lane == 0 && owner != (unsigned int)a.peer.rank) atomicAdd(&a.stats->nvlink_bytes, 8ull * kChunksPerTile + 8ull);
+    }
+    const bool valid = c < n_chunks_global;
+    unsigned long long g = nested_shift(valid ? rec_S[c_loc] : 0u, valid ? rec_e[c_loc] : kChunkEmpty, E_s);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, g, o); if (lane >= o) g += up; }
+    const double inv_t = 1. / (double)T_s;
+    const TileBase base = tile_base_exact(tile_pre[t_loc], T_s, nested_section_offset(word, sg, T_s), n_s, inv_t);
+    const unsigned int slot_end = local_count(g, base.rem, (double)base.rem, T_s, (double)n_s, n_s, inv_t);   // slots of the tile up to and including chunk `lane`
+    const unsigned int j = (wt % (kScanThreads / 32)) * 4u + (unsigned int)min(lane, 4);   // lanes 0..4: chunk j of the tile (32: one past its end)
+    const unsigned int prev = __shfl_sync(0xffffffffu, slot_end, (int)max(j, 1u) - 1);
+    return (unsigned int)(a_s + base.n_start) + (j == 0u ? 0u : prev);
+}
+
+// several GPUs, no plan pass: the tiles of chunks (whole sections) that own slots of this shard's range
+__device__ __forceinline__ void nested_tile_range_sections(const NestedPrefixes& nb, unsigned long long w0, unsigned long long w_end, unsigned int& tg_lo, unsigned int& tg_hi) {
+    const int lane = threadIdx.x & 31;
+    unsigned int lo = 0xffffffffu, hi = 0u;
+    for (unsigned int s = lane; s < nb.n_sec_global; s += 32) {
+        const unsigned long long a_s = nb.sec_a[s], n_s = nb.sec_n[s];
+        if (n_s != 0ull && a_s < w_end && a_s + n_s > w0) { lo = min(lo, s); hi = max(hi, s); }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if (lo == 0xffffffffu) { tg_lo = 1u; tg_hi = 0u; return; }   // (no slot at all: cannot happen while W > 0)
+    tg_lo = lo * kTilesPerSection; tg_hi = hi * kTilesPerSection + (kTilesPerSection - 1);
+}
+
+template <typename Real, bool PULL>
+__device__ __forceinline__ void nested_expand_warp_tile(const FixedArgs<Real>& a, DeviceStats* st, unsigned short* head, unsigned int wt, unsigned int P_w /* lanes 0..4: slot starts */,
+                                                        const unsigned int (&q)[4][4], const unsigned int (&excl)[4], unsigned int S_w, NestedHeavyEntry* heavy) {
+    const int lane = threadIdx.x & 31;
     unsigned int n[4][4], ws;
     const unsigned int total = nested_warp_tile_counts(wt, P_w, S_w, st->rand_word, q, excl, n, ws);
     unsigned int lo = 0, hi = total;
@@ -602,8 +649,17 @@ __device__ __forceinline__ void nested_expand_warp_tile(const FixedArgs<Real>& a
             warp_expand_chunk<Real, kNestedWarpSlots, false, PULL>(a, head, n, 0u, total, chunk_lo, (unsigned long long)ws, src0);
 }
 
+// lanes 0..4: the slot starts of warp tile wt's 4 chunks (and one past) -- from the plan pass' array, or derived on the spot
+template <typename Real, bool PULL>
+__device__ __forceinline__ unsigned int nested_slot_starts(const FixedArgs<Real>& a, const NestedPrefixes& nb, const ChunkRecords& rec_own, int par, unsigned int wt,
+                                                          unsigned int n_chunks_global, unsigned long long word) {
+    if (a.inline_level1) return nested_inline_level1<Real, PULL>(a, nb, rec_own, par, wt, n_chunks_global, word);
+    const unsigned int c_w = 4u * wt + (unsigned int)min((int)(threadIdx.x & 31), 4);
+    return c_w <= n_chunks_global ? nb.P[c_w] : (unsigned int)a.n_out;
+}
+
 template <typename Real, bool RECOMPUTE, bool PULL>
-__global__ void __launch_bounds__(kScanThreads, PULL ? 3 : 4) nested_expand_kernel(FixedArgs<Real> a, NestedPrefixes nb, const int* rec_e_own, int par, unsigned int n_tiles_local,
+__global__ void __launch_bounds__(kScanThreads, PULL ? 3 : 4) nested_expand_kernel(FixedArgs<Real> a, NestedPrefixes nb, ChunkRecords rec_own, int par, unsigned int n_tiles_local,
                                                                                    unsigned int n_tiles_global, unsigned int n_chunks_global, NestedHeavyEntry* heavy) {
     __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -613,27 +669,39 @@ __global__ void __launch_bounds__(kScanThreads, PULL ? 3 : 4) nested_expand_kern
     // grid is only released once every block of the two small passes in between is past its own dependency wait -- so they are
     // complete and visible already: load them (and do the warp-local scans) before waiting for the plan pass' slot ranges.
     if constexpr (!PULL) {
-        nested_load_warp_tile<Real, RECOMPUTE, false>(a, rec_e_own, par, blockIdx.x * (kScanThreads / 32) + warp, n_chunks_global, q);
+        nested_load_warp_tile<Real, RECOMPUTE, false>(a, rec_own.e, par, blockIdx.x * (kScanThreads / 32) + warp, n_chunks_global, q);
         chunk_exclusive_prefixes(q, excl, S_w);
     }
     pdl_wait();
     pdl_trigger();
     if (blockIdx.x == 0 && tid == 0) st->trace[11] = global_ns();
-    if (a.dynamic && !st->do_resample) return;   // ESS above the threshold (the plan pass cleared the step's flag)
-    if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the plan pass)
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    if (a.dynamic && !st->do_resample) {   // ESS above the threshold: keep the population, weights keep accumulating
+        if (a.inline_level1 && blockIdx.x == 0 && tid == 0) st->resampled_flag[epoch & 1] = 0;   // (else the plan pass did)
+        return;
+    }
+    if (a.inline_level1 && blockIdx.x == 0 && tid == 0) nested_bookkeeping(a, st, epoch);   // (else the plan pass did)
+    if (st->W == 0ull) {   // degenerate: every weight is -inf (or NaN): identity ancestors (flagged by the bookkeeping)
         for (size_t i = (size_t)blockIdx.x * kScanThreads + tid; i < a.n; i += (size_t)gridDim.x * kScanThreads) a.anc[i] = a.src_base + (int32_t)i;
         return;
     }
+    const unsigned long long word = st->rand_word;
     if constexpr (!PULL) {
-        nested_expand_warp_tile<Real, false>(a, nb, st, head[warp], blockIdx.x * (kScanThreads / 32) + warp, n_chunks_global, q, excl, S_w, heavy);
+        const unsigned int wt = blockIdx.x * (kScanThreads / 32) + warp;
+        nested_expand_warp_tile<Real, false>(a, st, head[warp], wt, nested_slot_starts<Real, false>(a, nb, rec_own, par, wt, n_chunks_global, word), q, excl, S_w, heavy);
     } else {
         unsigned int tg_lo, tg_hi;
-        nested_tile_range(nb, a.out_base, n_tiles_local, n_tiles_global, tg_lo, tg_hi);
+        if (a.inline_level1) nested_tile_range_sections(nb, a.out_base, a.out_base + a.n_out_local, tg_lo, tg_hi);
+        else nested_tile_range(nb, a.out_base, n_tiles_local, n_tiles_global, tg_lo, tg_hi);
         for (unsigned int tg = tg_lo + blockIdx.x; tg <= tg_hi; tg += gridDim.x) {
             const unsigned int wt = tg * (kScanThreads / 32) + warp;
-            nested_load_warp_tile<Real, RECOMPUTE, true>(a, rec_e_own, par, wt, n_chunks_global, q);
+            nested_load_warp_tile<Real, RECOMPUTE, true>(a, rec_own.e, par, wt, n_chunks_global, q);   // (in flight while the slot starts are worked out)
+            const unsigned int P_w = nested_slot_starts<Real, true>(a, nb, rec_own, par, wt, n_chunks_global, word);
+            // (whole sections are walked when there is no plan pass: most tiles of an edge section own none of this shard's slots)
+            const unsigned int p_first = __shfl_sync(0xffffffffu, P_w, 0), p_last = __shfl_sync(0xffffffffu, P_w, 4);
+            if (p_last <= a.out_base || p_first >= a.out_base + a.n_out_local || p_last == p_first) continue;
             chunk_exclusive_prefixes(q, excl, S_w);
-            nested_expand_warp_tile<Real, true>(a, nb, st, head[warp], wt, n_chunks_global, q, excl, S_w, heavy);
+            nested_expand_warp_tile<Real, true>(a, st, head[warp], wt, P_w, q, excl, S_w, heavy);
         }
     }
     if (tid == 0 && atomicAdd(&st->ticket, 1u) == gridDim.x - 1) { st->ticket = 0; st->trace[8] = global_ns(); }   // (time stamp of the last block; diagnostics)
@@ -642,7 +710,7 @@ __global__ void __launch_bounds__(kScanThreads, PULL ? 3 : 4) nested_expand_kern
 // ---- heavy warp tiles: every warp of the grid recomputes the tile's counts (512 particles) and expands its share of the passes.
 // Launched only once a heavy tile has been seen (host-mapped flag), like the single-level scheme's overflow pass.
 template <typename Real, bool RECOMPUTE, bool PULL>
-__global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Real> a, NestedPrefixes nb, const int* rec_e_own, int par, unsigned int n_chunks_global,
+__global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Real> a, NestedPrefixes nb, ChunkRecords rec_own, int par, unsigned int n_chunks_global,
                                                                     const NestedHeavyEntry* heavy) {
     __shared__ __align__(16) unsigned short head[kScanThreads / 32][kNestedWarpSlots];
     DeviceStats* st = a.stats;
@@ -656,10 +724,9 @@ __global__ void __launch_bounds__(kScanThreads) nested_heavy_kernel(FixedArgs<Re
     for (unsigned int k = 0; k < count; ++k) {
         const unsigned int wt = heavy[k].wt;
         unsigned int q[4][4], excl[4], S_w = 0u, n[4][4], ws;
-        nested_load_warp_tile<Real, RECOMPUTE, PULL>(a, rec_e_own, par, wt, n_chunks_global, q);
+        nested_load_warp_tile<Real, RECOMPUTE, PULL>(a, rec_own.e, par, wt, n_chunks_global, q);
         chunk_exclusive_prefixes(q, excl, S_w);
-        const unsigned int c_w = 4u * wt + (unsigned int)min(lane, 4);
-        const unsigned int P_w = c_w <= n_chunks_global ? nb.P[c_w] : (unsigned int)a.n_out;
+        const unsigned int P_w = nested_slot_starts<Real, PULL>(a, nb, rec_own, par, wt, n_chunks_global, st->rand_word);
         const unsigned int total = nested_warp_tile_counts(wt, P_w, S_w, st->rand_word, q, excl, n, ws);
         unsigned int lo = 0, hi = total;
         if constexpr (PULL) nested_pass_range(a.out_base, a.n_out_local, ws, total, lo, hi);

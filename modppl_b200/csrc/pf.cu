@@ -73,6 +73,7 @@ template <typename Real> Hmm<Real> make_hmm(const mpl_model& m) {
 
 // ---- launches with programmatic stream serialisation (the kernels call pdl_wait() first thing) -------------------
 static bool g_use_pdl = getenv("MPL_NO_PDL") == nullptr;
+static int g_inline_level1 = -1;   // nested scheme: -1 = by shard size, 0 = always a plan pass, 1 = never (mpl_test_set_inline_level1)
 template <typename... KArgs, typename... Args>
 static cudaError_t pdl_launch(void (*kernel)(KArgs...), unsigned int grid, unsigned int block, cudaStream_t stream, Args... args) {
     cudaLaunchConfig_t cfg;
@@ -293,6 +294,7 @@ static FixedArgs<Real> fixed_args(mpl_ps* ps, bool dynamic, bool dev_t) {
     a.rt = dev_t ? -1 : ps->t - 1;
     a.accumulate_lml = 1;
     a.dynamic = dynamic ? 1 : 0;
+    a.inline_level1 = 0;
     return a;
 }
 
@@ -357,13 +359,13 @@ int ensure_chunk_records(mpl_ps* ps) {
     MPL_CUDA_OK(cudaMalloc(&ps->nest_sec, (size_t)kMaxSections * 7 * sizeof(unsigned long long)));
     MPL_CUDA_OK(cudaMemset(ps->nest_sec, 0, (size_t)kMaxSections * 7 * sizeof(unsigned long long)));
     const size_t nsec = (ps->ld + kSection - 1) / kSection;
-    MPL_CUDA_OK(cudaMalloc(&ps->nest_tile_pre, nsec * kTilesPerSection * sizeof(unsigned long long)));
+    MPL_CUDA_OK(cudaMalloc(&ps->nest_tile_pre, 2 * nsec * kTilesPerSection * sizeof(unsigned long long)));   // (a pair, like the chunk records)
     // plan of the WHOLE population (a shard plans the sections whose slots it fills, wherever their particles live)
     const size_t nch_g = (ps->n_global + kChunk - 1) / kChunk, nt_g = (ps->n_global + kScanTile - 1) / kScanTile;
     MPL_CUDA_OK(cudaMalloc(&ps->nest_P, (nch_g + 2) * sizeof(unsigned int)));
     MPL_CUDA_OK(cudaMalloc(&ps->nest_F, (nt_g + 1) * sizeof(unsigned int)));
     if (ps->world <= 1) {   // one GPU: the "peer" tables point at this system's own arrays (kernels use one code path)
-        for (int p = 0; p < 2; ++p) { ps->peer.lw[p][0] = ps->lw; ps->peer.rec_e[p][0] = ps->rec_e2; ps->peer.rec_S[p][0] = ps->rec_S2; }
+        for (int p = 0; p < 2; ++p) { ps->peer.lw[p][0] = ps->lw; ps->peer.rec_e[p][0] = ps->rec_e2; ps->peer.rec_S[p][0] = ps->rec_S2; ps->peer.tile_pre[p][0] = ps->nest_tile_pre; }
         ps->peer.n_loc = (unsigned int)ps->n;
     }
     return MPL_OK;
@@ -372,7 +374,8 @@ int ensure_chunk_records(mpl_ps* ps) {
 static NestedPrefixes make_prefixes(mpl_ps* ps) {
     unsigned long long* sec = ps->nest_sec;
     const size_t n_sec_global = (ps->n_global + kSection - 1) / kSection;
-    return NestedPrefixes{ps->nest_tile_pre, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
+    const size_t n_tp = ((ps->ld + kSection - 1) / kSection) * kTilesPerSection;
+    return NestedPrefixes{ps->nest_tile_pre + (size_t)ps->par * n_tp, (int*)sec, sec + kMaxSections, (double*)(sec + 2 * kMaxSections), sec + 3 * kMaxSections, sec + 4 * kMaxSections,
                           sec + 5 * kMaxSections, sec + 6 * kMaxSections, ps->nest_P, ps->nest_F,
                           (unsigned int)(ps->gid_offset / kSection), (unsigned int)((ps->n + kSection - 1) / kSection), (unsigned int)n_sec_global};
 }
@@ -389,6 +392,8 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     if (n_sec_global > (size_t)kMaxSections) return fail(MPL_ERR_UNSUPPORTED, "nested scheme: at most 2^28 particles");
     FixedArgs<Real> a = fixed_args<Real>(ps, dynamic, false);
     a.overflow_follows = ps->host_flags[0] != 0 ? 1 : 0;   // the heavy-tile pass runs only once a heavy warp tile has been seen
+    // small shards: a kernel boundary costs more than level 1 recomputed by every warp of the expansion -- no plan pass
+    a.inline_level1 = g_inline_level1 >= 0 ? g_inline_level1 : (ps->n <= ((size_t)1 << 22) ? 1 : 0);
     const bool post = (phases & 2) && !dynamic && !ps->in_device_loop;   // the call-per-step API polls the result in mapped host memory
     if (post) { ps->host_seq += 1; if (ps->host_seq == 0) ps->host_seq = 1; }
     a.host_seq = post ? ps->host_seq : 0u;
@@ -411,7 +416,7 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
         else if (phases == 1) pdl_launch(nested_sections_kernel<Real, 1>, nb.n_sec, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
         else pdl_launch(nested_sections_kernel<Real, 2>, 1, kScanThreads, ps->stream, a, rec, nb, num_tiles, num_chunks);
     }
-    if (phases & 2) {
+    if ((phases & 2) && !a.inline_level1) {
         ScopedLaunch sl(ps, "nested_plan");
         pdl_launch(nested_plan_kernel<Real>, (unsigned int)n_sec_global, kScanThreads, ps->stream, a, nb, ps->par, n_chunks_global);
     }
@@ -419,23 +424,23 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
         ScopedLaunch sl(ps, "nested_expand");
         NestedHeavyEntry* hv = (NestedHeavyEntry*)ps->overflow;
         if (ps->world > 1) {   // the chunks that own this shard's slots: about its own tiles, one more at each edge, more when the weights are lopsided (grid-stride)
-            const unsigned int grid = num_tiles + 2;
-            if (dynamic) pdl_launch(nested_expand_kernel<Real, true, true>, grid, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
-            else pdl_launch(nested_expand_kernel<Real, false, true>, grid, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
+            const unsigned int grid = num_tiles + (a.inline_level1 ? 2u * kTilesPerSection : 2u);
+            if (dynamic) pdl_launch(nested_expand_kernel<Real, true, true>, grid, kScanThreads, ps->stream, a, nb, rec, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
+            else pdl_launch(nested_expand_kernel<Real, false, true>, grid, kScanThreads, ps->stream, a, nb, rec, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
         } else {
-            if (dynamic) pdl_launch(nested_expand_kernel<Real, true, false>, num_tiles, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
-            else pdl_launch(nested_expand_kernel<Real, false, false>, num_tiles, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
+            if (dynamic) pdl_launch(nested_expand_kernel<Real, true, false>, num_tiles, kScanThreads, ps->stream, a, nb, rec, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
+            else pdl_launch(nested_expand_kernel<Real, false, false>, num_tiles, kScanThreads, ps->stream, a, nb, rec, ps->par, num_tiles, n_tiles_global, n_chunks_global, hv);
         }
     }
     if ((phases & 2) && a.overflow_follows) {
         ScopedLaunch sl(ps, "nested_heavy");
         const NestedHeavyEntry* hv = (const NestedHeavyEntry*)ps->overflow;
         if (ps->world > 1) {
-            if (dynamic) pdl_launch(nested_heavy_kernel<Real, true, true>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, n_chunks_global, hv);
-            else pdl_launch(nested_heavy_kernel<Real, false, true>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, n_chunks_global, hv);
+            if (dynamic) pdl_launch(nested_heavy_kernel<Real, true, true>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, rec, ps->par, n_chunks_global, hv);
+            else pdl_launch(nested_heavy_kernel<Real, false, true>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, rec, ps->par, n_chunks_global, hv);
         } else {
-            if (dynamic) pdl_launch(nested_heavy_kernel<Real, true, false>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, n_chunks_global, hv);
-            else pdl_launch(nested_heavy_kernel<Real, false, false>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, (const int*)ps->rec_e, ps->par, n_chunks_global, hv);
+            if (dynamic) pdl_launch(nested_heavy_kernel<Real, true, false>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, rec, ps->par, n_chunks_global, hv);
+            else pdl_launch(nested_heavy_kernel<Real, false, false>, kNumSMs * 2, kScanThreads, ps->stream, a, nb, rec, ps->par, n_chunks_global, hv);
         }
     }
     MPL_CUDA_OK(cudaGetLastError());
@@ -1135,6 +1140,12 @@ extern "C" int mpl_ps_run(mpl_ps* ps, size_t first_step, size_t n_steps, int sch
         ps->hist_broken = ps->hist_cap != 0;   // which steps resampled is only known on the device
     }
     return rc;
+}
+
+extern "C" int mpl_test_set_inline_level1(int mode) {
+    if (mode < -1 || mode > 1) return fail(MPL_ERR_INVALID, "mode: -1 (by shard size), 0, 1");
+    g_inline_level1 = mode;
+    return MPL_OK;
 }
 
 extern "C" int mpl_ps_num_resamples(mpl_ps* ps, uint64_t* out) {

@@ -91,6 +91,7 @@ struct PeerTable {
     const void* lw[2][kMaxPeers];
     const int* rec_e[2][kMaxPeers];
     const unsigned int* rec_S[2][kMaxPeers];
+    const unsigned long long* tile_pre[2][kMaxPeers];   // per tile of 32 chunks: exclusive prefix of the chunk masses inside its section (section pass)
 };
 __device__ __forceinline__ unsigned int peer_owner(const PeerTable& p, unsigned int gid) { return p.shift >= 0 ? gid >> p.shift : gid / p.n_loc; }
 
@@ -490,6 +491,7 @@ struct FixedArgs {
                               // same buffer carry the log total weight of this resample to the host (tagged with host_seq)
     unsigned int host_seq;    // tag of this resample call (nested scheme: the host polls the mapped words instead of synchronising)
     double* sq_partials;      // per tile: sum of (q * 2^-k)^2, for ESS = W^2 / sum q^2
+    int inline_level1;        // nested scheme, small shards: no plan pass -- every warp of the expansion derives its chunks' slot starts itself
 };
 template <typename Real>
 __device__ __forceinline__ float fixed_max(const FixedArgs<Real>& a) {

@@ -61,3 +61,8 @@ def virtual_shards(model, n_global, world, obs, dtype="f32", seed=0, scheme=2):
                                       st.ctypes.data_as(_lib.c_double_p), lw.ctypes.data_as(_lib.c_double_p), C.byref(lml), C.byref(ms)))
     virtual_shards.last_loop_ms = ms.value
     return st, lw, lml.value
+
+
+def set_inline_level1(mode):
+    """test hook (include/modppl_b200.h: mpl_test_set_inline_level1): -1 by shard size, 0 plan pass, 1 inside the expansion"""
+    check(lib.mpl_test_set_inline_level1(int(mode)))

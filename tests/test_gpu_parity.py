@@ -542,11 +542,16 @@ def test_nested_systematic_bit_exact(n):
         lw = lw.astype(np.float32)
         if not np.isfinite(lw).any():
             lw[0] = 0.0
-        anc, lse, W = m.parity.fixed_resample(lw, scheme=4, seed=77, t=5)
         ref_anc, ref_lse, ref_W = O.nested_systematic(lw, O.resample_offset_word(77, 5))
-        assert W == ref_W, name
-        assert np.array_equal(anc, ref_anc), (name, np.nonzero(anc != ref_anc)[0][:5])
-        assert abs(lse - ref_lse) <= 1e-12 * max(1.0, abs(ref_lse))
+        for mode in (0, 1):   # level 1 in a plan pass of its own (large shards) / inside the expansion (small shards): the same ancestors
+            m.parity.set_inline_level1(mode)
+            try:
+                anc, lse, W = m.parity.fixed_resample(lw, scheme=4, seed=77, t=5)
+            finally:
+                m.parity.set_inline_level1(-1)
+            assert W == ref_W, (name, mode)
+            assert np.array_equal(anc, ref_anc), (name, mode, np.nonzero(anc != ref_anc)[0][:5])
+            assert abs(lse - ref_lse) <= 1e-12 * max(1.0, abs(ref_lse))
 
 
 def test_nested_systematic_full_size_properties():
@@ -602,13 +607,18 @@ def test_nested_fused_epilogue_equals_standalone_quantisation():
     # (truth check of this scheme at benchmark-like sizes: test_benchmarked_schemes_vs_kalman_within_mc_error)
 
 
+@pytest.mark.parametrize("inline_level1", [0, 1])
 @pytest.mark.parametrize("world,dtype", [(2, "f32"), (4, "f32"), (8, "f32"), (2, "f64"), (4, "f64")])
-def test_virtual_shards_nested_scheme_reproduces_single_gpu(world, dtype):
+def test_virtual_shards_nested_scheme_reproduces_single_gpu(world, dtype, inline_level1):
     # the nested scheme's only exchange is one record per 2^17-particle section; sections are groups of global ids, so
     # the sharded run (fused quantisation in the extend kernel for f32) equals the unsharded one bit for bit
     n, T = (1 << 20) if world == 8 else (1 << 19), 5
     ys = lgssm_data(T)
-    st, lw, lml = m.parity.virtual_shards(m.lgssm4(), n, world, ys, dtype=dtype, seed=29, scheme=m.SYSTEMATIC_NESTED)
+    m.parity.set_inline_level1(inline_level1)     # shards: plan pass over the sections that own their slots / no plan pass at all
+    try:
+        st, lw, lml = m.parity.virtual_shards(m.lgssm4(), n, world, ys, dtype=dtype, seed=29, scheme=m.SYSTEMATIC_NESTED)
+    finally:
+        m.parity.set_inline_level1(-1)
     one = m.ParticleSystem(m.lgssm4(), n, seed=29, dtype=dtype)
     one.init_step(ys[0]); one.resample(m.SYSTEMATIC_NESTED)
     for t in range(1, T):
