@@ -70,6 +70,21 @@ int mpl_device_count(int* count);
  *   {xs...} (tests/dyngenfns/hierarchical.rs:32-46); "pointed" {xmin,xmax,ymin,ymax, cov[4]}
  *   (tests/pointed_model/model.rs). */
 mpl_model* mpl_model_create(const char* name, const double* params, size_t n_params);
+/* Model front-end (stands in for the `dyngen!` macro + DynUnfold, modppl-macros/src/lib.rs:20-114, dynunfold.rs:41-100): an Unfold
+ * model in the restricted vectorisable form written as a JSON spec --
+ *   {"name", "state_dim", "obs_dim", "params": {name: value, ...},
+ *    "init":    [one sample statement per state component, drawn at t = 0],
+ *    "step":    [one per component, drawn at t > 0 from the previous state],
+ *    "observe": [observation terms scored on the new state]}
+ * sample statement: {"dist": "normal" | "uniform" | "delta", "args": [..], "add_to": expr (optional: an increment)};
+ * observation term: {"dist": "normal" | "uniform" | "bernoulli", "value": expr, "args": [..]}, {"dist": "mvnormal2", "value": [2],
+ * "mean": [2], "cov": [4]}, {"dist": "expr", "value": log-density}.  Expressions are C++ expressions over x[i] (state), y[i]
+ * (observation), t and the parameter names.  The spec becomes a device functor compiled by NVRTC against the library's own kernel
+ * headers on first use (or by mpl_model_jit_compile): the model then runs through the same kernels as the built-in ones, without
+ * rebuilding the library.  NULL on a malformed spec (mpl_last_error()). */
+mpl_model* mpl_model_compile(const char* spec_json);
+int mpl_model_jit_compile(mpl_model*, int dtype, char* log, size_t log_bytes);   /* compile now (no device needed); log: compiler messages */
+const char* mpl_model_jit_source(const mpl_model*, int dtype);                   /* the generated translation unit, for inspection */
 void mpl_model_destroy(mpl_model*);
 int mpl_model_state_dim(const mpl_model*);
 int mpl_model_obs_dim(const mpl_model*);

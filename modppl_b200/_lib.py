@@ -58,6 +58,9 @@ SYMBOLS = {
     "mpl_version": (C.c_char_p,),
     "mpl_device_count": (C.c_int, C.POINTER(C.c_int)),
     "mpl_model_create": (C.c_void_p, C.c_char_p, c_double_p, C.c_size_t),
+    "mpl_model_compile": (C.c_void_p, C.c_char_p),
+    "mpl_model_jit_compile": (C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t),
+    "mpl_model_jit_source": (C.c_char_p, C.c_void_p, C.c_int),
     "mpl_model_destroy": (None, C.c_void_p),
     "mpl_model_state_dim": (C.c_int, C.c_void_p),
     "mpl_model_obs_dim": (C.c_int, C.c_void_p),

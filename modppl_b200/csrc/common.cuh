@@ -1,18 +1,33 @@
 // common.cuh -- shared device helpers: error handling, Philox4x32-10, uniform/normal transforms, reductions.
 // sm_100a only.
 #pragma once
+#ifdef __CUDACC_RTC__
+// compiled at run time by NVRTC (csrc/jit.cu: the kernel headers are embedded in the library and a model spec becomes one more
+// functor): no host headers there, only what device code needs
+typedef unsigned char uint8_t;
+typedef unsigned short uint16_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#define INFINITY __int_as_float(0x7f800000)
+#define NAN __int_as_float(0x7fffffff)
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
 #include <string>
+#endif
 
 namespace mpl {
 
+#ifndef __CUDACC_RTC__
 // ------------------------------------------------------------------------------------------------
 // error plumbing (thread-local message behind mpl_last_error())
 // ------------------------------------------------------------------------------------------------
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
+#endif
 
 #define MPL_CUDA_OK(expr)                                                                                     \
     do {                                                                                                      \
@@ -354,7 +369,7 @@ __device__ __forceinline__ uint64_t fixed_weight(float d, int kbits, float* qf =
     if (qf) *qf = v;
     return __float2ull_rn(v);                                // round-to-nearest-even to an integer
 }
-inline int fixed_kbits(uint64_t n_total) {
+__host__ __device__ inline int fixed_kbits(uint64_t n_total) {
     int lg = 0;
     while (((uint64_t)1 << lg) < n_total) ++lg;
     int k = 62 - lg;

@@ -2,16 +2,20 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/modppl_b200.h"
 #include "pf_kernels.cuh"
+
+namespace mpl { struct JitProgram; }
 
 struct mpl_model {
     int kind;
     std::string name;
     std::vector<double> params;
     int state_dim, obs_dim, num_latents;
+    std::shared_ptr<mpl::JitProgram> jit;   // M_JIT: the compiled spec (shared by the copies particle systems keep)
 };
 
 namespace mpl {
@@ -102,6 +106,8 @@ int ps_phase_reduce(mpl_ps* ps);
 int ps_phase_scan(mpl_ps* ps);
 int ensure_chunk_records(mpl_ps* ps);
 int materialise(mpl_ps* ps);   // apply a pending ancestor gather
+// jit.cu: launches pf_extend_kernel<JitModel<Real>, Real, mode, sharded, nested> of a model compiled from a spec
+int jit_launch_extend(const mpl_model& m, int dtype, int mode, bool sharded, int nested, const void* extend_args, unsigned int grid, unsigned int block, cudaStream_t stream, bool pdl);
 // categorical.rs:25-30: the sequential f64 running sum of `probs`, bit for bit (parallel emulation for long inputs); ps may be null
 int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, cudaStream_t stream);
 }

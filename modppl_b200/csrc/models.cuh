@@ -13,7 +13,8 @@ struct Obs {
     double v[4];
 };
 
-enum ModelKind : int { M_LGSSM4 = 0, M_SPIRAL = 1, M_SV = 2, M_HMM = 3, M_LINE = 10, M_HIER = 11, M_POINTED = 12 };
+enum ModelKind : int { M_LGSSM4 = 0, M_SPIRAL = 1, M_SV = 2, M_HMM = 3, M_LINE = 10, M_HIER = 11, M_POINTED = 12,
+                       M_JIT = 20 /* an Unfold model compiled from a spec at run time (jit.cu) */ };
 
 // ---- config 4: 4-D constant-velocity linear-Gaussian tracker, two independent `normal` observations -----------
 template <typename Real>
@@ -49,7 +50,6 @@ struct Spiral {
     static constexpr bool kGroupDraws = false;
     Real dr_std, dth_mean, dth_std;
     double prec[4], log_norm;   // mvnormal.rs:14-22 with det/inverse hoisted (quirk Q8)
-    Real inv_var, log_norm_r;
     __device__ __forceinline__ Real kernel(int64_t t, const Stream& s, Real (&x)[D], const Obs& obs) const {
         if (t == 0) {
             Real u[2];
@@ -62,17 +62,9 @@ struct Spiral {
             x[0] = x[0] + (z[0] * dr_std + (Real)0.);                     // normal.rs:26
             x[1] = x[1] + (z[1] * dth_std + dth_mean);
         }
-        if (sizeof(Real) == 8) {
-            double sn, cs;
-            sincos((double)x[1], &sn, &cs);
-            return (Real)mvnormal2_logpdf(obs.v[0], obs.v[1], (double)x[0] * cs, (double)x[0] * sn, prec, log_norm);
-        } else {
-            float sn, cs;
-            sincosf((float)x[1], &sn, &cs);
-            Real c0 = (Real)obs.v[0] - x[0] * (Real)cs, c1 = (Real)obs.v[1] - x[0] * (Real)sn;
-            Real mahal = c0 * c0 * inv_var + c1 * c1 * inv_var;
-            return -(log_norm_r + mahal) / 2;
-        }
+        // mvnormal.rs:14-22 in double for both precisions (det / inverse hoisted, quirk Q8) -- the form a run-time spec of this model
+        // compiles to as well (jit.cu), so the two agree to the last bit
+        return (Real)mvnormal2_logpdf((double)(Real)obs.v[0], (double)(Real)obs.v[1], (double)(x[0] * cos(x[1])), (double)(x[0] * sin(x[1])), prec, log_norm);
     }
 };
 

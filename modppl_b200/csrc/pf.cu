@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include "engine.h"
 #include "cumsum_exact.cuh"
 
@@ -47,8 +48,6 @@ template <typename Real> Spiral<Real> make_spiral(const mpl_model& m) {
     double det = ov * ov - 0. * 0.;
     f.prec[0] = ov / det; f.prec[1] = -0. / det; f.prec[2] = -0. / det; f.prec[3] = ov / det;
     f.log_norm = 2. * std::log(2. * kPi) + std::log(det);
-    f.inv_var = (Real)(1. / ov);
-    f.log_norm_r = (Real)(2. * std::log(2. * kPi) + std::log(ov * ov));
     return f;
 }
 template <typename Real> StochVol<Real> make_sv(const mpl_model& m) {
@@ -124,8 +123,8 @@ static int grid_for(size_t work_items, int per_block, int max_blocks) {
 }
 
 // ---- extend dispatch ----------------------------------------------------------------------------------------
-template <class Model, typename Real>
-static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& obs, bool from_dev_obs, bool dev_t, int nested = 0) {
+template <typename Real>
+static ExtendArgs<Real> build_extend_args(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs, bool dev_t) {
     ExtendArgs<Real> a;
     a.state_in = (const Real*)ps->state[ps->cur];
     a.state_out = (Real*)ps->state[mode == EXT_INIT || mode == EXT_ACCUM ? ps->cur : ps->cur ^ 1];
@@ -147,47 +146,61 @@ static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& 
     a.rec = ChunkRecords{ps->rec_e, ps->rec_S, ps->rec_sq};
     a.kbits = fixed_kbits(ps->n_global);
     if (mode == EXT_DYNAMIC) a.state_out = (Real*)ps->state[ps->cur ^ 1];
-    if (mode == EXT_INIT) MPL_CUDA_OK(cudaMemsetAsync(ps->stats->max_bits, 0, sizeof(ps->stats->max_bits), ps->stream));
+    return a;
+}
+
+// which instantiation pf_extend_kernel<Model, Real, MODE, SHARDED, NESTED> a call maps to.  NESTED (fp32): the kernel's epilogue
+// quantises each chunk (1: the integer weights replace the log-weights; 2: chunk records only, ESS-triggered loop).
+static void extend_variant(const mpl_ps* ps, int mode, int nested, bool f32, bool& sharded, int& k_nested) {
+    k_nested = 0;
+    if (f32 && nested == 1 && (mode == EXT_INIT || mode == EXT_GATHER)) k_nested = 1;
+    if (f32 && nested == 2 && (mode == EXT_INIT || mode == EXT_DYNAMIC)) k_nested = 2;
+    sharded = ps->world > 1 && (mode == EXT_GATHER || mode == EXT_DYNAMIC);
+}
+
+template <class Model, typename Real, int NESTED>
+static void launch_extend_kernel(mpl_ps* ps, const Model& model, const ExtendArgs<Real>& a, int mode, bool sharded) {
     const int grid = ps->grid_extend;
+    switch (mode) {
+        case EXT_INIT: pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false, NESTED>, grid, kExtendThreads, ps->stream, a, model); break;
+        case EXT_ACCUM: if constexpr (NESTED == 0) pdl_launch(pf_extend_kernel<Model, Real, EXT_ACCUM, false, 0>, grid, kExtendThreads, ps->stream, a, model); break;
+        case EXT_GATHER:
+            if constexpr (NESTED != 2) {
+                if (sharded) pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, true, NESTED>, grid, kExtendThreads, ps->stream, a, model);
+                else pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, false, NESTED>, grid, kExtendThreads, ps->stream, a, model);
+            }
+            break;
+        default:
+            if constexpr (NESTED != 1) {
+                if (sharded) pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, true, NESTED>, grid, kExtendThreads, ps->stream, a, model);
+                else pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, false, NESTED>, grid, kExtendThreads, ps->stream, a, model);
+            }
+            break;
+    }
+}
+
+// Model == void*: a model compiled from a spec at run time (jit.cu) -- the same kernel template, instantiated by NVRTC
+template <class Model, typename Real>
+static int launch_extend_t(mpl_ps* ps, const Model& model, int mode, const Obs& obs, bool from_dev_obs, bool dev_t, int nested = 0) {
+    ExtendArgs<Real> a = build_extend_args<Real>(ps, mode, obs, from_dev_obs, dev_t);
+    bool sharded;
+    int k_nested;
+    extend_variant(ps, mode, nested, sizeof(Real) == 4, sharded, k_nested);
+    if (mode == EXT_INIT) MPL_CUDA_OK(cudaMemsetAsync(ps->stats->max_bits, 0, sizeof(ps->stats->max_bits), ps->stream));
     {
         ScopedLaunch sl(ps, mode == EXT_INIT ? "init" : "extend");
-        if constexpr (sizeof(Real) == 4) {
-            if (nested == 1 && (mode == EXT_INIT || mode == EXT_GATHER)) {   // fused per-chunk quantisation (nested scheme, device-resident loop)
-                if (mode == EXT_INIT) pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false, 1>, grid, kExtendThreads, ps->stream, a, model);
-                else if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, true, 1>, grid, kExtendThreads, ps->stream, a, model);
-                else pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, false, 1>, grid, kExtendThreads, ps->stream, a, model);
-                MPL_CUDA_OK(cudaGetLastError());
-                if (mode == EXT_GATHER) ps->cur ^= 1;
-                ps->prequantised = 1;
-                goto extend_done;
-            }
-            if (nested == 2 && (mode == EXT_INIT || mode == EXT_DYNAMIC)) {   // chunk records only; the log-weights stay (ESS-triggered loop)
-                if (mode == EXT_INIT) pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false, 2>, grid, kExtendThreads, ps->stream, a, model);
-                else if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, true, 2>, grid, kExtendThreads, ps->stream, a, model);
-                else pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, false, 2>, grid, kExtendThreads, ps->stream, a, model);
-                MPL_CUDA_OK(cudaGetLastError());
-                if (mode == EXT_DYNAMIC) ps->cur ^= 1;
-                ps->prequantised = 2;
-                goto extend_done;
-            }
-        }
-        switch (mode) {
-            case EXT_INIT: pdl_launch(pf_extend_kernel<Model, Real, EXT_INIT, false>, grid, kExtendThreads, ps->stream, a, model); break;
-            case EXT_ACCUM: pdl_launch(pf_extend_kernel<Model, Real, EXT_ACCUM, false>, grid, kExtendThreads, ps->stream, a, model); break;
-            case EXT_GATHER:
-                if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, true>, grid, kExtendThreads, ps->stream, a, model);
-                else pdl_launch(pf_extend_kernel<Model, Real, EXT_GATHER, false>, grid, kExtendThreads, ps->stream, a, model);
-                break;
-            default:
-                if (ps->world > 1) pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, true>, grid, kExtendThreads, ps->stream, a, model);
-                else pdl_launch(pf_extend_kernel<Model, Real, EXT_DYNAMIC, false>, grid, kExtendThreads, ps->stream, a, model);
-                break;
-        }
+        if constexpr (std::is_same<Model, const mpl_model*>::value) {
+            int rc = jit_launch_extend(*model, ps->dtype, mode, sharded, k_nested, &a, (unsigned int)ps->grid_extend, kExtendThreads, ps->stream, g_use_pdl);
+            if (rc) return rc;
+        } else if constexpr (sizeof(Real) == 4) {
+            if (k_nested == 1) launch_extend_kernel<Model, Real, 1>(ps, model, a, mode, sharded);
+            else if (k_nested == 2) launch_extend_kernel<Model, Real, 2>(ps, model, a, mode, sharded);
+            else launch_extend_kernel<Model, Real, 0>(ps, model, a, mode, sharded);
+        } else launch_extend_kernel<Model, Real, 0>(ps, model, a, mode, sharded);
     }
     MPL_CUDA_OK(cudaGetLastError());
     if (mode == EXT_GATHER || mode == EXT_DYNAMIC) ps->cur ^= 1;
-    ps->prequantised = 0;
-extend_done:
+    ps->prequantised = k_nested;
     if (ps->hist_cap) {   // trajectory log: the state this step produced (kernel time index ps->t, not yet incremented by the caller)
         const size_t tt = (size_t)ps->t;
         if (tt < ps->hist_cap) {
@@ -208,6 +221,7 @@ static int launch_extend(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs
             case M_SPIRAL: return launch_extend_t<Spiral<float>, float>(ps, make_spiral<float>(m), mode, obs, from_dev_obs, dev_t, nested);
             case M_SV: return launch_extend_t<StochVol<float>, float>(ps, make_sv<float>(m), mode, obs, from_dev_obs, dev_t, nested);
             case M_HMM: return launch_extend_t<Hmm<float>, float>(ps, make_hmm<float>(m), mode, obs, from_dev_obs, dev_t, nested);
+            case M_JIT: return launch_extend_t<const mpl_model*, float>(ps, &ps->model, mode, obs, from_dev_obs, dev_t, nested);
         }
     } else {
         switch (m.kind) {
@@ -215,6 +229,7 @@ static int launch_extend(mpl_ps* ps, int mode, const Obs& obs, bool from_dev_obs
             case M_SPIRAL: return launch_extend_t<Spiral<double>, double>(ps, make_spiral<double>(m), mode, obs, from_dev_obs, dev_t);
             case M_SV: return launch_extend_t<StochVol<double>, double>(ps, make_sv<double>(m), mode, obs, from_dev_obs, dev_t);
             case M_HMM: return launch_extend_t<Hmm<double>, double>(ps, make_hmm<double>(m), mode, obs, from_dev_obs, dev_t);
+            case M_JIT: return launch_extend_t<const mpl_model*, double>(ps, &ps->model, mode, obs, from_dev_obs, dev_t);
         }
     }
     return fail(MPL_ERR_INVALID, "model is not an Unfold model");

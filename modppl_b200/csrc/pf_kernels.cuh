@@ -13,7 +13,6 @@
 //                        running sum, bit-exact.
 //   gather_kernel        K6 stand-alone (only when the host reads state right after a resample).
 #pragma once
-#include <type_traits>
 #include "common.cuh"
 #include "models.cuh"
 #include "nested_quant.cuh"
@@ -140,6 +139,9 @@ __device__ __forceinline__ double from_ordered_bits(unsigned long long u) {
     return __longlong_as_double((long long)((u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u));
 }
 
+template <int V> struct AncVecOf;
+template <> struct AncVecOf<4> { typedef int4 type; };
+template <> struct AncVecOf<2> { typedef int2 type; };
 template <typename Real> struct VecOf;
 template <> struct VecOf<float> { typedef float4 type; static constexpr int N = 4; };
 template <> struct VecOf<double> { typedef double2 type; static constexpr int N = 2; };
@@ -278,7 +280,7 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
     Real run_max = (Real)-INFINITY;
     if (blockIdx.x == 0 && tid == 0) { a.stats->max_bits[(t + 1) & 1] = 0ull; a.stats->trace[13] = global_ns(); }   // slot of the next step (its last reader finished before this launch)
     const size_t stride = (size_t)gridDim.x * kExtendThreads * V;
-    typedef typename std::conditional<V == 4, int4, int2>::type AncVec;
+    typedef typename AncVecOf<V>::type AncVec;
     size_t base = ((size_t)blockIdx.x * kExtendThreads + tid) * V;
     AncVec anc_next = AncVec();
     if (gather && base < a.ld) anc_next = __ldcs(reinterpret_cast<const AncVec*>(a.anc + base));
@@ -309,8 +311,8 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
                     load_particle_ro<Real, D>(a.state_in, src, x[v]);
                 }
             } else {   // parents are global ids: read them where they live (a peer's HBM over NVLink)
-#pragma unroll
                 unsigned int n_remote = 0;
+#pragma unroll
                 for (int v = 0; v < V; ++v) {
                     const unsigned int g = (unsigned int)par[v];
                     const unsigned int r = peer_owner(a.peer, g);

@@ -38,6 +38,51 @@ class Model:
             lib.mpl_model_destroy(h)
 
 
+class CompiledModel(Model):
+    """An Unfold model written as a declarative spec (dict or JSON string; include/modppl_b200.h: mpl_model_compile) -- the
+    stand-in for authoring with `dyngen!` (modppl-macros/src/lib.rs:20-114).  NVRTC compiles it against the library's own kernel
+    headers on first use; `compile(dtype)` does it right away and returns the compiler's log."""
+
+    def __init__(self, spec):
+        import json
+        self.spec = spec if isinstance(spec, str) else json.dumps(spec)
+        self.name = "compiled"
+        self.params = np.zeros(0)
+        self._h = check_handle(lib.mpl_model_compile(self.spec.encode()))
+
+    def compile(self, dtype="f32"):
+        log = C.create_string_buffer(1 << 16)
+        rc = lib.mpl_model_jit_compile(self._h, 0 if dtype in ("f32", 0) else 1, log, len(log))
+        if rc != 0:
+            raise _lib.MplError(rc, _lib.last_error())
+        return log.value.decode()
+
+    def source(self, dtype="f32"):
+        return lib.mpl_model_jit_source(self._h, 0 if dtype in ("f32", 0) else 1).decode()
+
+
+def compile_model(spec):
+    return CompiledModel(spec)
+
+
+def lgssm4_spec(q_std=0.1, r_std=0.5, x0_std=1.0):
+    """config 4's model written in the spec language; compiles to the arithmetic of the built-in functor"""
+    return {"name": "lgssm4_spec", "state_dim": 4, "obs_dim": 2, "params": {"q": q_std, "r": r_std, "x0": x0_std},
+            "init": [{"dist": "normal", "args": ["0", "x0"]}] * 4,
+            "step": [{"dist": "normal", "args": ["x[0] + x[2]", "q"]}, {"dist": "normal", "args": ["x[1] + x[3]", "q"]},
+                     {"dist": "normal", "args": ["x[2]", "q"]}, {"dist": "normal", "args": ["x[3]", "q"]}],
+            "observe": [{"dist": "normal", "value": "y[0]", "args": ["x[0]", "r"]}, {"dist": "normal", "value": "y[1]", "args": ["x[1]", "r"]}]}
+
+
+def spiral_spec(dr_std=0.1, dtheta_mean=0.4, dtheta_std=0.2, obs_var=0.001):
+    """tests/dyngenfns/unfold.rs:14-33 written in the spec language"""
+    return {"name": "spiral_spec", "state_dim": 2, "obs_dim": 2,
+            "params": {"dr_std": dr_std, "dth_mean": dtheta_mean, "dth_std": dtheta_std, "ov": obs_var, "two_pi": 2.0 * np.pi},
+            "init": [{"dist": "uniform", "args": ["0", "1"]}, {"dist": "uniform", "args": ["0", "two_pi"]}],
+            "step": [{"dist": "normal", "args": ["0", "dr_std"], "add_to": "x[0]"}, {"dist": "normal", "args": ["dth_mean", "dth_std"], "add_to": "x[1]"}],
+            "observe": [{"dist": "mvnormal2", "value": ["y[0]", "y[1]"], "mean": ["x[0] * cos(x[1])", "x[0] * sin(x[1])"], "cov": ["ov", "0", "0", "ov"]}]}
+
+
 def lgssm4(q_std=0.1, r_std=0.5, x0_std=1.0):
     return Model("lgssm4", [q_std, r_std, x0_std])
 

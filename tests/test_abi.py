@@ -62,3 +62,37 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in text and "libmodppl_oracle" not in text and "modppl_oracle.h" not in text, f
+
+
+# ------------------------------------------------------------------------------------------------- model front-end (no device needed)
+def test_model_spec_compiles_with_nvrtc_without_a_device():
+    """a declarative spec becomes a device functor; NVRTC compiles it against the library's embedded kernel headers
+    (sm_100a cubin) -- which needs no GPU, so the whole front-end up to the module load is checked here."""
+    import modppl_b200 as m
+    for spec in (m.lgssm4_spec(), m.spiral_spec()):
+        mod = m.compile_model(spec)
+        assert mod.state_dim == spec["state_dim"] and mod.obs_dim == spec["obs_dim"]
+        src = mod.source("f32")
+        assert "struct JitModel" in src and '#include "pf_kernels.cuh"' in src
+        for dtype in ("f32", "f64"):
+            log = mod.compile(dtype)          # raises with the compiler's messages if the generated functor does not compile
+            assert "error" not in log.lower()
+
+
+def test_model_spec_errors_are_reported():
+    import modppl_b200 as m
+    bad = [
+        "not json",
+        {"state_dim": 2, "obs_dim": 1},                                                            # no sample statements
+        {"state_dim": 1, "obs_dim": 1, "init": [{"dist": "poisson", "args": ["1", "2"]}], "step": [{"dist": "delta", "args": ["x[0]"]}]},
+        {"state_dim": 1, "obs_dim": 1, "params": {"x": 1.0}, "init": [{"dist": "delta", "args": ["0"]}], "step": [{"dist": "delta", "args": ["x[0]"]}]},   # reserved name
+        {"state_dim": 1, "obs_dim": 1, "init": [{"dist": "delta", "args": ["0; return 1"]}], "step": [{"dist": "delta", "args": ["x[0]"]}]},  # not an expression
+    ]
+    for spec in bad:
+        with pytest.raises(m.MplError):
+            m.compile_model(spec)
+    # well-formed JSON whose expression does not compile: reported with the compiler's message when it is compiled
+    mod = m.compile_model({"state_dim": 1, "obs_dim": 1, "init": [{"dist": "delta", "args": ["0"]}], "step": [{"dist": "delta", "args": ["undefined_name + x[0]"]}]})
+    with pytest.raises(m.MplError) as e:
+        mod.compile("f64")
+    assert "undefined_name" in str(e.value)

@@ -903,3 +903,70 @@ def test_island_copy_is_exact():
     b.step(ys[2]); b.resample(m.SYSTEMATIC_NESTED)        # b continues with its own random numbers and its own running log-ML
     assert np.isfinite(b.log_marginal_likelihood_estimate()) and b.log_marginal_likelihood_estimate() != lml_b
     assert not np.array_equal(a.traces, b.traces)
+
+
+# ------------------------------------------------------------------------------------------------- model front-end
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_compiled_spec_of_lgssm4_reproduces_the_builtin_functor_bit_for_bit(dtype):
+    # the spec goes through NVRTC against the library's embedded kernel headers: same kernels, same arithmetic, same bits
+    T, n = 8, 70000
+    ys = lgssm_data(T)
+    a = m.ParticleSystem(m.lgssm4(), n, seed=12, dtype=dtype)
+    b = m.ParticleSystem(m.compile_model(m.lgssm4_spec()), n, seed=12, dtype=dtype)
+    for f in (a, b):
+        f.init_step(ys[0])
+    assert np.array_equal(a.traces, b.traces) and np.array_equal(a.log_weights, b.log_weights)
+    for f in (a, b):
+        f.step(ys[1])                                   # weights accumulate (EXT_ACCUM)
+    assert np.array_equal(a.traces, b.traces) and np.array_equal(a.log_weights, b.log_weights)
+    for f in (a, b):
+        f.resample(m.SYSTEMATIC_NESTED)
+        for y in ys[2:5]:
+            f.step_resample(y, m.SYSTEMATIC_NESTED)     # gather fused into the extend (fp32: and the quantisation epilogue)
+    assert np.array_equal(a.parents, b.parents) and np.array_equal(a.traces, b.traces)
+    assert a.log_marginal_likelihood_estimate() == b.log_marginal_likelihood_estimate()
+    # device-resident loop, ESS-triggered (EXT_DYNAMIC)
+    c = m.ParticleSystem(m.lgssm4(), n, seed=13, dtype=dtype)
+    d = m.ParticleSystem(m.compile_model(m.lgssm4_spec()), n, seed=13, dtype=dtype)
+    for f in (c, d):
+        f.upload_observations(ys)
+        f.run(0, T, m.SYSTEMATIC_NESTED if dtype == "f32" else m.SYSTEMATIC_FIXED, ess_threshold=0.5)
+    assert c.num_resamples() == d.num_resamples() and np.array_equal(c.traces, d.traces)
+    assert c.log_marginal_likelihood_estimate() == d.log_marginal_likelihood_estimate()
+
+
+def test_compiled_spec_of_the_spiral_model_matches_the_builtin_and_the_oracle():      # tests/dyngenfns/unfold.rs:14-33 as a spec
+    T, n = 6, 4000
+    th = 2 * math.pi * np.arange(T) / T + 0.7
+    ys = np.stack([0.4 * np.cos(th), 0.4 * np.sin(th)], 1)
+    a = m.ParticleSystem(m.spiral_model(), n, seed=3, dtype="f64")
+    b = m.ParticleSystem(m.compile_model(m.spiral_spec()), n, seed=3, dtype="f64")
+    r = O.OraclePS("spiral", [0.1, 0.4, 0.2, 0.001], n, dtype="f64", seed=3)
+    a.init_step(ys[0]); b.init_step(ys[0]); r.init_step(ys[0])
+    assert np.array_equal(a.traces, b.traces) and np.array_equal(a.log_weights, b.log_weights)
+    assert rel(b.traces, r.traces) <= 1e-9 and rel(b.log_weights, r.log_weights) <= 1e-9
+    for f in (a, b):
+        f.write_state(r.traces); f.write_log_weights(r.log_weights)
+        f.step(ys[1])
+    r.step(ys[1])
+    assert np.array_equal(a.traces, b.traces) and np.array_equal(a.log_weights, b.log_weights)
+    assert rel(b.traces, r.traces) <= 1e-9 and rel(b.log_weights, r.log_weights) <= 1e-9
+
+
+def test_compiled_spec_of_a_model_outside_the_registry():
+    # stochastic volatility written as a spec (the built-in functor shares one Philox block between 4 particles, a spec draws per
+    # particle: other random numbers, the same model) -- the two log-ML estimates agree within Monte Carlo error
+    T, n = 40, 1 << 18
+    ys = np.random.default_rng(5).normal(size=(T, 1)) * 0.6
+    spec = {"name": "sv_spec", "state_dim": 1, "obs_dim": 1, "params": {"mu": -1.024, "phi": 0.9702, "sig": 0.178, "sd0": 0.178 / math.sqrt(1 - 0.9702 ** 2)},
+            "init": [{"dist": "normal", "args": ["mu", "sd0"]}],
+            "step": [{"dist": "normal", "args": ["mu + phi * (x[0] - mu)", "sig"]}],
+            "observe": [{"dist": "normal", "value": "y[0]", "args": ["0", "exp(x[0] / 2)"]}]}
+    model = m.compile_model(spec)
+    est = []
+    for f in (m.ParticleSystem(m.stochastic_volatility(), n, seed=1, dtype="f32"), m.ParticleSystem(model, n, seed=1, dtype="f32"),
+              m.ParticleSystem(model, n, seed=2, dtype="f64")):
+        f.upload_observations(ys)
+        f.run(0, T, m.SYSTEMATIC_FIXED, ess_threshold=0.5)
+        est.append(f.log_marginal_likelihood_estimate())
+    assert abs(est[1] - est[0]) < 0.05 and abs(est[2] - est[0]) < 0.05, est
