@@ -718,7 +718,8 @@ def run_config2(args):
             "e2e": {"value": out["line"]["proposals_per_s_all_traces_to_host"], "unit": "proposals/s", "h2d_bytes_per_step": 88, "d2h_bytes_per_step": (L + 1) * n * 8 + 8,
                     "note": "importance_sampling as the reference returns it: every latent and normalised log-weight copied to the host; `value` returns the log-ML estimate only"},
             "gpu_launches": 3 * batches, "clocks": clocks,
-            "roofline": dict({"bound": "fp64 pipe / issue (register-resident: one thread per proposal, 11 observation log-densities each)", "peak": None, "traffic": None},
+            "roofline": dict({"bound": "issue slots (register-resident, fp64: one thread per proposal, 11 observation log-densities each; not an HBM path)", "peak": 100.0, "traffic": None,
+                              "note": "achieved = issue-slot utilisation of is_kernel under ncu (provenance: profiles/ncu_constants.json); the batch also runs weight_reduce (fp64 exp per weight) and the normalisation"},
                              **consts.get("is_kernel", {})),
             "cpu_baseline": cpu_baseline_config2()}
     print(json.dumps(line))
@@ -749,7 +750,7 @@ def run_config3(args):
             "e2e": {"value": value, "unit": "chain-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 8,
                     "note": "chains live in HBM between calls by design (like the reference's traces live in the caller's memory); one launch runs all sweeps, the accept count comes back"},
             "gpu_launches": 1, "clocks": clocks,
-            "roofline": dict({"bound": "fp64 pipe / issue (register-resident: one chain per thread, fused propose / score / accept)", "peak": None, "traffic": None},
+            "roofline": dict({"bound": "issue slots (register-resident, fp64: one chain per thread, fused propose / score / accept; not an HBM path)", "peak": 100.0, "traffic": None},
                              **consts.get("mh_sweep_kernel", {})),
             "cpu_baseline": cpu_baseline_config3()}
     print(json.dumps(line))
