@@ -217,7 +217,8 @@ int mpl_ps_live_buffer(mpl_ps*, int* out);                 /* which state buffer
 int mpl_ps_island_copy_from(mpl_ps*, int src_island, int src_live_buffer);   /* this island := a copy of island src (uniform weights) */
 int mpl_ps_copy_state(mpl_ps* dst, mpl_ps* src);           /* the same between two particle systems of one process */
 /* Test hook: the nested scheme computes level 1 (the first output slot of every chunk) in a plan pass of its own for large shards
- * and inside the expansion for shards of at most 2^22 particles (-1, the default); 0 / 1 force one or the other.  Same results. */
+ * and inside the expansion for an unsharded population of at most 2^22 particles (-1, the default); 0 / 1 force one or the other, also
+ * for shards.  Same results. */
 int mpl_test_set_inline_level1(int mode);
 /* Test hook: `world` shards emulated on ONE GPU run the multi-GPU kernels phase by phase (remote loads/stores become
  * local).  init + resample, then steps with a resample after each except the last; outputs the final state

@@ -502,7 +502,11 @@ __device__ __forceinline__ void nested_load_warp_tile(const FixedArgs<Real>& a, 
         }
         if (idx < n_own) {   // (chunks are quantised whole: entries past n inside the last chunk hold 0)
             if constexpr (sizeof(Real) == 4) {
-                const uint4 v = *reinterpret_cast<const uint4*>(lw + idx);   // the integers' bit patterns
+                // the integers' bit patterns; last use of an array that is read once: evict-first, so that it does not push the
+                // ancestors this kernel writes (the next extend reads them) out of L2.  (A peer's memory: a plain load.)
+                uint4 v;
+                if constexpr (PULL) v = *reinterpret_cast<const uint4*>(lw + idx);
+                else v = __ldcs(reinterpret_cast<const uint4*>(lw + idx));
                 q[r][0] = v.x; q[r][1] = v.y; q[r][2] = v.z; q[r][3] = v.w;
             } else {
                 const double2 u = *reinterpret_cast<const double2*>(lw + idx), v = *reinterpret_cast<const double2*>(lw + idx + 2);
@@ -578,14 +582,18 @@ struct NestedHeavyEntry { unsigned int wt; };
 // Level 1 without a plan pass (small shards, where a kernel boundary costs more than the arithmetic): the warp derives the slot
 // starts of its own 4 chunks from the section pass' tile prefix -- lane <-> chunk of the 32-chunk tile, exactly the arithmetic of
 // the plan pass, hence the same numbers.  Lanes 0..4 return P[4 wt .. 4 wt + 4].
+// one warp, lane <-> chunk of the 32-chunk tile `tile_g` (global): returns the tile's first slot in `start` and, per lane, the
+// number of the tile's slots up to and including that lane's chunk.  false: the tile's section owns no slot (start = its a_s).
 template <typename Real, bool PULL>
-__device__ __forceinline__ unsigned int nested_inline_level1(const FixedArgs<Real>& a, const NestedPrefixes& nb, const ChunkRecords& rec_own, int par, unsigned int wt,
-                                                            unsigned int n_chunks_global, unsigned long long word) {
+__device__ __forceinline__ bool nested_tile_slot_ends(const FixedArgs<Real>& a, const NestedPrefixes& nb, const ChunkRecords& rec_own, int par, unsigned int tile_g,
+                                                      unsigned int n_chunks_global, unsigned long long word, unsigned int& start, unsigned int& slot_end) {
     const int lane = threadIdx.x & 31;
-    const unsigned int tile_g = wt / (kScanThreads / 32), sg = tile_g / kTilesPerSection;
-    if (sg >= nb.n_sec_global) return (unsigned int)a.n_out;
+    const unsigned int sg = tile_g / kTilesPerSection;
+    slot_end = 0u;
+    if (sg >= nb.n_sec_global) { start = (unsigned int)a.n_out; return false; }
     const unsigned long long n_s = nb.sec_n[sg], a_s = nb.sec_a[sg], T_s = nb.sec_T[sg];
-    if (n_s == 0ull || T_s == 0ull) return (unsigned int)a_s;   // no slot in this section: every chunk "starts" at the section's first slot
+    start = (unsigned int)a_s;
+    if (n_s == 0ull || T_s == 0ull) return false;   // no slot in this section: every chunk "starts" at the section's first slot
     const int E_s = nb.sec_E[sg];
     const unsigned int c = tile_g * kChunksPerTile + lane;   // global chunk of this lane
     unsigned int c_loc = c, t_loc = tile_g;
@@ -605,10 +613,47 @@ __device__ __forceinline__ unsigned int nested_inline_level1(const FixedArgs<Rea
     for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, g, o); if (lane >= o) g += up; }
     const double inv_t = 1. / (double)T_s;
     const TileBase base = tile_base_exact(tile_pre[t_loc], T_s, nested_section_offset(word, sg, T_s), n_s, inv_t);
-    const unsigned int slot_end = local_count(g, base.rem, (double)base.rem, T_s, (double)n_s, n_s, inv_t);   // slots of the tile up to and including chunk `lane`
+    slot_end = local_count(g, base.rem, (double)base.rem, T_s, (double)n_s, n_s, inv_t);
+    start = (unsigned int)(a_s + base.n_start);
+    return true;
+}
+
+// Level 1 without a plan pass (small populations, where a kernel boundary costs more than the arithmetic): the warp derives the
+// slot starts of its own 4 chunks from the section pass' tile prefix -- exactly the arithmetic of the plan pass, hence the same
+// numbers.  Lanes 0..4 return P[4 wt .. 4 wt + 4].
+template <typename Real, bool PULL>
+__device__ __forceinline__ unsigned int nested_inline_level1(const FixedArgs<Real>& a, const NestedPrefixes& nb, const ChunkRecords& rec_own, int par, unsigned int wt,
+                                                            unsigned int n_chunks_global, unsigned long long word) {
+    const int lane = threadIdx.x & 31;
+    unsigned int start, slot_end;
+    nested_tile_slot_ends<Real, PULL>(a, nb, rec_own, par, wt / (kScanThreads / 32), n_chunks_global, word, start, slot_end);
     const unsigned int j = (wt % (kScanThreads / 32)) * 4u + (unsigned int)min(lane, 4);   // lanes 0..4: chunk j of the tile (32: one past its end)
     const unsigned int prev = __shfl_sync(0xffffffffu, slot_end, (int)max(j, 1u) - 1);
-    return (unsigned int)(a_s + base.n_start) + (j == 0u ? 0u : prev);
+    return start + (j == 0u ? 0u : prev);
+}
+
+// ---- level-1 pass of a single GPU: one warp per tile of 32 chunks writes their slot starts (the plan pass above does the same
+// for the sections a SHARD needs, wherever their particles live, and also finds the chunk range that owns the shard's slots)
+template <typename Real>
+__global__ void __launch_bounds__(kScanThreads) nested_level1_kernel(FixedArgs<Real> a, NestedPrefixes nb, ChunkRecords rec, unsigned int num_tiles, unsigned int n_chunks_global) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DeviceStats* st = a.stats;
+    pdl_wait();
+    pdl_trigger();   // the expansion may become resident and load its weights
+    const long long epoch = a.epoch < 0 ? st->t : a.epoch;
+    if (a.dynamic && !st->do_resample) {   // ESS above the threshold: keep the population, weights keep accumulating
+        if (blockIdx.x == 0 && tid == 0) st->resampled_flag[epoch & 1] = 0;
+        return;
+    }
+    if (blockIdx.x == 0 && tid == 0) { st->trace[10] = global_ns(); nested_bookkeeping(a, st, epoch); }
+    const unsigned int tile = blockIdx.x * (kScanThreads / 32) + warp;
+    if (tile >= num_tiles || st->W == 0ull) return;
+    unsigned int start, slot_end;
+    nested_tile_slot_ends<Real, false>(a, nb, rec, 0, tile, n_chunks_global, st->rand_word, start, slot_end);
+    const unsigned int c = tile * kChunksPerTile + lane;
+    const unsigned int prev = __shfl_up_sync(0xffffffffu, slot_end, 1);
+    if (c <= n_chunks_global) nb.P[c] = start + (lane == 0 ? 0u : prev);
+    if (lane == 31 && c + 1 <= n_chunks_global) nb.P[c + 1] = start + slot_end;   // (== the next tile's first entry; the sentinel after the last chunk)
 }
 
 // several GPUs, no plan pass: the tiles of chunks (whole sections) that own slots of this shard's range

@@ -407,8 +407,10 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     if (n_sec_global > (size_t)kMaxSections) return fail(MPL_ERR_UNSUPPORTED, "nested scheme: at most 2^28 particles");
     FixedArgs<Real> a = fixed_args<Real>(ps, dynamic, false);
     a.overflow_follows = ps->host_flags[0] != 0 ? 1 : 0;   // the heavy-tile pass runs only once a heavy warp tile has been seen
-    // small shards: a kernel boundary costs more than level 1 recomputed by every warp of the expansion -- no plan pass
-    a.inline_level1 = g_inline_level1 >= 0 ? g_inline_level1 : (ps->n <= ((size_t)1 << 22) ? 1 : 0);
+    // small populations on one GPU: a kernel boundary costs more than level 1 recomputed by every warp of the expansion -- no plan pass
+    // (measured: on 8 GPUs the walk over whole edge sections costs more than the plan pass it saves -- 62.6 against 52 us per step;
+    //  a single GPU with 2^21 particles gains 3 us per step)
+    a.inline_level1 = g_inline_level1 >= 0 ? g_inline_level1 : (ps->world <= 1 && ps->n <= ((size_t)1 << 22) ? 1 : 0);
     const bool post = (phases & 2) && !dynamic && !ps->in_device_loop;   // the call-per-step API polls the result in mapped host memory
     if (post) { ps->host_seq += 1; if (ps->host_seq == 0) ps->host_seq = 1; }
     a.host_seq = post ? ps->host_seq : 0u;
@@ -433,7 +435,8 @@ static int resample_nested_t(mpl_ps* ps, int phases = 3, bool dynamic = false) {
     }
     if ((phases & 2) && !a.inline_level1) {
         ScopedLaunch sl(ps, "nested_plan");
-        pdl_launch(nested_plan_kernel<Real>, (unsigned int)n_sec_global, kScanThreads, ps->stream, a, nb, ps->par, n_chunks_global);
+        if (ps->world > 1) pdl_launch(nested_plan_kernel<Real>, (unsigned int)n_sec_global, kScanThreads, ps->stream, a, nb, ps->par, n_chunks_global);
+        else pdl_launch(nested_level1_kernel<Real>, (num_tiles + kScanThreads / 32 - 1) / (kScanThreads / 32), kScanThreads, ps->stream, a, nb, rec, num_tiles, n_chunks_global);
     }
     if (phases & 2) {
         ScopedLaunch sl(ps, "nested_expand");
