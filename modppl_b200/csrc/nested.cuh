@@ -145,13 +145,13 @@ __device__ __forceinline__ void nested_top_level_warp(const NestedPrefixes& nb, 
     }
 }
 
-// several GPUs: collect every other shard's section records (the caller then runs the top level), one warp.  The records are
-// PULLED: every rank publishes its own in its own mailbox and the readers poll them over NVLink -- a kernel that stores into
-// another GPU's memory cannot complete before those stores are acknowledged (~4 us at every kernel boundary), a kernel
-// that only loads has nothing to wait for.
-__device__ __forceinline__ void collect_section_records_warp(const PeerTable& p, long long epoch, const NestedPrefixes& nb) {
+// several GPUs: collect every other shard's section records (the caller then runs the top level), the whole block: one record
+// per thread, so that all of them are in flight together -- ONE NVLink round trip.  The records are PULLED: every rank publishes
+// its own in its own mailbox and the readers poll them over NVLink -- a kernel that stores into another GPU's memory cannot
+// complete before those stores are acknowledged (~4 us at every kernel boundary), a kernel that only loads has nothing to wait for.
+__device__ __forceinline__ void collect_section_records(const PeerTable& p, long long epoch, const NestedPrefixes& nb) {
     SpinGuard g(p);
-    for (unsigned int sg = threadIdx.x & 31; sg < nb.n_sec_global; sg += 32) {
+    for (unsigned int sg = threadIdx.x; sg < nb.n_sec_global; sg += blockDim.x) {
         if (sg - nb.sec0 < nb.n_sec) continue;   // own sections: already in place
         const volatile unsigned long long* src = p.mail[sg / nb.n_sec]->sec_ll[epoch & 1][sg];   // (equal shards of whole sections: the owner of global section sg)
         unsigned long long w[6];
@@ -169,17 +169,18 @@ __device__ __forceinline__ void collect_section_records_warp(const PeerTable& p,
         nb.sec_sq[sg] = __longlong_as_double((long long)((w[4] & 0xffffffffull) | (w[5] << 32)));
     }
     __threadfence();
-    __syncwarp();
+    __syncthreads();
 }
 
-// the tail of the section level, by the warp that completed this shard's LAST section: (several GPUs: the other shards' records,)
-// the top level
-__device__ __forceinline__ void nested_after_sections_warp(const PeerTable& peer, const NestedPrefixes& nb, DeviceStats* st, long long epoch, uint64_t seed, long long rt,
-                                                           unsigned long long n_out, int dynamic, double ess_threshold) {
-    const int lane = threadIdx.x & 31;
-    if (peer.world > 1) { if (lane == 0) st->trace[6] = global_ns(); collect_section_records_warp(peer, epoch, nb); }
-    nested_top_level_warp(nb, st, seed, rt, n_out, dynamic, ess_threshold);
-    if (lane == 0) st->trace[7] = global_ns();
+// the tail of the section level, by the block that completed this shard's LAST section: (several GPUs: the other shards' records,)
+// the top level (one warp)
+__device__ __forceinline__ void nested_after_sections(const PeerTable& peer, const NestedPrefixes& nb, DeviceStats* st, long long epoch, uint64_t seed, long long rt,
+                                                      unsigned long long n_out, int dynamic, double ess_threshold) {
+    if (peer.world > 1) { if (threadIdx.x == 0) st->trace[6] = global_ns(); collect_section_records(peer, epoch, nb); }
+    if (threadIdx.x < 32) {
+        nested_top_level_warp(nb, st, seed, rt, n_out, dynamic, ess_threshold);
+        if (threadIdx.x == 0) st->trace[7] = global_ns();
+    }
 }
 
 // scalar bookkeeping of resample(): particle_filter.rs:104-105,114 (one thread of the expansion kernel)
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     const long long epoch = a.epoch < 0 ? st->t : a.epoch;
     if (blockIdx.x == 0 && tid == 0) st->trace[9] = global_ns();
     if constexpr (PHASES == 2) {
-        if (warp == 0) nested_after_sections_warp(a.peer, nb, st, epoch, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
+        nested_after_sections(a.peer, nb, st, epoch, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
         return;
     }
     const unsigned int sec = blockIdx.x;
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kScanThreads) nested_sections_kernel(FixedArgs
     if (tid == 0) { st->overflow_count = 0; st->blocks_done = 0; st->trace[5] = global_ns(); }
     if constexpr (PHASES == 3) {
         __syncthreads();
-        if (warp == 0) nested_after_sections_warp(a.peer, nb, st, epoch, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
+        nested_after_sections(a.peer, nb, st, epoch, a.seed, a.rt, a.n_out, a.dynamic, a.ess_threshold);
     }
 }
 
