@@ -476,6 +476,7 @@ def run_config4_multi(args):
     l0 = ps.launch_count()
     nv0 = ps.nvlink_bytes()
     dist.barrier(); torch.cuda.synchronize()
+    ps.device_barrier()      # the host barrier releases the ranks hundreds of us apart: the GPUs rendezvous themselves in front of the timed steps
     ms = ps.run(1 + W, K, scheme)
     ps.sync()
     dist.barrier(); torch.cuda.synchronize()
@@ -617,6 +618,7 @@ def run_config5(args):
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     if world > 1:
         dist.barrier(); torch.cuda.synchronize()
+        ps.device_barrier()
     l0 = ps.launch_count()
     ms = ps.run(1 + W, K, scheme, ess_threshold=0.5)
     ps.sync()

@@ -203,6 +203,7 @@ int mpl_logpdf(const char* dist, const double* x, const double* params, size_t n
 int mpl_ps_peer_export(mpl_ps*, void* blob /* MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_attach(mpl_ps*, int rank, int world, const void* blobs /* world * MPL_PEER_BLOB_BYTES */);
 int mpl_ps_peer_detach(mpl_ps*);
+int mpl_ps_peer_barrier(mpl_ps*);           /* queues a device-side rendezvous of all ranks' streams (no host round trip); every rank calls it */
 int mpl_ps_peer_error(mpl_ps*, int* out);   /* 1 if a kernel gave up waiting for a peer (bounded spin) */
 int mpl_ps_nvlink_bytes(mpl_ps*, uint64_t* out);   /* payload bytes requested from the peers' memory so far (remote parents, weights, records) */
 int mpl_ps_trace(mpl_ps*, long long* out16);   /* device time stamps (ns) of the last sharded step's phases; diagnostics */

@@ -109,6 +109,7 @@ SYMBOLS = {
     "mpl_ps_peer_export": (C.c_int, C.c_void_p, C.c_void_p),
     "mpl_ps_peer_attach": (C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p),
     "mpl_ps_peer_detach": (C.c_int, C.c_void_p),
+    "mpl_ps_peer_barrier": (C.c_int, C.c_void_p),
     "mpl_ps_peer_error": (C.c_int, C.c_void_p, C.POINTER(C.c_int)),
     "mpl_ps_trace": (C.c_int, C.c_void_p, C.POINTER(C.c_longlong)),
     "mpl_ps_nvlink_bytes": (C.c_int, C.c_void_p, c_u64_p),

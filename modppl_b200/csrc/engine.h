@@ -92,6 +92,7 @@ struct mpl_ps {
     mpl::Mailbox* mailbox;            // device memory of this rank, written by every rank
     void* ipc_opened[9][mpl::kMaxPeers];   // pointers obtained from cudaIpcOpenMemHandle (to close on detach)
     bool peer_virtual;                // peers live in this process (single-GPU emulation used by the tests)
+    unsigned long long barrier_seq;   // mpl_ps_peer_barrier calls so far (every rank makes the same sequence of calls)
     // islands (local resampling; multi_gpu.cu): the other islands' state buffers, for the occasional island-level resampling
     int n_islands, island_rank;
     const void* island_state[2][mpl::kMaxPeers];

@@ -242,6 +242,27 @@ extern "C" int mpl_ps_trace(mpl_ps* ps, long long* out16) {
     return MPL_OK;
 }
 
+// device-side rendezvous of all ranks' streams (no host involved): every rank raises its own barrier word and polls the peers'.
+// Queued in front of a timed run it makes all GPUs start the run together -- the host-side barrier before it releases the ranks
+// hundreds of microseconds apart, which a loop of 50 us steps that meets at a gate every step would otherwise count as step time.
+static __global__ void peer_barrier_kernel(PeerTable p, unsigned long long seq) {
+    if (threadIdx.x == 0) {
+        *(volatile unsigned long long*)&p.mail[p.rank]->barrier_seq = seq;
+        SpinGuard g(p);
+        for (int h = 0; h < p.world; ++h)
+            while (*(volatile unsigned long long*)&p.mail[h]->barrier_seq < seq) if (g.give_up()) return;
+    }
+}
+extern "C" int mpl_ps_peer_barrier(mpl_ps* ps) {
+    if (!ps) return fail(MPL_ERR_INVALID, "null handle");
+    if (ps->world <= 1 || ps->peer_virtual) return MPL_OK;
+    MPL_CUDA_OK(cudaSetDevice(ps->device));
+    ps->barrier_seq += 1;
+    peer_barrier_kernel<<<1, 32, 0, ps->stream>>>(ps->peer, ps->barrier_seq);
+    MPL_CUDA_OK(cudaGetLastError());
+    return MPL_OK;
+}
+
 extern "C" int mpl_ps_nvlink_bytes(mpl_ps* ps, uint64_t* out) {
     // payload bytes this GPU has requested from its peers' memory so far: parent states gathered across a shard edge, integer
     // weights and chunk records of chunks that own some of this GPU's slots, the peers' section records

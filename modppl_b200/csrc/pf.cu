@@ -676,7 +676,7 @@ extern "C" mpl_ps* mpl_particle_system_new(const mpl_model* model, uint64_t num_
     ps->sq_partials = nullptr; ps->host_flags = nullptr; ps->host_flags_dev = nullptr; ps->ess_threshold_abs = 0.; ps->dynamic_state_known = false; ps->hist_broken = false;
     ps->profile = false; ps->launch_count = 0; ps->rank = 0; ps->world = 1; ps->mailbox = nullptr; ps->peer_virtual = false;
     std::memset(&ps->peer, 0, sizeof ps->peer); ps->peer.world = 1; std::memset(ps->ipc_opened, 0, sizeof ps->ipc_opened);
-    ps->n_islands = 1; ps->island_rank = 0; std::memset(ps->island_state, 0, sizeof ps->island_state); std::memset(ps->island_opened, 0, sizeof ps->island_opened);
+    ps->barrier_seq = 0; ps->n_islands = 1; ps->island_rank = 0; std::memset(ps->island_state, 0, sizeof ps->island_state); std::memset(ps->island_opened, 0, sizeof ps->island_opened);
     ps->probs = nullptr; ps->cums = nullptr; ps->icum = nullptr; ps->obs_dev = nullptr; ps->obs_steps = 0; ps->staging = nullptr;
     const size_t es = elem_size(ps);
     const size_t num_tiles = ps->ld / kScanTile;

@@ -68,6 +68,7 @@ struct Mailbox {
     int error;
     int pad;
     unsigned long long nvlink_polled;   // bytes of section records fetched from peers (one successful poll each; diagnostics)
+    unsigned long long barrier_seq;     // mpl_ps_peer_barrier: this rank has reached barrier number ... (polled by the peers)
     // nested scheme: (E_s, T_s, sum q^2) of every section of THIS shard, indexed by [step & 1][GLOBAL section number]; published
     // here by the owner and polled by the peers.  Two parities: a rank may already publish step t + 1 while a slow peer is still
     // collecting step t (it cannot get to t + 2 before that peer has published t + 1, i.e. is done with t)

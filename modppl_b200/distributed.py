@@ -81,6 +81,10 @@ class ShardedParticleSystem(ParticleSystem):
         return {"extend_gate_wait": tr[1] - tr[0], "extend_body": tr[2] - tr[1], "to_reduce_gate": tr[3] - tr[2], "reduce_gate_wait": tr[4] - tr[3],
                 "reduce_body": tr[5] - tr[4], "to_scan_gate": tr[6] - tr[5], "scan_gate_wait": tr[7] - tr[6], "scan_to_signal": tr[8] - tr[7]}
 
+    def device_barrier(self):
+        """queue a device-side rendezvous of all ranks' streams: whatever is queued after it starts on all GPUs together"""
+        check(lib.mpl_ps_peer_barrier(self._h))
+
     def nvlink_bytes(self):
         """payload bytes this rank has requested from its peers' memory so far (remote parents, weights, records)"""
         n = C.c_uint64()
