@@ -25,7 +25,7 @@ modppl_b200/lib/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVCCFLAGS) -c -o $@ $< 2> modppl_b200/lib/$*.ptxas.log || (cat modppl_b200/lib/$*.ptxas.log; false)
 
 $(LIB): $(OBJS)
-	$(NVCC) -shared -o $@ $(OBJS) -ldl
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared -o $@ $(OBJS) -ldl
 	@cat modppl_b200/lib/*.ptxas.log > modppl_b200/lib/ptxas.log
 
 oracle:

@@ -174,15 +174,16 @@ static __global__ void __launch_bounds__(kCxThreads) cx_pairs_kernel(const doubl
 }
 
 // ---- pass 4: the sequential walk over tiles (one block) ----------------------------------------------------------------------
-constexpr int kCxWalkChunk = 512;   // tile records staged in shared memory per round (global loads are ~500 cycles each)
+constexpr int kCxWalkChunk = 256;   // tile records staged in shared memory per round (global loads are ~500 cycles each)
 static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double* __restrict__ p, size_t n, CxTile* tiles, unsigned int num_tiles, double* __restrict__ out) {
     __shared__ double buf[kCxTile];
     __shared__ unsigned long long c_even[kCxWalkChunk], c_odd[kCxWalkChunk];
     __shared__ double c_start[kCxWalkChunk];
     __shared__ int c_epred[kCxWalkChunk];
     __shared__ signed char c_reg[kCxWalkChunk];
-    __shared__ double s_run;
-    __shared__ unsigned int stop_at;
+    __shared__ double s_run, s_start_tile;
+    __shared__ unsigned int stop_at, nz_total, nz_warp[kCxThreads / 32];
+    __shared__ unsigned short nz_rank[kCxTile];
     const int tid = threadIdx.x;
     if (tid == 0) s_run = 0.;
     for (unsigned int chunk0 = 0; chunk0 < num_tiles; chunk0 += kCxWalkChunk) {
@@ -218,29 +219,53 @@ static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double
             __syncthreads();
             k = stop_at;
             if (k >= cnt) break;
-            // irregular tile: exact additions in index order by one thread, staged through shared memory
+            // irregular tile: exact additions in index order by one thread, staged through shared memory.  Adding +0 never changes
+            // the running sum, and importance weights are mostly exact zeros (exp underflow): the zeros are compacted away by all
+            // threads first (order kept), the one thread adds the non-zero elements only, and every position then reads the sum
+            // after the last non-zero element at or before it.
             const size_t base = (size_t)(chunk0 + k) * kCxTile;
-            for (int i = tid; i < kCxTile; i += kCxThreads) buf[i] = (base + i < n) ? p[base + i] : 0.;
+            {
+                // thread t owns elements [8 t, 8 t + 8): inclusive count of non-zero elements (warp scan + warp totals)
+                double v[kCxIpt];
+                unsigned int c = 0;
+#pragma unroll
+                for (int i = 0; i < kCxIpt; ++i) { const size_t idx = base + (size_t)tid * kCxIpt + i; v[i] = idx < n ? p[idx] : 0.; c += v[i] != 0. ? 1u : 0u; }
+                unsigned int incl = c;
+                const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+                if (lane == 31) nz_warp[warp] = incl;
+                __syncthreads();
+                unsigned int before = incl - c;
+                for (int w = 0; w < warp; ++w) before += nz_warp[w];
+#pragma unroll
+                for (int i = 0; i < kCxIpt; ++i) {
+                    if (v[i] != 0.) buf[before++] = v[i];                       // compacted, in index order
+                    nz_rank[tid * kCxIpt + i] = (unsigned short)before;       // non-zero elements at or before this position
+                }
+                if (tid == kCxThreads - 1) nz_total = before;
+            }
             __syncthreads();
             if (tid == 0) {
-                // (padding beyond n is zero, so running over the whole tile is harmless; loads are hoisted out of the
-                //  dependent chain of additions)
                 double S = s_run;
-                for (int i = 0; i < kCxTile; i += 8) {
+                const unsigned int cnt_nz = nz_total;
+                for (unsigned int i = 0; i < cnt_nz; i += 8) {   // (loads hoisted out of the dependent chain of additions)
                     double r[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = buf[i + j];
+                    for (int j = 0; j < 8; ++j) r[j] = i + j < cnt_nz ? buf[i + j] : 0.;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { S = __dadd_rn(S, r[j]); r[j] = S; }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) buf[i + j] = r[j];
+                    for (int j = 0; j < 8; ++j) if (i + j < cnt_nz) buf[i + j] = r[j];
                 }
+                s_start_tile = s_run;
                 s_run = S;
             }
             __syncthreads();
-            for (int i = tid; i < kCxTile; i += kCxThreads) if (base + i < n) out[base + i] = buf[i];
+            for (int i = tid; i < kCxTile; i += kCxThreads) if (base + i < n) { const unsigned int rk = nz_rank[i]; out[base + i] = rk ? buf[rk - 1] : s_start_tile; }
             k += 1;
             __syncthreads();
+            continue;
         }
         __syncthreads();
         for (unsigned int i = tid; i < cnt; i += kCxThreads) { tiles[chunk0 + i].s_start = c_start[i]; tiles[chunk0 + i].regular = c_reg[i]; }

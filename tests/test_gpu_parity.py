@@ -397,6 +397,14 @@ def cumsum_cases(n, rng):
     yield "tiny_then_big", np.concatenate([np.full(n // 2, 1e-300), rng.random(n - n // 2)])
     yield "subnormals", np.concatenate([np.full(n // 2, 5e-324), rng.random(n - n // 2) * 1e-310])
     yield "powers_of_two", 2.0 ** rng.integers(-60, -10, size=n).astype(np.float64)
+    # importance weights: exp of log-weights spread over thousands of nats -- mostly exact zeros (underflow), the rest over hundreds of
+    # binades, so nearly every tile holds a binade crossing and takes the sequential path (which skips the zeros)
+    lw = -np.abs(rng.normal(size=n)) * 2000.0
+    lw[rng.integers(0, n, size=max(4, n // 500))] = -rng.random(max(4, n // 500)) * 30.0
+    yield "importance_weights", np.exp(lw - lw.max())
+    w = np.exp(rng.normal(size=n) * 40.0)
+    w[rng.random(n) < 0.9] = 0.0
+    yield "sparse_wide", w
 
 
 @pytest.mark.parametrize("n", [8192, 8192 + 3, 100000, (1 << 22) + 17])
