@@ -433,28 +433,21 @@ __device__ __forceinline__ void chunk_exclusive_prefixes(const unsigned int (&q)
     }
 }
 
-// Level 2 count: floor((C * n_c + rem_c) / S_c) for C <= S_c < 2^30, n_c <= kLevel2FloatMax.  The quotient is estimated in
-// fp32 (nine roundings, each 2^-24 relative: the estimate is off by less than (n_c + 1) 2^-20.8) and rounded to the nearest
-// integer by the adder (no conversion instruction); only when the estimate is within `eps` = (n_c + 2) 2^-19 of an integer
-// -- where the floor could go either way -- is the exact 64-bit form evaluated.  The result is exact either way.
+// Level 2 count: floor((C * n_c + rem_c) / S_c) + 1 for C <= S_c < 2^30, n_c <= kLevel2FloatMax.  The quotient plus one half is
+// estimated in fp32 as x = C (n_c / S_c) + (rem_c / S_c + 1/2) (C accumulated in fp32: at most eight roundings of 2^-24 relative,
+// so x is off by less than (n_c + 1) 2^-21) and rounded to the nearest integer k by the adder (no conversion instruction).
+// The quotient lies within 1/2 - |x - k| of the middle between k - 1 and k: unless that leaves less than `eps` = (n_c + 2) 2^-19
+// to an integer -- where the floor could go either way -- its floor is k - 1; otherwise the exact 64-bit form is evaluated.
+// The result is exact either way.
 constexpr unsigned int kLevel2FloatMax = 2048u;
 // slots expanded per pass by one warp: a warp tile (512 particles) owns 512 slots on average, so 512 would need a second
 // pass half of the time; 768 almost never does
 constexpr int kNestedWarpSlots = 768;
-__device__ __forceinline__ unsigned int level2_count(unsigned int C, float Cf, unsigned int n_c, float n_cf, unsigned int rem_c, float rem_cf, unsigned int S_c,
-                                                    float inv_sf, float eps) {
-    const float fd = __fmul_rn(fmaf(Cf, n_cf, rem_cf), inv_sf);
-    const float t = __fadd_rn(fd, 8388608.0f);
-    const float diff = __fsub_rn(fd, __fsub_rn(t, 8388608.0f));   // fd - nearest integer, in [-0.5, 0.5]
-    unsigned int f = ((unsigned int)__float_as_int(t) & 0x7fffffu);
-    if (fabsf(diff) < eps) {
-        const unsigned long long y = (unsigned long long)C * n_c + rem_c;
-        unsigned long long p = (unsigned long long)f * S_c;
-        while (p > y) { --f; p -= S_c; }
-        while (p + S_c <= y) { ++f; p += S_c; }
-        return f;
-    }
-    return diff < 0.f ? f - 1u : f;
+__device__ __forceinline__ unsigned int level2_count_exact(unsigned int k, unsigned long long y, unsigned int S_c) {   // floor(y / S_c) + 1 from the guess k
+    unsigned long long p = (unsigned long long)k * S_c;
+    while (p > y) { --k; p -= S_c; }
+    while (p + S_c <= y) { ++k; p += S_c; }
+    return k + 1u;
 }
 
 // The lane's 16 integer weights of GLOBAL warp tile `wt` (chunks 4 wt .. 4 wt + 3; round r == chunk 4 wt + r), read from the GPU
@@ -521,31 +514,50 @@ __device__ __forceinline__ void nested_load_warp_tile(const FixedArgs<Real>& a, 
 // first output slot `ws` (global); returns the number of slots the warp tile owns.  P_w: lanes 0..4 hold P[4 wt .. 4 wt + 4].
 __device__ __forceinline__ unsigned int nested_warp_tile_counts(unsigned int wt, unsigned int P_w, unsigned int S_w, unsigned long long word, const unsigned int (&q)[4][4],
                                                                const unsigned int (&excl)[4], unsigned int (&n)[4][4], unsigned int& ws) {
+    const int lane = threadIdx.x & 31;
     ws = __shfl_sync(0xffffffffu, P_w, 0);
+    // the per-chunk scalars are computed once, by lane r for chunk r (the offset hash alone is ~35 instructions), and broadcast
+    const unsigned int n_own = __shfl_down_sync(0xffffffffu, P_w, 1) - P_w;
+    unsigned int rem_own = 0u;
+    float inv_own = 0.f;
+    if (lane < 4 && S_w != 0u) {
+        rem_own = S_w - (unsigned int)nested_chunk_offset(word, 4ull * wt + (unsigned int)lane, (unsigned long long)S_w) - 1u;
+        inv_own = __frcp_rn((float)S_w);
+    }
     unsigned int we = ws;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const unsigned int n_c = __shfl_sync(0xffffffffu, P_w, r + 1) - __shfl_sync(0xffffffffu, P_w, r);
+        const unsigned int n_c = __shfl_sync(0xffffffffu, n_own, r);
         const unsigned int cb = we - ws;   // chunks own consecutive slot ranges
         const unsigned int S_c = __shfl_sync(0xffffffffu, S_w, r);
+        // local slot l sits at l*S_c + U_c; particle with inclusive chunk prefix C owns the slots below C*n_c
+        const unsigned int rem_c = __shfl_sync(0xffffffffu, rem_own, r);
+        const float inv_sf = __shfl_sync(0xffffffffu, inv_own, r);
         if (n_c == 0u || S_c == 0u) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) n[r][j] = cb;
             continue;
         }
         we += n_c;
-        // local slot l sits at l*S_c + U_c; particle with inclusive chunk prefix C owns the slots below C*n_c
-        const unsigned long long chunk_gid = 4ull * wt + r;
-        const unsigned int rem_c = S_c - (unsigned int)nested_chunk_offset(word, chunk_gid, (unsigned long long)S_c) - 1u;
         unsigned int C = excl[r];
         if (n_c <= kLevel2FloatMax) {   // (warp-uniform)
-            const float n_cf = (float)n_c, rem_cf = (float)rem_c, inv_sf = __frcp_rn((float)S_c), eps = (n_cf + 2.f) * 0x1.0p-19f;
+            const float n_cf = (float)n_c, slope = __fmul_rn(n_cf, inv_sf), icpt = fmaf((float)rem_c, inv_sf, 0.5f), safe = 0.5f - (n_cf + 2.f) * 0x1.0p-19f;
+            const unsigned int cbm1 = cb - 1u;
             float Cf = (float)C;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                C += q[r][j];
                 Cf += __uint_as_float(q[r][j] | 0x4B000000u) - 8388608.0f;   // (float)q, exact for q <= 2^22
-                n[r][j] = cb + level2_count(C, Cf, n_c, n_cf, rem_c, rem_cf, S_c, inv_sf, eps);
+                const float x = fmaf(Cf, slope, icpt);
+                const float t = __fadd_rn(x, 8388608.0f);
+                const float d = __fsub_rn(x, __fsub_rn(t, 8388608.0f));   // x - k, in [-0.5, 0.5]
+                unsigned int k = (unsigned int)__float_as_int(t) & 0x7fffffu;
+                if (!(fabsf(d) < safe)) {
+                    unsigned int Cj = C;
+#pragma unroll
+                    for (int i = 0; i <= j; ++i) Cj += q[r][i];
+                    k = level2_count_exact(k, (unsigned long long)Cj * n_c + rem_c, S_c);
+                }
+                n[r][j] = cbm1 + k;
             }
         } else {   // a chunk that owns thousands of slots: fp64 estimate with its own exact fallback
             const double inv_s = 1. / (double)S_c, rem_cd = (double)rem_c, n_cd = (double)n_c;
@@ -689,7 +701,7 @@ __device__ __forceinline__ void nested_expand_warp_tile(const FixedArgs<Real>& a
     if (total > kWarpHeavyCap && lane == 0 && a.overflow_seen_host) *(volatile int*)a.overflow_seen_host = 1;
     const int32_t src0 = (int32_t)(wt * (unsigned int)kWarpTile) - 1;   // global id of the warp tile's first particle, minus 1
     // n[][] counts from 0 at the warp tile's first slot
-    if (!PULL && total <= (unsigned int)kNestedWarpSlots) warp_expand_chunk<Real, kNestedWarpSlots, true, false>(a, head, n, 0u, total, 0u, (unsigned long long)ws, src0);
+    if (!PULL && total + 3u <= (unsigned int)kNestedWarpSlots) warp_expand_chunk<Real, kNestedWarpSlots, true, false>(a, head, n, 0u, total, 0u, (unsigned long long)ws, src0);
     else
         for (unsigned int chunk_lo = lo; chunk_lo < hi; chunk_lo += kNestedWarpSlots)
             warp_expand_chunk<Real, kNestedWarpSlots, false, PULL>(a, head, n, 0u, total, chunk_lo, (unsigned long long)ws, src0);

@@ -78,7 +78,9 @@ __device__ __forceinline__ void warp_tile_counts(unsigned long long wp, const un
 
 // One warp expands slots [chunk_lo, chunk_lo + CAP) of its own range [0, total) (relative to ws).  CAP = 32 * (slots per
 // lane), a multiple of 256: `head` holds CAP 16-bit entries.
-// SINGLE: the caller guarantees chunk_lo == 0 and total <= CAP (the whole range in one pass): the window tests drop out.
+// SINGLE: one GPU; the caller guarantees chunk_lo == 0 and total + 3 <= CAP (the whole range in one pass): the window tests drop
+// out, and the window is laid out from the 16-byte boundary at or below the first slot, so that the ancestors leave as 128-bit
+// stores (4 slots per lane and instruction).
 // CLIP: pull organisation (nested scheme on several GPUs) -- this shard fills only its OWN slot range, wherever the parents live:
 // slots outside [out_base, out_base + n_out_local) are some other GPU's to fill and are dropped here.
 template <typename Real, int CAP = kWarpChunk, bool SINGLE = false, bool CLIP = false>
@@ -92,6 +94,9 @@ __device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsi
 #pragma unroll
     for (int k = 0; k < VEC; ++k) head4[lane * VEC + k] = make_uint4(0, 0, 0, 0);
     __syncwarp();
+    unsigned int shift = 0u;   // SINGLE: head[] position of the first slot (its index in the output array, modulo 4)
+    if constexpr (SINGLE) shift = (unsigned int)((slot_base - a.out_base) & 3ull);
+    const unsigned int org = ws - shift;
     // run heads: element e (order r, lane, j) owns relative slots [n_prev - ws, n_e - ws)
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -100,7 +105,7 @@ __device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsi
         if (lane == 0) prev = (r == 0) ? ws : last_prev_round;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const unsigned int start = prev - ws, end = n[r][j] - ws;
+            const unsigned int start = prev - org, end = n[r][j] - org;
             if constexpr (SINGLE) {
                 if (end > start) head[start] = (unsigned short)(r * 128 + lane * 4 + j + 1);
             } else {
@@ -111,26 +116,29 @@ __device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsi
         }
     }
     __syncwarp();
-    // max-scan: lane owns slots [PER_LANE*lane, PER_LANE*lane + PER_LANE) of the chunk
-    unsigned int v[PER_LANE];
+    // max-scan: lane owns slots [PER_LANE*lane, PER_LANE*lane + PER_LANE) of the chunk, two per 32-bit word; the scan runs on the
+    // packed words (VIMNMX.U16x2): R[w] = running maxima over the even (low half) and over the odd (high half) slots up to word w
+    constexpr int NW = PER_LANE / 2;
+    unsigned int R[NW];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
         const uint4 h = head4[lane * VEC + k];
-        v[8 * k + 0] = h.x & 0xffffu; v[8 * k + 1] = h.x >> 16; v[8 * k + 2] = h.y & 0xffffu; v[8 * k + 3] = h.y >> 16;
-        v[8 * k + 4] = h.z & 0xffffu; v[8 * k + 5] = h.z >> 16; v[8 * k + 6] = h.w & 0xffffu; v[8 * k + 7] = h.w >> 16;
+        R[4 * k + 0] = h.x; R[4 * k + 1] = h.y; R[4 * k + 2] = h.z; R[4 * k + 3] = h.w;
     }
 #pragma unroll
-    for (int i = 1; i < PER_LANE; ++i) v[i] = max(v[i], v[i - 1]);
-    unsigned int incl = v[PER_LANE - 1];
+    for (int w = 1; w < NW; ++w) R[w] = __vmaxu2(R[w], R[w - 1]);
+    unsigned int incl = max(R[NW - 1] & 0xffffu, R[NW - 1] >> 16);
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl = max(incl, up); }
     unsigned int pre = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) pre = 0;
+    const unsigned int pre2 = pre | (pre << 16);
+    // slot 2w: max(pre, evens up to w, odds up to w - 1); slot 2w + 1: max(pre, evens up to w, odds up to w)
 #pragma unroll
-    for (int i = 0; i < PER_LANE; ++i) v[i] = max(v[i], pre);
+    for (int w = NW - 1; w >= 0; --w)
+        R[w] = __vimax3_u16x2(__byte_perm(R[w], 0u, 0x1010), __byte_perm(w ? R[w - 1] : 0u, R[w], 0x7632), pre2);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k)
-        head4[lane * VEC + k] = make_uint4(v[8 * k] | (v[8 * k + 1] << 16), v[8 * k + 2] | (v[8 * k + 3] << 16), v[8 * k + 4] | (v[8 * k + 5] << 16), v[8 * k + 6] | (v[8 * k + 7] << 16));
+    for (int k = 0; k < VEC; ++k) head4[lane * VEC + k] = make_uint4(R[4 * k + 0], R[4 * k + 1], R[4 * k + 2], R[4 * k + 3]);
     __syncwarp();
     const unsigned int valid = min((unsigned int)CAP, total - chunk_lo);
     const unsigned long long slot0 = slot_base + chunk_lo;
@@ -141,6 +149,28 @@ __device__ __forceinline__ bool warp_expand_chunk(const FixedArgs<Real>& a, unsi
             const unsigned int o = k * 32 + lane;
             const unsigned long long rel = rel0 + o;
             if (o < valid && rel < a.n_out_local) a.anc[rel] = src0 + (int32_t)head[o];
+        }
+        __syncwarp();
+        return false;
+    }
+    if constexpr (SINGLE) {
+        const unsigned int end_p = total + shift;
+        int32_t* dst = a.anc + (slot0 - a.out_base) - shift;   // 16-byte aligned
+        const uint2* head2 = reinterpret_cast<const uint2*>(head);
+#pragma unroll
+        for (int k = 0; k < CAP / 128; ++k) {
+            const unsigned int p0 = 4u * (k * 32 + lane);
+            if (p0 < end_p) {
+                const uint2 h = head2[k * 32 + lane];
+                const int4 v = make_int4(src0 + (int32_t)(h.x & 0xffffu), src0 + (int32_t)(h.x >> 16), src0 + (int32_t)(h.y & 0xffffu), src0 + (int32_t)(h.y >> 16));
+                if (p0 >= shift && p0 + 4u <= end_p) *reinterpret_cast<int4*>(dst + p0) = v;
+                else {   // the first and the last group of the range
+                    if (p0 >= shift) dst[p0] = v.x;
+                    if (p0 + 1u >= shift && p0 + 1u < end_p) dst[p0 + 1] = v.y;
+                    if (p0 + 2u >= shift && p0 + 2u < end_p) dst[p0 + 2] = v.z;
+                    if (p0 + 3u < end_p) dst[p0 + 3] = v.w;
+                }
+            }
         }
         __syncwarp();
         return false;
