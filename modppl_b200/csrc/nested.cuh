@@ -434,8 +434,8 @@ __device__ __forceinline__ void chunk_exclusive_prefixes(const unsigned int (&q)
 }
 
 // Level 2 count: floor((C * n_c + rem_c) / S_c) + 1 for C <= S_c < 2^30, n_c <= kLevel2FloatMax.  The quotient plus one half is
-// estimated in fp32 as x = C (n_c / S_c) + (rem_c / S_c + 1/2) (C accumulated in fp32: at most eight roundings of 2^-24 relative,
-// so x is off by less than (n_c + 1) 2^-21) and rounded to the nearest integer k by the adder (no conversion instruction).
+// estimated in fp32 as x = C (n_c / S_c) + (rem_c / S_c + 1/2), carried from particle to particle (x += q slope: at most eight
+// roundings of 2^-24 relative, so x is off by less than (n_c + 2) 2^-21), and rounded to the nearest integer k by the adder (no conversion instruction).
 // The quotient lies within 1/2 - |x - k| of the middle between k - 1 and k: unless that leaves less than `eps` = (n_c + 2) 2^-19
 // to an integer -- where the floor could go either way -- its floor is k - 1; otherwise the exact 64-bit form is evaluated.
 // The result is exact either way.
@@ -543,11 +543,10 @@ __device__ __forceinline__ unsigned int nested_warp_tile_counts(unsigned int wt,
         if (n_c <= kLevel2FloatMax) {   // (warp-uniform)
             const float n_cf = (float)n_c, slope = __fmul_rn(n_cf, inv_sf), icpt = fmaf((float)rem_c, inv_sf, 0.5f), safe = 0.5f - (n_cf + 2.f) * 0x1.0p-19f;
             const unsigned int cbm1 = cb - 1u;
-            float Cf = (float)C;
+            float x = fmaf((float)C, slope, icpt);   // (the running estimate itself is carried: one conversion and one fma per particle)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                Cf += __uint_as_float(q[r][j] | 0x4B000000u) - 8388608.0f;   // (float)q, exact for q <= 2^22
-                const float x = fmaf(Cf, slope, icpt);
+                x = fmaf((float)q[r][j], slope, x);
                 const float t = __fadd_rn(x, 8388608.0f);
                 const float d = __fsub_rn(x, __fsub_rn(t, 8388608.0f));   // x - k, in [-0.5, 0.5]
                 unsigned int k = (unsigned int)__float_as_int(t) & 0x7fffffu;
