@@ -544,20 +544,25 @@ __device__ __forceinline__ unsigned int nested_warp_tile_counts(unsigned int wt,
             const float n_cf = (float)n_c, slope = __fmul_rn(n_cf, inv_sf), icpt = fmaf((float)rem_c, inv_sf, 0.5f), safe = 0.5f - (n_cf + 2.f) * 0x1.0p-19f;
             const unsigned int cbm1 = cb - 1u;
             float x = fmaf((float)C, slope, icpt);   // (the running estimate itself is carried: one conversion and one fma per particle)
+            unsigned int k[4];
+            bool close = false;   // some estimate of the lane's four is too close to an integer to be floored safely (rare)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 x = fmaf((float)q[r][j], slope, x);
                 const float t = __fadd_rn(x, 8388608.0f);
                 const float d = __fsub_rn(x, __fsub_rn(t, 8388608.0f));   // x - k, in [-0.5, 0.5]
-                unsigned int k = (unsigned int)__float_as_int(t) & 0x7fffffu;
-                if (!(fabsf(d) < safe)) {
-                    unsigned int Cj = C;
-#pragma unroll
-                    for (int i = 0; i <= j; ++i) Cj += q[r][i];
-                    k = level2_count_exact(k, (unsigned long long)Cj * n_c + rem_c, S_c);
-                }
-                n[r][j] = cbm1 + k;
+                k[j] = (unsigned int)__float_as_int(t) & 0x7fffffu;
+                close |= !(fabsf(d) < safe);
             }
+            if (close) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    C += q[r][j];
+                    k[j] = level2_count_exact(k[j], (unsigned long long)C * n_c + rem_c, S_c);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) n[r][j] = cbm1 + k[j];
         } else {   // a chunk that owns thousands of slots: fp64 estimate with its own exact fallback
             const double inv_s = 1. / (double)S_c, rem_cd = (double)rem_c, n_cd = (double)n_c;
 #pragma unroll
