@@ -85,58 +85,68 @@ __device__ __forceinline__ unsigned long long nested_chunk_offset(unsigned long 
 // 2^(-2d), exactly, for 0 <= d < 500 (rescales a sum of squares between two power-of-two references)
 __device__ __forceinline__ double pow2_neg2(int d) { return __longlong_as_double((long long)(1023 - 2 * d) << 52); }
 
-// Top level, by ONE WARP (of the section pass' last block): E, M_s, W, the ESS, and level 0 of the resampling (slot j sits at j*W + U; section s owns the slots
-// [a_s, a_s + n_s)) from the section records.  Sections are taken in groups of 128, 4 consecutive ones per lane.
-__device__ __forceinline__ void nested_top_level_warp(const NestedPrefixes& nb, DeviceStats* st, uint64_t seed, long long rt, unsigned long long n_out, int dynamic,
-                                                      double ess_threshold) {
-    const int lane = threadIdx.x & 31;
+// Top level, by the section pass' last block (every thread of it): E, M_s, W, the ESS, and level 0 of the resampling (slot j sits
+// at j*W + U; section s owns the slots [a_s, a_s + n_s)) from the section records.  One section per thread, 256 per round: up to
+// 2^25 particles the prefixes never leave the registers, and the exact 128-bit slot base is one evaluation deep.
+__device__ __forceinline__ void nested_top_level_block(const NestedPrefixes& nb, DeviceStats* st, uint64_t seed, long long rt, unsigned long long n_out, int dynamic,
+                                                       double ess_threshold) {
+    __shared__ unsigned long long s_tot[kScanThreads / 32];
+    __shared__ double s_sq[kScanThreads / 32];
+    __shared__ int s_E[kScanThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n_sec = nb.n_sec_global;
     int E = kChunkEmpty;
-    for (unsigned int i = lane; i < n_sec; i += 32) E = max(E, __ldcg(nb.sec_E + i));
+    for (unsigned int i = tid; i < n_sec; i += kScanThreads) E = max(E, __ldcg(nb.sec_E + i));
     E = __reduce_max_sync(0xffffffffu, E);
+    if (lane == 0) s_E[warp] = E;
     const unsigned long long word = resample_rand_word(seed, rt, st);   // (independent of the loads)
-    unsigned long long carry = 0;
-    double sqt = 0.;
-    for (unsigned int base = 0; base < n_sec; base += 128) {
-        const unsigned int first = base + 4u * lane;
-        unsigned long long v[4], tot = 0;
+    __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool ok = first + i < n_sec;
-            const int e_s = ok ? __ldcg(nb.sec_E + first + i) : kChunkEmpty;
-            const unsigned long long T = ok ? __ldcg(nb.sec_T + first + i) : 0ull;
-            const double sq = ok ? __ldcg(nb.sec_sq + first + i) : 0.;
-            v[i] = nested_shift(T, e_s, E);
-            if (e_s != kChunkEmpty && E - e_s < 500) sqt += sq * pow2_neg2(E - e_s);
-            tot += v[i];
-        }
-        unsigned long long incl = tot;
+    for (int w = 0; w < kScanThreads / 32; ++w) E = max(E, s_E[w]);
+    unsigned long long carry = 0, v = 0, pre = 0;
+    double sqt = 0.;
+    for (unsigned int base = 0; base < n_sec; base += kScanThreads) {
+        const unsigned int sc = base + tid;
+        const bool ok = sc < n_sec;
+        const int e_s = ok ? __ldcg(nb.sec_E + sc) : kChunkEmpty;
+        const unsigned long long T = ok ? __ldcg(nb.sec_T + sc) : 0ull;
+        const double sq = ok ? __ldcg(nb.sec_sq + sc) : 0.;
+        v = nested_shift(T, e_s, E);
+        if (e_s != kChunkEmpty && E - e_s < 500) sqt += sq * pow2_neg2(E - e_s);
+        unsigned long long incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
-        unsigned long long pre = carry + incl - tot;
+        if (lane == 31) s_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long before = 0, all = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { if (first + i < n_sec) { nb.sec_pre[first + i] = pre; nb.sec_M[first + i] = v[i]; } pre += v[i]; }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        for (int w = 0; w < kScanThreads / 32; ++w) { const unsigned long long t = s_tot[w]; if (w < warp) before += t; all += t; }
+        pre = carry + before + incl - v;
+        if (ok && n_sec > (unsigned int)kScanThreads) { nb.sec_pre[sc] = pre; nb.sec_M[sc] = v; }   // (several rounds: parked until W is known)
+        carry += all;
+        __syncthreads();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sqt += __shfl_xor_sync(0xffffffffu, sqt, o);
+    if (lane == 0) s_sq[warp] = sqt;
     const unsigned long long W = carry;
     if (W != 0ull) {
         const unsigned long long U = __umul64hi(word, W);
         const double inv_w = 1. / (double)W;
-        for (unsigned int base = 0; base < n_sec; base += 128) {   // (every lane re-reads what it wrote itself)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const unsigned int sc = base + 4u * lane + i;
-                if (sc >= n_sec) break;
-                const unsigned long long m = nb.sec_M[sc];
-                const TileBase sb = tile_base_exact(nb.sec_pre[sc], W, U, n_out, inv_w);
-                nb.sec_a[sc] = sb.n_start;
-                nb.sec_n[sc] = local_count(m, sb.rem, (double)sb.rem, W, (double)n_out, n_out, inv_w);
-            }
+        for (unsigned int base = 0; base < n_sec; base += kScanThreads) {
+            const unsigned int sc = base + tid;
+            if (sc >= n_sec) break;
+            if (n_sec > (unsigned int)kScanThreads) { pre = nb.sec_pre[sc]; v = nb.sec_M[sc]; }   // (what this thread wrote itself)
+            const TileBase sb = tile_base_exact(pre, W, U, n_out, inv_w);
+            nb.sec_a[sc] = sb.n_start;
+            nb.sec_n[sc] = local_count(v, sb.rem, (double)sb.rem, W, (double)n_out, n_out, inv_w);
         }
     }
-    if (lane == 0) {
+    __syncthreads();
+    if (tid == 0) {
+        sqt = 0.;
+#pragma unroll
+        for (int w = 0; w < kScanThreads / 32; ++w) sqt += s_sq[w];
         st->W = W; st->c_offset = 0; st->nest_E = E; st->rand_word = word;
         st->sumexp2 = sqt;
         const double ess = sqt > 0. ? ((double)W * (double)W) / sqt : 0.;
@@ -173,14 +183,12 @@ __device__ __forceinline__ void collect_section_records(const PeerTable& p, long
 }
 
 // the tail of the section level, by the block that completed this shard's LAST section: (several GPUs: the other shards' records,)
-// the top level (one warp)
+// the top level
 __device__ __forceinline__ void nested_after_sections(const PeerTable& peer, const NestedPrefixes& nb, DeviceStats* st, long long epoch, uint64_t seed, long long rt,
                                                       unsigned long long n_out, int dynamic, double ess_threshold) {
     if (peer.world > 1) { if (threadIdx.x == 0) st->trace[6] = global_ns(); collect_section_records(peer, epoch, nb); }
-    if (threadIdx.x < 32) {
-        nested_top_level_warp(nb, st, seed, rt, n_out, dynamic, ess_threshold);
-        if (threadIdx.x == 0) st->trace[7] = global_ns();
-    }
+    nested_top_level_block(nb, st, seed, rt, n_out, dynamic, ess_threshold);
+    if (threadIdx.x == 0) st->trace[7] = global_ns();
 }
 
 // scalar bookkeeping of resample(): particle_filter.rs:104-105,114 (one thread of the expansion kernel)
