@@ -758,7 +758,19 @@ __global__ void __launch_bounds__(kScanThreads, PULL ? 3 : 4) nested_expand_kern
     const unsigned long long word = st->rand_word;
     if constexpr (!PULL) {
         const unsigned int wt = blockIdx.x * (kScanThreads / 32) + warp;
-        nested_expand_warp_tile<Real, false>(a, st, head[warp], wt, nested_slot_starts<Real, false>(a, nb, rec_own, par, wt, n_chunks_global, word), q, excl, S_w, heavy);
+        unsigned int P_w;
+        if (a.inline_level1) {   // no level-1 pass was launched: warp 0 derives the slot starts of the block's 32 chunks, the others pick theirs up
+            __shared__ unsigned int s_P[kChunksPerTile + 1];
+            if (warp == 0) {
+                unsigned int start, slot_end;
+                nested_tile_slot_ends<Real, false>(a, nb, rec_own, par, blockIdx.x, n_chunks_global, word, start, slot_end);
+                s_P[(tid & 31) + 1] = start + slot_end;
+                if (tid == 0) s_P[0] = start;
+            }
+            __syncthreads();
+            P_w = s_P[warp * 4 + min(tid & 31, 4)];
+        } else P_w = nested_slot_starts<Real, false>(a, nb, rec_own, par, wt, n_chunks_global, word);
+        nested_expand_warp_tile<Real, false>(a, st, head[warp], wt, P_w, q, excl, S_w, heavy);
     } else {
         unsigned int tg_lo, tg_hi;
         if (a.inline_level1) nested_tile_range_sections(nb, a.out_base, a.out_base + a.n_out_local, tg_lo, tg_hi);
