@@ -174,7 +174,8 @@ static __global__ void __launch_bounds__(kCxThreads) cx_pairs_kernel(const doubl
 }
 
 // ---- pass 4: the sequential walk over tiles (one block) ----------------------------------------------------------------------
-constexpr int kCxWalkChunk = 256;   // tile records staged in shared memory per round (global loads are ~500 cycles each)
+constexpr int kCxMaxRounds = 4;      // binade crossings handled by block scans inside one irregular tile before the element-by-element path takes over
+constexpr int kCxWalkChunk = kCxThreads;   // tile records staged in shared memory per round: one per thread
 static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double* __restrict__ p, size_t n, CxTile* tiles, unsigned int num_tiles, double* __restrict__ out) {
     __shared__ double buf[kCxTile];
     __shared__ unsigned long long c_even[kCxWalkChunk], c_odd[kCxWalkChunk];
@@ -182,7 +183,9 @@ static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double
     __shared__ int c_epred[kCxWalkChunk];
     __shared__ signed char c_reg[kCxWalkChunk];
     __shared__ double s_run, s_start_tile;
-    __shared__ unsigned int stop_at, nz_total, nz_warp[kCxThreads / 32];
+    __shared__ unsigned int run_len, n_fast, cross_at, nz_total, nz_warp[kCxThreads / 32];
+    __shared__ double c_sum[kCxWalkChunk], s_prev, s_cross;
+    __shared__ CxPair run_warp[kCxThreads / 32];
     __shared__ unsigned short nz_rank[kCxTile];
     const int tid = threadIdx.x;
     if (tid == 0) s_run = 0.;
@@ -191,78 +194,148 @@ static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double
         __syncthreads();
         for (unsigned int i = tid; i < cnt; i += kCxThreads) {
             const CxTile& T = tiles[chunk0 + i];
-            c_even[i] = T.inc_even; c_odd[i] = T.inc_odd; c_epred[i] = T.e_pred; c_reg[i] = (signed char)T.regular;
+            c_even[i] = T.inc_even; c_odd[i] = T.inc_odd; c_epred[i] = T.e_pred; c_reg[i] = (signed char)T.regular; c_sum[i] = T.approx_sum;
         }
         __syncthreads();
         unsigned int k = 0;
         while (k < cnt) {
-            if (tid == 0) {   // integer updates through regular tiles until one needs the element-by-element path
-                double S = s_run;
-                unsigned int j = k;
-                for (; j < cnt; ++j) {
-                    bool fast = false;
-                    if (c_reg[j] == 1 && S > 0. && cx_grid_exp(S) == c_epred[j]) {
-                        const unsigned long long M = cx_mantissa(S);
-                        const unsigned long long inc = (M & 1ull) ? c_odd[j] : c_even[j];
-                        // the whole tile stays on this grid iff the final M does (increments are non-negative)
-                        if (c_even[j] < kCxHuge && c_odd[j] < kCxHuge && M + inc < (1ull << 53)) {
-                            c_start[j] = S;
-                            S = cx_from_grid(M + inc, c_epred[j]);
-                            fast = true;
-                        }
-                    }
-                    if (!fast) { c_reg[j] = 2; c_start[j] = S; break; }
+            // The run of regular tiles from k on that are predicted to live in the binade of tile k, thread i <-> tile k + i: their
+            // tile functions compose associatively, so one block scan gives every tile's exact start -- as long as the running sum
+            // really is in that binade at k and has not left it by the end of a tile (increments are non-negative: the tiles that
+            // pass are a prefix of the run).  The first tile that fails is walked element by element, exactly as a sequential walk
+            // over the tiles would decide.
+            if (tid == 0) { run_len = kCxThreads; n_fast = kCxThreads; }
+            __syncthreads();
+            const double S = s_run;
+            const int e_run = c_epred[k];
+            const unsigned int j = k + tid;
+            const bool in_run = j < cnt && c_reg[j] == 1 && c_epred[j] == e_run && c_even[j] < kCxHuge && c_odd[j] < kCxHuge;
+            if (!in_run) atomicMin(&run_len, (unsigned int)tid);
+            __syncthreads();
+            const bool mine = (unsigned int)tid < run_len;
+            CxPair rin = mine ? CxPair{c_even[j], c_odd[j]} : CxPair{0ull, 0ull}, rex;
+            {
+                const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    CxPair up{__shfl_up_sync(0xffffffffu, rin.e, o), __shfl_up_sync(0xffffffffu, rin.o, o)};
+                    if (lane >= o) rin = cx_compose(up, rin);
                 }
-                s_run = S;
-                stop_at = j;
+                if (lane == 31) run_warp[warp] = rin;
+                rex = CxPair{__shfl_up_sync(0xffffffffu, rin.e, 1), __shfl_up_sync(0xffffffffu, rin.o, 1)};
+                if (lane == 0) rex = CxPair{0ull, 0ull};
+                __syncthreads();
+                CxPair pre{0ull, 0ull};
+                for (int w = 0; w < warp; ++w) pre = cx_compose(pre, run_warp[w]);
+                rin = cx_compose(pre, rin);
+                rex = cx_compose(pre, rex);
+            }
+            const bool at_home = S > 0. && cx_grid_exp(S) == e_run;
+            const unsigned long long M = cx_mantissa(S);
+            const unsigned long long m_start = M + ((M & 1ull) ? rex.o : rex.e), m_end = M + ((M & 1ull) ? rin.o : rin.e);
+            if (mine && !(at_home && m_end < (1ull << 53))) atomicMin(&n_fast, (unsigned int)tid);
+            __syncthreads();
+            const unsigned int fast = min(n_fast, run_len);
+            if ((unsigned int)tid < fast) {
+                c_start[j] = cx_from_grid(m_start, e_run);
+                if ((unsigned int)tid == fast - 1) s_run = cx_from_grid(m_end, e_run);
             }
             __syncthreads();
-            k = stop_at;
-            if (k >= cnt) break;
-            // irregular tile: exact additions in index order by one thread, staged through shared memory.  Adding +0 never changes
+            k += fast;
+            if (fast != 0u) continue;   // (the tile after the run: the next round decides -- a new run, or the exact path right below)
+            if (tid == 0) { c_reg[k] = 2; c_start[k] = S; }
+            // Irregular tile.  thread t owns elements [8 t, 8 t + 8).
+            const size_t base = (size_t)(chunk0 + k) * kCxTile;
+            double v[kCxIpt];
+#pragma unroll
+            for (int i = 0; i < kCxIpt; ++i) { const size_t idx = base + (size_t)tid * kCxIpt + i; v[i] = idx < n ? p[idx] : 0.; }
+            // (a) A tile that holds one or two binade crossings (the usual case for resampling weights: its predicted sum is
+            // comparable to the running sum): between two crossings the integer recurrence holds, so the block scans the pairs
+            // from `pos` on, finds the first addition that leaves the binade, writes everything before it, performs that one
+            // addition in fp64 -- exactly what the sequential loop does there -- and goes on from the element after it.
+            unsigned int pos = 0;
+            if (S > 0. && c_sum[k] < 3. * S) {
+                double Sr = S;
+                for (int round = 0; round < kCxMaxRounds && pos < (unsigned int)kCxTile; ++round) {
+                    const int e = cx_grid_exp(Sr);
+                    const unsigned long long M = cx_mantissa(Sr);
+                    CxPair el[kCxIpt], incl[kCxIpt];
+#pragma unroll
+                    for (int i = 0; i < kCxIpt; ++i) el[i] = (unsigned int)(tid * kCxIpt + i) >= pos ? cx_element(v[i], e) : CxPair{0ull, 0ull};
+                    if (tid == 0) cross_at = kCxTile;
+                    cx_block_inclusive(el, incl, run_warp);   // (one block barrier inside: orders the store above, too)
+                    unsigned long long m[kCxIpt];
+#pragma unroll
+                    for (int i = 0; i < kCxIpt; ++i) m[i] = M + ((M & 1ull) ? incl[i].o : incl[i].e);
+#pragma unroll
+                    for (int i = kCxIpt - 1; i >= 0; --i) if ((unsigned int)(tid * kCxIpt + i) >= pos && m[i] >= (1ull << 53)) atomicMin(&cross_at, (unsigned int)(tid * kCxIpt + i));
+                    __syncthreads();
+                    const unsigned int cross = cross_at;
+#pragma unroll
+                    for (int i = 0; i < kCxIpt; ++i) {
+                        const unsigned int q = tid * kCxIpt + i;
+                        if (q >= pos && q < cross) {
+                            const double val = cx_from_grid(m[i], e);
+                            if (base + q < n) out[base + q] = val;
+                            if (q + 1 == cross || q + 1 == (unsigned int)kCxTile) s_prev = val;   // the running sum before the crossing / at the end of the tile
+                        }
+                        if (q == cross) s_cross = v[i];
+                    }
+                    __syncthreads();
+                    if (cross >= (unsigned int)kCxTile) { pos = kCxTile; Sr = s_prev; break; }
+                    Sr = __dadd_rn(cross > pos ? s_prev : Sr, s_cross);
+                    if (tid == 0 && base + cross < n) out[base + cross] = Sr;
+                    pos = cross + 1;
+                    __syncthreads();
+                }
+                if (tid == 0) s_run = Sr;
+                __syncthreads();
+            }
+            // (b) Whatever is left (tiles with many crossings -- importance weights spread over hundreds of binades -- and the first
+            // tile of all): exact additions in index order by one thread, staged through shared memory.  Adding +0 never changes
             // the running sum, and importance weights are mostly exact zeros (exp underflow): the zeros are compacted away by all
             // threads first (order kept), the one thread adds the non-zero elements only, and every position then reads the sum
             // after the last non-zero element at or before it.
-            const size_t base = (size_t)(chunk0 + k) * kCxTile;
-            {
-                // thread t owns elements [8 t, 8 t + 8): inclusive count of non-zero elements (warp scan + warp totals)
-                double v[kCxIpt];
-                unsigned int c = 0;
+            if (pos < (unsigned int)kCxTile) {
+                {
+                    unsigned int c = 0;   // inclusive count of the non-zero elements from `pos` on (warp scan + warp totals)
 #pragma unroll
-                for (int i = 0; i < kCxIpt; ++i) { const size_t idx = base + (size_t)tid * kCxIpt + i; v[i] = idx < n ? p[idx] : 0.; c += v[i] != 0. ? 1u : 0u; }
-                unsigned int incl = c;
-                const int lane = tid & 31, warp = tid >> 5;
+                    for (int i = 0; i < kCxIpt; ++i) { if ((unsigned int)(tid * kCxIpt + i) < pos) v[i] = 0.; c += v[i] != 0. ? 1u : 0u; }
+                    unsigned int incl = c;
+                    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
-                if (lane == 31) nz_warp[warp] = incl;
+                    for (int o = 1; o < 32; o <<= 1) { const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+                    if (lane == 31) nz_warp[warp] = incl;
+                    __syncthreads();
+                    unsigned int before = incl - c;
+                    for (int w = 0; w < warp; ++w) before += nz_warp[w];
+#pragma unroll
+                    for (int i = 0; i < kCxIpt; ++i) {
+                        if (v[i] != 0.) buf[before++] = v[i];                       // compacted, in index order
+                        nz_rank[tid * kCxIpt + i] = (unsigned short)before;       // non-zero elements at or before this position
+                    }
+                    if (tid == kCxThreads - 1) nz_total = before;
+                }
                 __syncthreads();
-                unsigned int before = incl - c;
-                for (int w = 0; w < warp; ++w) before += nz_warp[w];
+                if (tid == 0) {
+                    double Sq = s_run;
+                    const unsigned int cnt_nz = nz_total;
+                    for (unsigned int i = 0; i < cnt_nz; i += 8) {   // (loads hoisted out of the dependent chain of additions)
+                        double r[8];
 #pragma unroll
-                for (int i = 0; i < kCxIpt; ++i) {
-                    if (v[i] != 0.) buf[before++] = v[i];                       // compacted, in index order
-                    nz_rank[tid * kCxIpt + i] = (unsigned short)before;       // non-zero elements at or before this position
+                        for (int j = 0; j < 8; ++j) r[j] = i + j < cnt_nz ? buf[i + j] : 0.;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) { Sq = __dadd_rn(Sq, r[j]); r[j] = Sq; }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (i + j < cnt_nz) buf[i + j] = r[j];
+                    }
+                    s_start_tile = s_run;
+                    s_run = Sq;
                 }
-                if (tid == kCxThreads - 1) nz_total = before;
+                __syncthreads();
+                for (unsigned int i = tid; i < (unsigned int)kCxTile; i += kCxThreads)
+                    if (i >= pos && base + i < n) { const unsigned int rk = nz_rank[i]; out[base + i] = rk ? buf[rk - 1] : s_start_tile; }
             }
-            __syncthreads();
-            if (tid == 0) {
-                double S = s_run;
-                const unsigned int cnt_nz = nz_total;
-                for (unsigned int i = 0; i < cnt_nz; i += 8) {   // (loads hoisted out of the dependent chain of additions)
-                    double r[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = i + j < cnt_nz ? buf[i + j] : 0.;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { S = __dadd_rn(S, r[j]); r[j] = S; }
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) if (i + j < cnt_nz) buf[i + j] = r[j];
-                }
-                s_start_tile = s_run;
-                s_run = S;
-            }
-            __syncthreads();
-            for (int i = tid; i < kCxTile; i += kCxThreads) if (base + i < n) { const unsigned int rk = nz_rank[i]; out[base + i] = rk ? buf[rk - 1] : s_start_tile; }
             k += 1;
             __syncthreads();
             continue;

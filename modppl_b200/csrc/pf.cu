@@ -506,6 +506,19 @@ int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, 
     const unsigned int num_tiles = (unsigned int)((n + kCxTile - 1) / kCxTile);
     CxTile* tiles = nullptr;
     int* bad = nullptr;
+    {   // the tile records come from the device's stream-ordered pool; by default the pool hands its memory back to the driver at
+        // every synchronisation, and a caller that synchronises after each resample would pay a fresh cudaMalloc (~0.8 ms) per call
+        static thread_local int pool_kept_for = -1;
+        int dev = 0;
+        MPL_CUDA_OK(cudaGetDevice(&dev));
+        if (pool_kept_for != dev) {
+            cudaMemPool_t pool;
+            unsigned long long keep = ~0ull;
+            MPL_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+            MPL_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            pool_kept_for = dev;
+        }
+    }
     MPL_CUDA_OK(cudaMallocAsync(&tiles, (size_t)num_tiles * sizeof(CxTile) + 64, stream));
     bad = reinterpret_cast<int*>(reinterpret_cast<char*>(tiles) + (size_t)num_tiles * sizeof(CxTile));
     MPL_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), stream));
