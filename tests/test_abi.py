@@ -96,3 +96,41 @@ def test_model_spec_errors_are_reported():
     with pytest.raises(m.MplError) as e:
         mod.compile("f64")
     assert "undefined_name" in str(e.value)
+
+
+def _split_args(arglist):
+    arglist = arglist.strip()
+    if arglist in ("", "void"):
+        return []
+    return [a for a in arglist.split(",") if a.strip()]
+
+
+def test_rust_ffi_matches_the_header():
+    """rust/modppl-b200/src/ffi.rs (the reference-language binding; no Rust toolchain in this image) declares the header's entry
+    points with the same argument counts, only exported symbols, and the header's constants."""
+    import modppl_b200
+    header = open(os.path.join(ROOT, "include", "modppl_b200.h")).read()
+    header_nc = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = {m.group(1): len(_split_args(m.group(2))) for m in re.finditer(r"\b(mpl_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", header_nc)}
+    rust = open(os.path.join(ROOT, "rust", "modppl-b200", "src", "ffi.rs")).read()
+    rust_nc = re.sub(r"//[^\n]*", "", rust)
+    decls = {m.group(1): len(_split_args(m.group(2))) for m in re.finditer(r"pub fn (mpl_[a-z0-9_]+)\s*\(([^()]*)\)", rust_nc)}
+    assert len(decls) >= 60
+    lib = ctypes.CDLL(modppl_b200.LIB_PATH)
+    for name, n_args in decls.items():
+        assert name in protos, f"{name} declared in ffi.rs but not in the header"
+        assert protos[name] == n_args, f"{name}: {n_args} arguments in ffi.rs, {protos[name]} in the header"
+        assert hasattr(lib, name)
+    missing = [s for s in protos if s not in decls and not s.startswith("mpl_test_") and s != "mpl_fixed_resample"]
+    assert missing == [], f"header entry points without a Rust declaration: {missing}"
+    defines = dict(re.findall(r"#define\s+(MPL_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", header_nc))
+    consts = dict(re.findall(r"pub const (MPL_[A-Z0-9_]+): [a-z_0-9]+ = (-?\d+);", rust_nc))
+    assert len(consts) >= 15
+    for k, v in consts.items():
+        assert k in defines and int(defines[k]) == int(v), (k, v, defines.get(k))
+    # the two #[repr(C)] structs mirror the header's field order
+    for struct, fields in (("mpl_pf_config", ["dtype", "device", "seed", "gid_offset", "n_global"]), ("mpl_move", ["kind", "proposal", "arg", "mask", "repeat"])):
+        body_h = re.search(r"typedef struct " + struct + r"\s*\{(.*?)\}", header_nc, flags=re.S).group(1)
+        body_r = re.search(r"pub struct " + struct + r"\s*\{(.*?)\}", rust_nc, flags=re.S).group(1)
+        assert re.findall(r"(\w+)\s*;", body_h) == fields
+        assert re.findall(r"pub (\w+):", body_r) == fields
