@@ -218,8 +218,10 @@ __global__ void __launch_bounds__(256) is_kernel(Model model, uint32_t n, uint64
         Rng64 g(seed, i, batch, P_IS);
         double z[Model::L];
         w[i] = model.generate(g, z);
+        if (latents) {   // (null: the caller wants the log-ML estimate only -- the traces never leave the registers)
 #pragma unroll
-        for (int k = 0; k < Model::L; ++k) latents[(size_t)k * n + i] = z[k];
+            for (int k = 0; k < Model::L; ++k) latents[(size_t)k * n + i] = z[k];
+        }
     }
 }
 
@@ -444,12 +446,12 @@ static int importance_impl(const mpl_model* m, const double* obs, size_t n_obs, 
     cudaStream_t s = ws.stream;
     MPL_CUDA_OK(cudaMemsetAsync(ws.st, 0, sizeof(DeviceStats), s));
     rc = with_static_model(m, obs, n_obs, [&](auto model) {
-        is_kernel<<<grid, 256, 0, s>>>(model, n, seed, (uint32_t)batch, ws.lat, ws.w);
+        is_kernel<<<grid, 256, 0, s>>>(model, n, seed, (uint32_t)batch, latents ? ws.lat : nullptr, ws.w);
         return MPL_OK;
     });
     if (rc) return rc;
     weight_reduce_kernel<double><<<grid, 256, 0, s>>>(ws.w, n, ws.st, ws.part);
-    is_normalize_kernel<<<grid, 256, 0, s>>>(ws.w, n, ws.st, ws.lnw, dprobs);
+    if (lnw_out || n_ret) is_normalize_kernel<<<grid, 256, 0, s>>>(ws.w, n, ws.st, ws.lnw, dprobs);   // (log-ML only: the two scalars of the reduction suffice)
     if (n_ret) {   // importance.rs:46-48: n_ret categorical draws over exp(lnw) -- the sequential-f64 running sum, reproduced in parallel
         if ((rc = launch_cumsum_exact(nullptr, dprobs, n, ws.cum, s))) return rc;
         is_resample_search_kernel<<<(n_ret + 255) / 256, 256, 0, s>>>(ws.cum, n, n_ret, seed, (uint32_t)batch, ws.idx);

@@ -417,22 +417,39 @@ __global__ void __launch_bounds__(kExtendThreads, 4) pf_extend_kernel(ExtendArgs
 // ================================================================================================
 // K3 stand-alone weight reduction (also the parity hook mpl_logsumexp_stats)
 // ================================================================================================
+// Rounds of kReduceIpt elements per thread, held in registers: the warp's maximum first (shuffles only), then ONE exp per
+// element against it and two shuffle sums -- the running (max, sum, sum of squares) is rescaled once per round and warp, not
+// once per element and shuffle step (an fp64 exp is ~100 instructions; with one online update per element and a combine per
+// shuffle step the pass spent three of them per weight).
+constexpr int kReduceIpt = 8;
 template <typename Real>
 __global__ void __launch_bounds__(256) weight_reduce_kernel(const Real* __restrict__ lw, size_t n, DeviceStats* stats, Lse3<double>* partials) {
     typedef Real Acc;
     const int tid = threadIdx.x;
-    Lse3<Acc> run = lse3_identity<Acc>();
-    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n; i += (size_t)gridDim.x * 256) {
-        Real w = lw[i];
-        if (w == w && w > (Real)-INFINITY) {
-            if ((Acc)w <= run.m) { Acc e = exp((Acc)w - run.m); run.s += e; run.s2 += e * e; }
-            else { Acc e = exp(run.m - (Acc)w); run.s = run.s * e + 1; run.s2 = run.s2 * e * e + 1; run.m = (Acc)w; }
+    Lse3<Acc> run = lse3_identity<Acc>();   // of this warp (every lane holds the same value)
+    for (size_t base = (size_t)blockIdx.x * (256 * kReduceIpt); base < n; base += (size_t)gridDim.x * (256 * kReduceIpt)) {
+        Real w[kReduceIpt];
+        Acc m = (Acc)-INFINITY;
+#pragma unroll
+        for (int k = 0; k < kReduceIpt; ++k) {
+            const size_t i = base + (size_t)k * 256 + tid;
+            w[k] = i < n ? lw[i] : (Real)-INFINITY;
+            if (!(w[k] == w[k])) w[k] = (Real)-INFINITY;   // NaN counts as -inf (quirk Q9)
+            m = fmax(m, (Acc)w[k]);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (m == (Acc)-INFINITY) continue;   // (warp-uniform) nothing finite in this round
+        Acc s = 0, s2 = 0;
+#pragma unroll
+        for (int k = 0; k < kReduceIpt; ++k) { const Acc e = stat_exp((Acc)w[k] - m); s += e; s2 += e * e; }   // exp(-inf) = 0
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        run = lse3_combine(run, Lse3<Acc>{m, s, s2});
     }
     __shared__ Lse3<double> warp_part[8];
     __shared__ bool is_last;
-    Lse3<Acc> wr = lse3_warp_reduce(run);
-    if ((tid & 31) == 0) warp_part[tid >> 5] = Lse3<double>{(double)wr.m, (double)wr.s, (double)wr.s2};
+    if ((tid & 31) == 0) warp_part[tid >> 5] = Lse3<double>{(double)run.m, (double)run.s, (double)run.s2};
     __syncthreads();
     if (tid == 0) {
         Lse3<double> b = warp_part[0];
