@@ -134,3 +134,17 @@ def test_rust_ffi_matches_the_header():
         body_r = re.search(r"pub struct " + struct + r"\s*\{(.*?)\}", rust_nc, flags=re.S).group(1)
         assert re.findall(r"(\w+)\s*;", body_h) == fields
         assert re.findall(r"pub (\w+):", body_r) == fields
+
+
+def test_example_spec_compiles_without_a_device():
+    """examples/custom_model.py's model (the one README.md shows) goes through the spec front-end and NVRTC on the CPU"""
+    import importlib.util
+    import modppl_b200 as m
+    spec = importlib.util.spec_from_file_location("custom_model_example", os.path.join(ROOT, "examples", "custom_model.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    model = m.compile_model(ex.SPEC)
+    assert model.state_dim == 1 and model.obs_dim == 1
+    model.compile("f32")
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    assert '"params": {"phi": 0.9, "q": 0.3, "r": 0.5}' in readme      # the same parameter names (x, y, t, z, u, s are reserved)
