@@ -765,9 +765,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=4, choices=[1, 2, 3, 4, 5], help="BASELINE.json configs[config - 1]; 4 is the one the metric is quoted on")
-    ap.add_argument("--scheme", default="nested", choices=["systematic", "multinomial", "nested", "reference"],
-                    help="config 4/5 resampler: nested systematic on integer weights (default, fastest), single-level systematic, multinomial on integer "
-                         "weights, or the reference's own multinomial (bit-exact parity path)")
+    ap.add_argument("--scheme", default=None, choices=["systematic", "multinomial", "nested", "reference"],
+                    help="config 4/5 resampler: nested systematic on integer weights (config 4's default: fastest when every step resamples), single-level "
+                         "systematic (config 5's default: fastest when the ESS trigger fires on one step in ten), multinomial on integer weights, or the "
+                         "reference's own multinomial (bit-exact parity path)")
     ap.add_argument("--log2-particles", type=int, default=LOG2_PARTICLES)
     ap.add_argument("--variant", default="global", choices=["global", "island"],
                     help="several GPUs, config 4: global resampling over all shards (default; the same ancestors as on one GPU) or one island per GPU "
@@ -776,6 +777,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.scheme is None:
+        args.scheme = "systematic" if args.config == 5 else "nested"
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
