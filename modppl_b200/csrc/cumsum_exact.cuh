@@ -176,7 +176,7 @@ static __global__ void __launch_bounds__(kCxThreads) cx_pairs_kernel(const doubl
 // ---- pass 4: the sequential walk over tiles (one block) ----------------------------------------------------------------------
 constexpr int kCxMaxRounds = 4;      // binade crossings handled by block scans inside one irregular tile before the element-by-element path takes over
 constexpr int kCxWalkChunk = kCxThreads;   // tile records staged in shared memory per round: one per thread
-static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double* __restrict__ p, size_t n, CxTile* tiles, unsigned int num_tiles, double* __restrict__ out) {
+static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double* __restrict__ p, size_t n, CxTile* tiles, unsigned int num_tiles, double* __restrict__ out, const int* bad) {
     __shared__ double buf[kCxTile];
     __shared__ unsigned long long c_even[kCxWalkChunk], c_odd[kCxWalkChunk];
     __shared__ double c_start[kCxWalkChunk];
@@ -188,6 +188,7 @@ static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double
     __shared__ CxPair run_warp[kCxThreads / 32];
     __shared__ unsigned short nz_rank[kCxTile];
     const int tid = threadIdx.x;
+    const bool clean = *bad == 0;   // negative / NaN / infinite inputs: no integer recurrence, every tile is added element by element
     if (tid == 0) s_run = 0.;
     for (unsigned int chunk0 = 0; chunk0 < num_tiles; chunk0 += kCxWalkChunk) {
         const unsigned int cnt = min((unsigned int)kCxWalkChunk, num_tiles - chunk0);
@@ -254,7 +255,7 @@ static __global__ void __launch_bounds__(kCxThreads) cx_walk_kernel(const double
             // from `pos` on, finds the first addition that leaves the binade, writes everything before it, performs that one
             // addition in fp64 -- exactly what the sequential loop does there -- and goes on from the element after it.
             unsigned int pos = 0;
-            if (S > 0. && c_sum[k] < 3. * S) {
+            if (clean && S > 0. && c_sum[k] < 3. * S) {
                 double Sr = S;
                 for (int round = 0; round < kCxMaxRounds && pos < (unsigned int)kCxTile; ++round) {
                     const int e = cx_grid_exp(Sr);

@@ -525,7 +525,7 @@ int launch_cumsum_exact(mpl_ps* ps, const double* probs, size_t n, double* out, 
     cx_tilesum_kernel<<<num_tiles, kCxThreads, 0, stream>>>(probs, n, tiles, bad);
     cx_classify_kernel<<<1, 1024, 0, stream>>>(tiles, num_tiles, bad);
     cx_pairs_kernel<<<num_tiles, kCxThreads, 0, stream>>>(probs, n, tiles);
-    cx_walk_kernel<<<1, kCxThreads, 0, stream>>>(probs, n, tiles, num_tiles, out);
+    cx_walk_kernel<<<1, kCxThreads, 0, stream>>>(probs, n, tiles, num_tiles, out, bad);
     cx_fill_kernel<<<num_tiles, kCxThreads, 0, stream>>>(probs, n, tiles, out);
     if (ps) ps->launch_count += 5;
     MPL_CUDA_OK(cudaGetLastError());

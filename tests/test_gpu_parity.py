@@ -429,6 +429,14 @@ def test_parallel_cumsum_bad_inputs_fall_back_to_sequential_semantics():
     p[5000] = np.nan
     got, ref = m.parity.cumsum_sequential(p), np.cumsum(p)
     assert np.array_equal(got[:5000], ref[:5000]) and np.all(np.isnan(got[5000:]))
+    # a negative element far from the start, in a tile whose sum is small against the running sum (where clean inputs take the
+    # block-scan path between binade crossings)
+    p = rng.random(1 << 16)
+    p /= p.sum()
+    for at in (12345, 40000, 65535):
+        q = p.copy()
+        q[at] = -q[at]
+        assert np.array_equal(m.parity.cumsum_sequential(q), np.cumsum(q)), at
 
 
 # ------------------------------------------------------------------------------------------------- ESS-triggered device loop (config 5)
